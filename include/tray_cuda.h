@@ -1,0 +1,227 @@
+/*
+ * tray_cuda.h — C ABI of the B200-native CWBVH closest-hit traversal backend for tray_racing.
+ *
+ * This is the drop-in boundary.  Every entry point is what a Rust `tray_cuda`
+ * crate would bind with `extern "C"`; the slot it fills is the reference's software-GPU entry point
+ *
+ *     rt_gpu_software::start(event_loop, options, scene, bvh_bytes, instance_bytes, tri_bytes,
+ *                            tlas_start) -> f32                  (src/rt_gpu/rt_gpu_software.rs:24-32)
+ *
+ * called from `cwbvh_gpu_runner` (src/rt_gpu/mod.rs:92-100,108-110), and — at ray-batch grain — the
+ * CPU operator `Traversable::traverse(&self, ray: Ray) -> RayHit` (traversable/src/lib.rs:13-28,
+ * src/cwbvh.rs:144-182).
+ *
+ * Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success and a
+ * negative tray_status on failure; `tray_cuda_last_error()` returns a thread-local message.
+ * Host buffers are borrowed for the duration of a call.  A `tray_scene` owns all device memory of
+ * ONE device (the BVH is replicated: one scene per GPU, rays sharded by image tile).
+ * Not re-entrant per scene; distinct scenes may be driven from distinct host threads.
+ */
+#ifndef TRAY_CUDA_H
+#define TRAY_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRAY_CUDA_ABI_VERSION 1u
+
+/* ---- status codes -------------------------------------------------------------------------- */
+typedef enum tray_status {
+    TRAY_OK = 0,
+    TRAY_ERR_ARG = -1,      /* bad pointer / size / stride / alignment                          */
+    TRAY_ERR_CUDA = -2,     /* a CUDA runtime call failed (message has the cudaError string)     */
+    TRAY_ERR_NO_DEVICE = -3,/* no CUDA device: there is NO CPU fallback by design                */
+    TRAY_ERR_OVERFLOW = -4  /* traversal stack overflow was detected (BVH deeper than supported) */
+} tray_status;
+
+/* ---- POD records (layouts pinned by static asserts in the implementation) --------------------
+ *
+ * CWBVH node: obvhs `CwBvhNode`, #[repr(C)], 80 bytes, viewed as uint4[5] by the reference shader
+ * (src/rt_gpu/rt_gpu_software_query.hlsl:40-43,219-264; encoder embree/src/bvh_embree_to_cwbvh.rs:172-185;
+ * stride asserted at src/rt_gpu/mod.rs:70,105).  Passed as raw bytes, index 0 = root.            */
+typedef struct tray_cwbvh_node {
+    float    p[3];               /*  0: quantisation origin = node AABB min                      */
+    uint8_t  e[3];               /* 12: biased f32 exponent per axis, scale = asfloat(e << 23)   */
+    uint8_t  imask;              /* 15: bit i set <=> child slot i is an inner node              */
+    uint32_t child_base_idx;     /* 16: index of first inner child (contiguous, slot order)      */
+    uint32_t primitive_base_idx; /* 20: index of first triangle of this node                     */
+    uint8_t  child_meta[8];      /* 24 */
+    uint8_t  child_min_x[8];     /* 32 */
+    uint8_t  child_max_x[8];     /* 40 */
+    uint8_t  child_min_y[8];     /* 48 */
+    uint8_t  child_max_y[8];     /* 56 */
+    uint8_t  child_min_z[8];     /* 64 */
+    uint8_t  child_max_z[8];     /* 72 */
+} tray_cwbvh_node;               /* 80 bytes                                                      */
+
+/* Triangle record, BVH order (tris[primitive_indices[i]], src/rt_cpu/mod.rs:38-43).
+ * f32 like the CPU path's obvhs `RtTriangle` {v0, e1 = v0 - v1, e2 = v2 - v0, ng = cross(e1, e2)}
+ *  — NOT the f16 `RtCompressedTriangle` of the wgpu path, which cannot meet
+ * the 1e-5 parity bar.  Two strides are accepted:
+ *   48: {v0.xyz, pad, e1.xyz, pad, e2.xyz, pad}           (ng recomputed in-register, bit-identical)
+ *   64: {v0, e1, e2, ng} each padded to 16 B              (byte image of [RtTriangle])           */
+typedef struct tray_tri48 {
+    float v0[3], pad0;
+    float e1[3], pad1;
+    float e2[3], pad2;
+} tray_tri48;
+
+typedef struct tray_tri64 {
+    float v0[3], pad0;
+    float e1[3], pad1;
+    float e2[3], pad2;
+    float ng[3], pad3;
+} tray_tri64;
+
+/* Ray = obvhs `Ray::new(origin, direction, tmin, tmax)` (src/rt_cpu/rt_cpu.rs:50-55).  32 bytes. */
+typedef struct tray_ray {
+    float origin[3];
+    float tmin;
+    float dir[3];
+    float tmax;
+} tray_ray;
+
+/* Hit = the (t, primitive_id) pair of obvhs `RayHit` (embree/src/embree_managed.rs:52-57).
+ * Miss: t = +inf, prim = 0xFFFFFFFF (RayHit::none()).  `prim` indexes the BVH-ordered triangle
+ * array; in TLAS mode it is the GLOBAL triangle index (src/rt_gpu/mod.rs:45-47).                 */
+typedef struct tray_hit {
+    float    t;
+    uint32_t prim;
+} tray_hit;
+
+#define TRAY_INVALID_PRIM 0xFFFFFFFFu
+
+/* `ViewUniform` (src/main.rs:589-617): column-major glam Mat4s, #[repr(C)], padded to 160 bytes. */
+typedef struct tray_view {
+    float    view_inv[16];
+    float    proj_inv[16];
+    float    eye[3];
+    float    exposure;
+    uint32_t tlas_start;
+    uint32_t pad[3];
+} tray_view;
+
+/* Per-launch work counters (the reference's PROFILE_RT counters,
+ * src/rt_gpu/rt_gpu_software_query.hlsl:377-379,407-409: aabb_hit_count/8 and tri_hit_count).     */
+typedef struct tray_counters {
+    uint64_t rays;       /* rays traced                                       */
+    uint64_t nodes;      /* CWBVH nodes fetched (80 B each)                   */
+    uint64_t tris;       /* triangle records tested                           */
+    uint64_t instances;  /* blas_offsets lookups (TLAS mode)                  */
+    uint64_t hits;       /* rays that ended with a hit                        */
+} tray_counters;
+
+typedef struct tray_scene_info {
+    uint64_t n_nodes, n_tris;
+    uint32_t tri_stride, n_instances, tlas_start, is_tlas;
+    int32_t  device;
+    uint32_t sm_count;
+    uint64_t device_bytes;          /* bytes of device memory owned by the scene                  */
+    uint64_t l2_bytes;              /* cudaDevAttrL2CacheSize                                     */
+    uint64_t l2_persist_bytes;      /* persisting-L2 window actually applied to the node array    */
+} tray_scene_info;
+
+/* render flags */
+#define TRAY_RENDER_BOUNCE     0x1u /* trace the 1-spp cosine "AO" bounce ray per hit pixel (rt_cpu.rs:61-88) */
+#define TRAY_RENDER_RGBA       0x2u /* write pow(col,2.2)*255 RGBA8 (rt_cpu.rs:102-107)                       */
+#define TRAY_RENDER_COUNTERS   0x4u /* run the counting build of the kernels (slower; fills tray_counters)    */
+
+typedef struct tray_scene tray_scene;
+
+/* ---- device / lifetime ---------------------------------------------------------------------- */
+
+/* Number of CUDA devices visible; 0 (not an error) when there is none. */
+int tray_cuda_device_count(void);
+
+unsigned tray_cuda_abi_version(void);
+
+/* Upload a CWBVH to `device`.  Mirrors the one-time storage-buffer upload of
+ * rt_gpu_software.rs:177-180 with the argument meaning of `start()` (rt_gpu_software.rs:24-32):
+ *   nodes/n_nodes   bvh_bytes as 80-byte nodes: flat BVH with root at 0, or BLAS0|BLAS1|..|TLAS with
+ *                   the TLAS root at index `tlas_start` (src/rt_gpu/mod.rs:62-69,88-91,99)
+ *   tris/n_tris     tri_bytes, BVH-ordered, stride 48 or 64 (see above)
+ *   blas_offsets    instance_bytes as u32: node offset of the BLAS behind TLAS leaf k
+ *                   (src/rt_gpu/mod.rs:72-78); NULL / n_instances = 0 selects single-level traversal
+ *   tlas_start      node index of the TLAS root; ignored when n_instances == 0                     */
+int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes,
+                           const void* tris, uint64_t n_tris, uint32_t tri_stride,
+                           const uint32_t* blas_offsets, uint32_t n_instances, uint32_t tlas_start,
+                           int device, tray_scene** out_scene);
+
+void tray_cuda_scene_destroy(tray_scene* scene);
+
+int tray_cuda_scene_info(const tray_scene* scene, tray_scene_info* out_info);
+
+/* ---- ray-batch operator: Traversable::traverse at batch grain (traversable/src/lib.rs:20) ----- */
+
+/* Closest hit for `n` rays.  HOST buffers: the copy H2D of rays and D2H of hits are inside the
+ * call (and inside *ms_total); *ms_kernel is the CUDA-event time of the traversal kernel alone.
+ * Either timing pointer may be NULL.                                                             */
+int tray_cuda_trace(tray_scene* scene, const tray_ray* rays, uint64_t n, tray_hit* hits,
+                    float* ms_kernel, float* ms_total);
+
+/* Same with DEVICE pointers (rays and hits already resident in HBM); launches on `stream`
+ * (a cudaStream_t passed as void*, NULL = the scene's own stream) and does NOT synchronise unless
+ * ms_kernel != NULL.                                                                             */
+int tray_cuda_trace_device(tray_scene* scene, const tray_ray* d_rays, uint64_t n, tray_hit* d_hits,
+                           void* stream, float* ms_kernel);
+
+/* ---- frame operator: the render loop body (src/rt_cpu/rt_cpu.rs:35-91, rt_gpu_software.hlsl:47-144) */
+
+/* Render the pixels of one frame that belong to shard `shard_index` of `shard_count`
+ * (interleaved 32x8-pixel tiles: tile k belongs to shard k % shard_count; 0/1 = whole frame).
+ * Rays are generated on the device from `view` (rt_cpu.rs:38-55); bounce rays per rt_cpu.rs:61-80.
+ * Results stay on the device (fetch them with tray_cuda_frame_download); returns after the
+ * kernels have been enqueued on the scene stream unless a timing pointer is non-NULL.
+ *   ms_primary / ms_bounce   CUDA-event time of the primary / bounce traversal kernel (NULL ok)   */
+int tray_cuda_render(tray_scene* scene, const tray_view* view, uint32_t width, uint32_t height,
+                     uint32_t frame_count, uint32_t flags, uint32_t shard_index, uint32_t shard_count,
+                     float* ms_primary, float* ms_bounce);
+
+/* Number of pixels (= primary rays) shard `shard_index` owns for a width x height frame. */
+uint64_t tray_cuda_shard_pixels(uint32_t width, uint32_t height, uint32_t shard_index, uint32_t shard_count);
+
+/* Copy the last rendered frame to HOST buffers, each width*height entries in row-major pixel order
+ * (pixels of other shards are left untouched).  Any pointer may be NULL.  `bounce_rays` receives the
+ * generated bounce rays (tmax = 0 where the primary ray missed) so a checker can trace the very
+ * same rays.                                                                                      */
+int tray_cuda_frame_download(tray_scene* scene, tray_hit* primary, tray_hit* bounce,
+                             tray_ray* bounce_rays, uint8_t* rgba);
+
+/* Device pointers of the last frame's buffers, for a caller that gathers them itself (NCCL / peer
+ * copy).  Layout: row-major full-frame arrays, see tray_cuda_frame_download.                        */
+int tray_cuda_frame_device_ptrs(tray_scene* scene, void** d_primary, void** d_bounce, void** d_rgba);
+
+/* Wait for everything enqueued on the scene stream. */
+int tray_cuda_sync(tray_scene* scene);
+
+/* Counters of the last tray_cuda_render / tray_cuda_trace call made with counting enabled
+ * (TRAY_RENDER_COUNTERS, or tray_cuda_set_counting).                                             */
+int tray_cuda_counters(tray_scene* scene, tray_counters* primary, tray_counters* bounce);
+int tray_cuda_set_counting(tray_scene* scene, int enabled);
+
+/* ---- the slot itself ------------------------------------------------------------------------- */
+
+/* Drop-in for rt_gpu_software::start (rt_gpu_software.rs:24-32): upload, then render frames for
+ * `render_time_s` seconds with the reference's timing protocol (one untimed warm-up frame before
+ * each timed frame when `benchmark` != 0, rt_gpu_software.rs:289-301), and return in *out_min_ms the
+ * MIN frame time in ms (rt_gpu_software.rs:339,376) and in *out_mean_ms the mean (rt_cpu.rs:113).
+ * `animate` advances frame_count per frame (rt_cpu.rs:95-97).                                     */
+int tray_cuda_start(const void* bvh_bytes, uint64_t bvh_len,
+                    const void* instance_bytes, uint64_t instance_len,
+                    const void* tri_bytes, uint64_t tri_len, uint32_t tri_stride,
+                    uint32_t tlas_start, int use_tlas,
+                    const tray_view* view, uint32_t width, uint32_t height,
+                    float render_time_s, int benchmark, int animate, int device,
+                    float* out_min_ms, float* out_mean_ms, uint32_t* out_frames);
+
+const char* tray_cuda_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRAY_CUDA_H */
