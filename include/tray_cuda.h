@@ -129,6 +129,7 @@ typedef struct tray_scene_info {
 #define TRAY_RENDER_BOUNCE     0x1u /* trace the 1-spp cosine "AO" bounce ray per hit pixel (rt_cpu.rs:61-88) */
 #define TRAY_RENDER_RGBA       0x2u /* write pow(col,2.2)*255 RGBA8 (rt_cpu.rs:102-107)                       */
 #define TRAY_RENDER_COUNTERS   0x4u /* run the counting build of the kernels (slower; fills tray_counters)    */
+#define TRAY_RENDER_KEEP_RAYS  0x8u /* also store the generated bounce rays (for checkers)                    */
 
 typedef struct tray_scene tray_scene;
 

@@ -1,0 +1,464 @@
+// traverse.cuh — sm_100a device code: 8-wide CWBVH closest-hit traversal + ray/triangle intersection.
+//
+// One kernel template serves the three ray sources of the path:
+//   SRC_BUFFER   rays read from a buffer            — Traversable::traverse at batch grain (traversable/src/lib.rs:20)
+//   SRC_PRIMARY  rays generated from the camera     — src/rt_cpu/rt_cpu.rs:38-55, rt_gpu_software.hlsl:69-80
+//   SRC_BOUNCE   1-spp cosine bounce from a hit     — src/rt_cpu/rt_cpu.rs:61-80, rt_gpu_software.hlsl:105-128
+//
+// Execution model (B200: 148 SMs, 4 schedulers each; no tensor cores — this is pointer chasing + FP32/ALU):
+//   * persistent warps: the grid is sized to the resident-CTA capacity of the chip; idle lanes pull new rays
+//     through one warp-aggregated atomicAdd on a global cursor (ray replacement keeps warps full on incoherent rays)
+//   * each lane runs the reference's per-ray state machine UNCHANGED (same node order, same triangle order, same
+//     shrinking tmax), so (prim, t) is bit-identical to the oracle by construction; only the WARP-level schedule
+//     is new: every iteration the warp votes (__ballot_sync/__popc) whether to run a node step or a triangle
+//     step, and only lanes whose next action is of that kind take part — no per-lane while-while divergence
+//   * 80-byte nodes are fetched as 5 x 16-byte ld.global.nc; 48/64-byte triangles as 3 x 16-byte
+//   * the traversal stack lives in shared memory, [entry][thread] so that a warp's accesses are conflict-free;
+//     entries past STACK_SMEM spill to a per-thread local array (checked; overflow raises a flag)
+//   * all parity-relevant float math uses round-to-nearest intrinsics without FMA contraction, because the
+//     reference CPU path (Rust/glam) never fuses (SURVEY.md §7 "bit-level float parity").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "tray_cuda.h"
+
+namespace tray {
+
+constexpr int BLOCK_THREADS = 128;
+constexpr int STACK_SMEM = 12;     // entries per thread in shared memory
+constexpr int STACK_SPILL = 36;    // further entries per thread in local memory (total 48 > obvhs' 32, cwbvh.rs:88)
+constexpr unsigned FULL = 0xffffffffu;
+constexpr uint32_t INVALID = 0xffffffffu;
+constexpr float F32_MAX_ = 3.402823466e+38f;
+constexpr float F32_EPS_ = 1.1920929e-7f;     // sampling.hlsl:3
+constexpr float BOX_EPS_ = 0.0001f;           // query.hlsl:274
+
+enum RaySource { SRC_BUFFER = 0, SRC_PRIMARY = 1, SRC_BOUNCE = 2 };
+
+struct TraceParams {
+    const uint4* __restrict__ nodes;          // 5 x uint4 per node
+    const uint4* __restrict__ tris;           // 3 or 4 x uint4 per triangle
+    const uint32_t* __restrict__ blas_offsets;
+    uint32_t tlas_start;
+    uint32_t flags;
+    // SRC_BUFFER
+    const tray_ray* __restrict__ rays_in;
+    unsigned long long n_work;                // work items: rays, or padded local pixels
+    // SRC_PRIMARY / SRC_BOUNCE
+    tray_view view;
+    uint32_t width, height, frame_count;
+    uint32_t shard_index, shard_count, tiles_x;   // tiles_x = ceil(width / 32)
+    const tray_hit* __restrict__ primary_in;      // SRC_BOUNCE: primary hits, local order
+    // outputs (local order)
+    tray_hit* __restrict__ hits_out;
+    tray_ray* __restrict__ rays_out;              // optional: the generated bounce rays
+    uchar4* __restrict__ rgba_out;                // optional
+    unsigned long long* __restrict__ cursor;      // work cursor
+    unsigned long long* __restrict__ counters;    // rays, nodes, tris, instances, hits (COUNT builds)
+    uint32_t* __restrict__ overflow;
+    uint32_t refill_min;                          // idle lanes needed before a partial warp refills
+    uint32_t tri_weight;                          // vote: triangle phase when n_tri * tri_weight >= n_node
+};
+
+// ---- exact float helpers (no contraction, IEEE rounding) --------------------------------------
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float dot3(float ax, float ay, float az, float bx, float by, float bz) {
+    return add(add(mul(ax, bx), mul(ay, by)), mul(az, bz));       // glam: (x*x' + y*y') + z*z'
+}
+__device__ __forceinline__ void cross3(float ax, float ay, float az, float bx, float by, float bz,
+                                       float& ox, float& oy, float& oz) {
+    ox = sub(mul(ay, bz), mul(az, by));
+    oy = sub(mul(az, bx), mul(ax, bz));
+    oz = sub(mul(ax, by), mul(ay, bx));
+}
+__device__ __forceinline__ void normalize3(float& x, float& y, float& z) {   // glam Vec3A: v / sqrt(dot)
+    float len = __fsqrt_rn(dot3(x, y, z, x, y, z));
+    x = __fdiv_rn(x, len); y = __fdiv_rn(y, len); z = __fdiv_rn(z, len);
+}
+// byte J of w as an exact float: PRMT builds 0x4B0000bb = 2^23 + byte, FADD removes 2^23 (no I2F: the
+// conversion pipe is quarter-rate).
+template <int J> __device__ __forceinline__ float byte_f32(uint32_t w) {
+    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + J)), 8388608.0f);
+}
+
+// ---- per-ray constants ---------------------------------------------------------------------------
+struct RayConst {
+    float ox, oy, oz, dx, dy, dz, ix, iy, iz, tmin;
+    uint32_t oct_inv4;
+};
+
+__device__ __forceinline__ void prepare_ray(RayConst& r, float ox, float oy, float oz, float dx, float dy, float dz, float tmin) {
+    r.ox = ox; r.oy = oy; r.oz = oz; r.tmin = tmin;
+    r.dx = dx == 0.0f ? F32_EPS_ : dx;           // query.hlsl:334
+    r.dy = dy == 0.0f ? F32_EPS_ : dy;
+    r.dz = dz == 0.0f ? F32_EPS_ : dz;
+    r.ix = __fdiv_rn(1.0f, r.dx); r.iy = __fdiv_rn(1.0f, r.dy); r.iz = __fdiv_rn(1.0f, r.dz);   // Ray::inv_direction
+    r.oct_inv4 = (r.dx < 0.0f ? 0u : 0x04040404u) | (r.dy < 0.0f ? 0u : 0x02020202u) |
+                 (r.dz < 0.0f ? 0u : 0x01010101u);                                              // query.hlsl:314-326
+}
+
+// ---- node test: CwBvhNode::intersect_ray, twin query.hlsl:213-303 -------------------------------
+template <int J>
+__device__ __forceinline__ uint32_t child_test(uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz,
+                                               float ax, float ay, float az, float bx, float by, float bz, float tmax,
+                                               uint32_t child_bits4, uint32_t bit_index4) {
+    // tmin3 = q_near * adj_inv + adj_org, tmax3 = q_far * adj_inv + adj_org: mul, then add (query.hlsl:285-286)
+    const float tnx = add(mul(byte_f32<J>(nx), ax), bx), tfx = add(mul(byte_f32<J>(fx), ax), bx);
+    const float tny = add(mul(byte_f32<J>(ny), ay), by), tfy = add(mul(byte_f32<J>(fy), ay), by);
+    const float tnz = add(mul(byte_f32<J>(nz), az), bz), tfz = add(mul(byte_f32<J>(fz), az), bz);
+    const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), BOX_EPS_);      // query.hlsl:288
+    const float tfar = fminf(fminf(fminf(tfx, tfy), tfz), tmax);          // query.hlsl:289
+    const uint32_t child_bits = (child_bits4 >> (8 * J)) & 0xffu;
+    const uint32_t bit_index = (bit_index4 >> (8 * J)) & 0xffu;
+    return tmin <= tfar ? (child_bits << bit_index) : 0u;                 // query.hlsl:291-298
+}
+
+__device__ __forceinline__ uint32_t node_test(const RayConst& r, float tmax, const uint4& n0, const uint4& n1,
+                                              const uint4& n2, const uint4& n3, const uint4& n4) {
+    const uint32_t e = n0.w;
+    // adj_inv = 2^(e-127) * inv_dir ; adj_org = (p - origin) * inv_dir  (CPU path: cached reciprocal; SURVEY §8c vi)
+    const float ax = mul(__uint_as_float((e & 0xffu) << 23), r.ix);
+    const float ay = mul(__uint_as_float(((e >> 8) & 0xffu) << 23), r.iy);
+    const float az = mul(__uint_as_float(((e >> 16) & 0xffu) << 23), r.iz);
+    const float bx = mul(sub(__uint_as_float(n0.x), r.ox), r.ix);
+    const float by = mul(sub(__uint_as_float(n0.y), r.oy), r.iy);
+    const float bz = mul(sub(__uint_as_float(n0.z), r.oz), r.iz);
+    const bool sx = r.dx < 0.0f, sy = r.dy < 0.0f, sz = r.dz < 0.0f;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const uint32_t meta4 = i == 0 ? n1.z : n1.w;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;          // query.hlsl:251
+        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
+        const uint32_t bit_index4 = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t lox = i == 0 ? n2.x : n2.y, hix = i == 0 ? n2.z : n2.w;
+        const uint32_t loy = i == 0 ? n3.x : n3.y, hiy = i == 0 ? n3.z : n3.w;
+        const uint32_t loz = i == 0 ? n4.x : n4.y, hiz = i == 0 ? n4.z : n4.w;
+        const uint32_t nx = sx ? hix : lox, fx = sx ? lox : hix;                   // query.hlsl:266-273
+        const uint32_t ny = sy ? hiy : loy, fy = sy ? loy : hiy;
+        const uint32_t nz = sz ? hiz : loz, fz = sz ? loz : hiz;
+        mask |= child_test<0>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4);
+        mask |= child_test<1>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4);
+        mask |= child_test<2>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4);
+        mask |= child_test<3>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4);
+    }
+    return mask;
+}
+
+// ---- triangle test: RtTriangle::intersect, twin query.hlsl:89-129; returns t or +inf -------------
+template <int TRI_STRIDE>
+__device__ __forceinline__ float tri_test(const RayConst& r, float tmax, const uint4* __restrict__ tris, uint32_t prim) {
+    const uint4* rec = tris + (size_t)prim * (TRI_STRIDE / 16);
+    const uint4 a = __ldg(rec), b = __ldg(rec + 1), c4 = __ldg(rec + 2);
+    const float v0x = __uint_as_float(a.x), v0y = __uint_as_float(a.y), v0z = __uint_as_float(a.z);
+    const float e1x = __uint_as_float(b.x), e1y = __uint_as_float(b.y), e1z = __uint_as_float(b.z);
+    const float e2x = __uint_as_float(c4.x), e2y = __uint_as_float(c4.y), e2z = __uint_as_float(c4.z);
+    float ngx, ngy, ngz;
+    if (TRI_STRIDE == 64) {
+        const uint4 g = __ldg(rec + 3);
+        ngx = __uint_as_float(g.x); ngy = __uint_as_float(g.y); ngz = __uint_as_float(g.z);
+    } else {
+        cross3(e1x, e1y, e1z, e2x, e2y, e2z, ngx, ngy, ngz);                       // :93
+    }
+    const float cx = sub(v0x, r.ox), cy = sub(v0y, r.oy), cz = sub(v0z, r.oz);     // :96
+    float rx, ry, rz; cross3(r.dx, r.dy, r.dz, cx, cy, cz, rx, ry, rz);            // :97
+    const float inv_det = __fdiv_rn(1.0f, dot3(ngx, ngy, ngz, r.dx, r.dy, r.dz));  // :98
+    const float u = mul(dot3(rx, ry, rz, e2x, e2y, e2z), inv_det);                 // :100
+    const float v = mul(dot3(rx, ry, rz, e1x, e1y, e1z), inv_det);                 // :101
+    const float w = sub(sub(1.0f, u), v);                                          // :102
+    const uint32_t hit = __float_as_uint(u) | __float_as_uint(v) | __float_as_uint(w);   // :112
+    float t = __int_as_float(0x7f800000);
+    if (inv_det != 0.0f && (hit & 0x80000000u) == 0u) {                            // :116
+        const float tt = mul(dot3(ngx, ngy, ngz, cx, cy, cz), inv_det);            // :118
+        if (tt >= r.tmin && tt <= tmax) t = tt;                                    // :119
+    }
+    return t;
+}
+
+// ---- work item -> pixel ------------------------------------------------------------------------
+// Local work item j of shard s: 256 consecutive items form one 32x8-pixel tile (tile k = s + (j/256)*S in
+// row-major tile order), 32 consecutive items form one 8x4 sub-tile — the footprint of one warp fetch.
+__device__ __forceinline__ bool item_to_pixel(const TraceParams& P, unsigned long long j, uint32_t& px, uint32_t& py) {
+    const uint32_t local_tile = (uint32_t)(j >> 8), w = (uint32_t)j & 255u;
+    const uint32_t k = P.shard_index + local_tile * P.shard_count;
+    const uint32_t sub = w >> 5, l = w & 31u;
+    px = (k % P.tiles_x) * 32u + (sub & 3u) * 8u + (l & 7u);
+    py = (k / P.tiles_x) * 8u + (sub >> 2) * 4u + (l >> 3);
+    return px < P.width && py < P.height;
+}
+
+// glam Mat4 * Vec4 (column-major): ((c0*x + c1*y) + c2*z) + c3*w
+__device__ __forceinline__ void mat4_mul(const float* m, float x, float y, float z, float w, float o[4]) {
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = add(add(add(mul(m[k], x), mul(m[4 + k], y)), mul(m[8 + k], z)), mul(m[12 + k], w));
+}
+
+// pixel -> primary ray direction (src/rt_cpu/rt_cpu.rs:38-55)
+__device__ __forceinline__ void primary_dir(const TraceParams& P, uint32_t px, uint32_t py, float& dx, float& dy, float& dz) {
+    const float uvx = __fdiv_rn((float)px, (float)P.width);
+    const float uvy = sub(1.0f, __fdiv_rn((float)py, (float)P.height));
+    const float ndcx = sub(mul(uvx, 2.0f), 1.0f), ndcy = sub(mul(uvy, 2.0f), 1.0f);
+    float vs[4]; mat4_mul(P.view.proj_inv, ndcx, ndcy, 1.0f, 1.0f, vs);
+    const float ww = vs[3];
+    vs[0] = __fdiv_rn(vs[0], ww); vs[1] = __fdiv_rn(vs[1], ww); vs[2] = __fdiv_rn(vs[2], ww); vs[3] = __fdiv_rn(vs[3], ww);
+    float wp[4]; mat4_mul(P.view.view_inv, vs[0], vs[1], vs[2], vs[3], wp);
+    dx = sub(wp[0], P.view.eye[0]); dy = sub(wp[1], P.view.eye[1]); dz = sub(wp[2], P.view.eye[2]);
+    normalize3(dx, dy, dz);
+}
+
+// sampling.hlsl:5-27
+__device__ __forceinline__ uint32_t uhash(uint32_t a, uint32_t b) {
+    uint32_t x = (a * 1597334673u) ^ (b * 3812015801u);
+    x = x ^ (x >> 16); x *= 0x7feb352du;
+    x = x ^ (x >> 15); x *= 0x846ca68bu;
+    x = x ^ (x >> 16);
+    return x;
+}
+__device__ __forceinline__ float hash_noise(uint32_t x, uint32_t y, uint32_t frame) {
+    return mul(__uint2float_rn(uhash(x, (y << 11) + frame)), 2.3283064365386963e-10f);   // 1 / float(0xffffffff) = 2^-32
+}
+// sin/cos(2*pi*u): fixed quadrant reduction + fmaf Horner, bit-reproducible on any IEEE machine (the platform
+// sin/cos the reference calls, sampling.hlsl:30-36, is not; the bounce direction is an input distribution).
+__device__ __forceinline__ void sincos_tau(float u, float& s, float& c) {
+    const float q4 = mul(u, 4.0f), qf = rintf(q4), r = sub(q4, qf);
+    const float x = mul(r, 1.57079632679489661923f), x2 = mul(x, x);
+    float sp = __fmaf_rn(x2, -1.9515295891e-4f, 8.3321608736e-3f);
+    sp = __fmaf_rn(sp, x2, -1.6666654611e-1f);
+    const float sn = __fmaf_rn(mul(x, x2), sp, x);
+    float cp = __fmaf_rn(x2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+    cp = __fmaf_rn(cp, x2, 4.166664568298827e-2f);
+    const float cs = __fmaf_rn(mul(x2, x2), cp, __fmaf_rn(x2, -0.5f, 1.0f));
+    const int q = (int)qf & 3;
+    s = q == 0 ? sn : q == 1 ? cs : q == 2 ? -sn : -cs;
+    c = q == 0 ? cs : q == 1 ? -sn : q == 2 ? -cs : sn;
+}
+
+// bounce ray from a primary hit (src/rt_cpu/rt_cpu.rs:61-76; basis sampling.hlsl:39-51)
+template <int TRI_STRIDE>
+__device__ __forceinline__ void bounce_ray(const TraceParams& P, uint32_t px, uint32_t py, float pdx, float pdy, float pdz,
+                                           float t, uint32_t prim, float& ox, float& oy, float& oz, float& dx, float& dy, float& dz) {
+    const uint4* rec = P.tris + (size_t)prim * (TRI_STRIDE / 16);
+    float nx, ny, nz;
+    if (TRI_STRIDE == 64) {
+        const uint4 g = __ldg(rec + 3);
+        nx = __uint_as_float(g.x); ny = __uint_as_float(g.y); nz = __uint_as_float(g.z);
+    } else {
+        const uint4 b = __ldg(rec + 1), c = __ldg(rec + 2);
+        cross3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z),
+               __uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z), nx, ny, nz);
+    }
+    normalize3(nx, ny, nz);                                                    // RtTriangle::compute_normal
+    const float sgn = copysignf(1.0f, dot3(nx, ny, nz, -pdx, -pdy, -pdz));     // f32::signum (rt_cpu.rs:65)
+    nx = mul(nx, sgn); ny = mul(ny, sgn); nz = mul(nz, sgn);
+    ox = sub(add(P.view.eye[0], mul(pdx, t)), mul(pdx, 0.01f));                // rt_cpu.rs:67
+    oy = sub(add(P.view.eye[1], mul(pdy, t)), mul(pdy, 0.01f));
+    oz = sub(add(P.view.eye[2], mul(pdz, t)), mul(pdz, 0.01f));
+    const float u0 = hash_noise(px, py, P.frame_count), u1 = hash_noise(px, py, P.frame_count + 1024u);   // rt_cpu.rs:70-73
+    const float rr = __fsqrt_rn(u0);
+    float sn, cs; sincos_tau(u1, sn, cs);
+    const float lx = mul(rr, cs), ly = mul(rr, sn), lz = __fsqrt_rn(fmaxf(0.0f, sub(1.0f, u0)));
+    const float sign = nz >= 0.0f ? 1.0f : -1.0f;                              // sampling.hlsl:40-50
+    const float a = __fdiv_rn(-1.0f, add(sign, nz));
+    const float b = mul(mul(nx, ny), a);
+    const float b1x = add(1.0f, mul(mul(mul(sign, nx), nx), a)), b1y = mul(sign, b), b1z = mul(-sign, nx);
+    const float b2x = b, b2y = add(sign, mul(mul(ny, ny), a)), b2z = -ny;
+    dx = add(add(mul(b1x, lx), mul(b2x, ly)), mul(nx, lz));                    // Mat3::from_cols(b1, b2, n) * l
+    dy = add(add(mul(b1y, lx), mul(b2y, ly)), mul(ny, lz));
+    dz = add(add(mul(b1z, lx), mul(b2z, ly)), mul(nz, lz));
+    normalize3(dx, dy, dz);
+}
+
+__device__ __forceinline__ uchar4 shade(float col) {                           // rt_cpu.rs:104-106
+    float g = powf(col, 2.2f) * 255.0f;
+    g = g < 0.0f ? 0.0f : (g > 255.0f ? 255.0f : g);
+    const unsigned char v = (unsigned char)g;
+    return make_uchar4(v, v, v, 255);
+}
+
+// ---- the kernel ---------------------------------------------------------------------------------
+template <int SRC, bool TLAS, bool COUNT, int TRI_STRIDE>
+__global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_constant__ TraceParams P) {
+    __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
+    uint2 spill[STACK_SPILL];
+    const unsigned lane = threadIdx.x & 31u;
+    uint2* const my_stack = s_stack + threadIdx.x;
+
+    RayConst r;
+    float best_t = 0.f;
+    uint32_t best_prim = INVALID;
+    uint32_t cur_x = 0, cur_y = 0, tri_x = 0, tri_y = 0;
+    int sp = 0;
+    uint32_t tlas_sp = INVALID, bvh_off = 0;
+    unsigned long long item = 0;
+    uint32_t px = 0, py = 0;
+    bool active = false;
+    bool exhausted = false;                      // warp-uniform
+    unsigned long long c_rays = 0, c_nodes = 0, c_tris = 0, c_insts = 0, c_hits = 0;
+
+    auto push = [&](uint32_t x, uint32_t y) {
+        if (sp < STACK_SMEM) my_stack[sp * BLOCK_THREADS] = make_uint2(x, y);
+        else if (sp < STACK_SMEM + STACK_SPILL) spill[sp - STACK_SMEM] = make_uint2(x, y);
+        else { atomicOr(P.overflow, 1u); return; }
+        sp++;
+    };
+    auto pop = [&]() -> uint2 {
+        sp--;
+        return sp < STACK_SMEM ? my_stack[sp * BLOCK_THREADS] : spill[sp - STACK_SMEM];
+    };
+
+    for (;;) {
+        // ---- refill idle lanes from the global cursor (persistent warps + ray replacement) ----
+        const unsigned idle = __ballot_sync(FULL, !active);
+        if (idle != 0u && !exhausted && ((unsigned)__popc(idle) >= P.refill_min || idle == FULL)) {
+            const int n_idle = __popc(idle);
+            const int leader = __ffs(idle) - 1;
+            unsigned long long base = 0;
+            if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)n_idle);
+            base = __shfl_sync(FULL, base, leader);
+            if (base + (unsigned long long)n_idle >= P.n_work) exhausted = true;
+            if (!active) {
+                item = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
+                if (item < P.n_work) {
+                    float ox, oy, oz, dx, dy, dz, tmin = 0.0f, tmax = F32_MAX_;
+                    bool go = true;
+                    if (SRC == SRC_BUFFER) {
+                        const float4* rp = reinterpret_cast<const float4*>(P.rays_in + item);
+                        const float4 a = __ldg(rp), b = __ldg(rp + 1);
+                        ox = a.x; oy = a.y; oz = a.z; tmin = a.w; dx = b.x; dy = b.y; dz = b.z; tmax = b.w;
+                    } else {
+                        go = item_to_pixel(P, item, px, py);
+                        if (go) {
+                            primary_dir(P, px, py, dx, dy, dz);
+                            ox = P.view.eye[0]; oy = P.view.eye[1]; oz = P.view.eye[2];
+                            if (SRC == SRC_BOUNCE) {
+                                const tray_hit ph = P.primary_in[item];
+                                tray_ray br; br.origin[0] = br.origin[1] = br.origin[2] = br.tmin = 0.f;
+                                br.dir[0] = br.dir[1] = br.dir[2] = br.tmax = 0.f;
+                                if (ph.t < F32_MAX_) {                                   // rt_cpu.rs:61
+                                    float bx, by, bz, ex, ey, ez;
+                                    bounce_ray<TRI_STRIDE>(P, px, py, dx, dy, dz, ph.t, ph.prim, bx, by, bz, ex, ey, ez);
+                                    ox = bx; oy = by; oz = bz; dx = ex; dy = ey; dz = ez;
+                                    br.origin[0] = ox; br.origin[1] = oy; br.origin[2] = oz; br.tmin = 0.f;
+                                    br.dir[0] = dx; br.dir[1] = dy; br.dir[2] = dz; br.tmax = F32_MAX_;
+                                } else {
+                                    go = false;
+                                    tray_hit miss; miss.t = __int_as_float(0x7f800000); miss.prim = INVALID;
+                                    P.hits_out[item] = miss;
+                                    if (P.rgba_out) P.rgba_out[item] = shade(__fdiv_rn(1.0f, ph.t));   // rt_cpu.rs:59
+                                }
+                                if (P.rays_out) P.rays_out[item] = br;
+                            }
+                        }
+                    }
+                    if (go) {
+                        prepare_ray(r, ox, oy, oz, dx, dy, dz, tmin);
+                        best_t = tmax; best_prim = INVALID;
+                        cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp = 0;   // root group, query.hlsl:343
+                        tlas_sp = INVALID; bvh_off = TLAS ? P.tlas_start : 0u;
+                        active = true;
+                        if (COUNT) c_rays++;
+                    }
+                }
+            }
+        }
+        if (__ballot_sync(FULL, active) == 0u) {
+            if (exhausted) break;
+            continue;
+        }
+
+        // ---- cheap transitions: pop the stack, or retire the ray (query.hlsl:417-427) ----
+        if (active && tri_y == 0u && (cur_y & 0xff000000u) == 0u) {
+            if (sp == 0) {
+                tray_hit h;
+                h.t = best_prim != INVALID ? best_t : __int_as_float(0x7f800000);   // RayHit::none()
+                h.prim = best_prim;
+                P.hits_out[item] = h;
+                if (SRC != SRC_BUFFER && P.rgba_out) {
+                    float col;
+                    if (SRC == SRC_PRIMARY) col = __fdiv_rn(1.0f, h.t);                                  // rt_cpu.rs:59
+                    else col = h.t < F32_MAX_ ? __fdiv_rn(h.t, add(1.0f, h.t)) : 1.0f;                   // rt_cpu.rs:82-87
+                    P.rgba_out[item] = shade(col);
+                }
+                if (COUNT && best_prim != INVALID) c_hits++;
+                active = false;
+            } else {
+                if (TLAS && (uint32_t)sp == tlas_sp) { tlas_sp = INVALID; bvh_off = P.tlas_start; }     // tlas:480-486
+                const uint2 e = pop();
+                cur_x = e.x; cur_y = e.y;
+                if ((cur_y & 0xff000000u) == 0u) { tri_x = cur_x; tri_y = cur_y; cur_x = 0; cur_y = 0; }  // query.hlsl:389-393
+            }
+        }
+
+        // ---- warp vote: node step or triangle step ----
+        const bool want_tri = active && tri_y != 0u;
+        const bool want_node = active && tri_y == 0u && (cur_y & 0xff000000u) != 0u;
+        const unsigned m_tri = __ballot_sync(FULL, want_tri), m_node = __ballot_sync(FULL, want_node);
+        if ((m_tri | m_node) == 0u) continue;
+        const bool tri_phase = m_node == 0u || (unsigned)__popc(m_tri) * P.tri_weight >= (unsigned)__popc(m_node);
+
+        if (!tri_phase) {
+            if (want_node) {
+                const uint32_t hits_imask = cur_y;
+                const uint32_t off = 31u - (uint32_t)__clz((int)hits_imask);                 // query.hlsl:358
+                cur_y &= ~(1u << off);                                                         // :362
+                if (cur_y & 0xff000000u) push(cur_x, cur_y);                                   // :365-368
+                const uint32_t slot = (off - 24u) ^ (r.oct_inv4 & 0xffu);                      // :370
+                const uint32_t rel = (uint32_t)__popc(hits_imask & ~(0xffffffffu << slot));    // :371
+                const uint4* np = P.nodes + (size_t)(bvh_off + cur_x + rel) * 5u;              // :373, tlas:383
+                const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                if (COUNT) c_nodes++;
+                const uint32_t hitmask = node_test(r, best_t, n0, n1, n2, n3, n4);             // :380
+                cur_x = n1.x; tri_x = n1.y;                                                    // :383-384
+                cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386
+                tri_y = hitmask & 0x00ffffffu;                                                 // :387
+            }
+        } else {
+            if (want_tri) {
+                const uint32_t local = 31u - (uint32_t)__clz((int)tri_y);                      // :398
+                tri_y &= ~(1u << local);                                                       // :401
+                const uint32_t g = tri_x + local;                                              // :403
+                if (TLAS && tlas_sp == INVALID) {
+                    // TLAS leaf: g is an instance slot (query_tlas.hlsl:410-446)
+                    if (tri_y != 0u) push(tri_x, tri_y);
+                    if (cur_y & 0xff000000u) push(cur_x, cur_y);
+                    tlas_sp = (uint32_t)sp;
+                    bvh_off = __ldg(P.blas_offsets + g);
+                    if (COUNT) c_insts++;
+                    cur_x = 0; cur_y = 0x80000000u; tri_y = 0;
+                } else {
+                    if (COUNT) c_tris++;
+                    const float t = tri_test<TRI_STRIDE>(r, best_t, P.tris, g);
+                    if (t < best_t) { best_t = t; best_prim = g; }          // CPU tie rule: first of equal t wins (§8a a11)
+                }
+            }
+        }
+    }
+
+    if (COUNT) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            c_rays += __shfl_xor_sync(FULL, c_rays, o); c_nodes += __shfl_xor_sync(FULL, c_nodes, o);
+            c_tris += __shfl_xor_sync(FULL, c_tris, o); c_insts += __shfl_xor_sync(FULL, c_insts, o);
+            c_hits += __shfl_xor_sync(FULL, c_hits, o);
+        }
+        if (lane == 0) {
+            atomicAdd(P.counters + 0, c_rays); atomicAdd(P.counters + 1, c_nodes); atomicAdd(P.counters + 2, c_tris);
+            atomicAdd(P.counters + 3, c_insts); atomicAdd(P.counters + 4, c_hits);
+        }
+    }
+}
+
+// compact local order -> row-major frame (one thread per local work item)
+template <typename T>
+__global__ void untile_kernel(const TraceParams P, const T* __restrict__ src, T* __restrict__ dst) {
+    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= P.n_work) return;
+    uint32_t px, py;
+    if (item_to_pixel(P, j, px, py)) dst[(size_t)py * P.width + px] = src[j];
+}
+
+}  // namespace tray

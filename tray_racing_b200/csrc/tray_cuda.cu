@@ -1,0 +1,488 @@
+// tray_cuda.cu — the C ABI of include/tray_cuda.h over the sm_100a kernels in traverse.cuh.
+// No CPU fallback exists: without a CUDA device every compute entry point fails with TRAY_ERR_NO_DEVICE.
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "traverse.cuh"
+
+static_assert(sizeof(tray_cwbvh_node) == 80, "CwBvhNode is 80 bytes (bvh_embree_to_cwbvh.rs:91, rt_gpu/mod.rs:70)");
+static_assert(sizeof(tray_tri48) == 48 && sizeof(tray_tri64) == 64, "triangle record strides");
+static_assert(sizeof(tray_ray) == 32 && sizeof(tray_hit) == 8, "ray / hit records");
+static_assert(sizeof(tray_view) == 160, "ViewUniform is padded to 160 bytes (main.rs:589-597)");
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap; va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(TRAY_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v && *v ? atoi(v) : dflt;
+}
+
+}  // namespace
+
+struct tray_scene {
+    int device = 0;
+    int sm_count = 0;
+    uint64_t n_nodes = 0, n_tris = 0;
+    uint32_t tri_stride = 48, n_instances = 0, tlas_start = 0;
+    bool tlas = false;
+    uint4* d_nodes = nullptr;
+    uint4* d_tris = nullptr;
+    uint32_t* d_blas = nullptr;
+    unsigned long long* d_cursor = nullptr;     // [0] cursor, then 2 x 5 counters
+    uint32_t* d_overflow = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
+    bool counting = false;
+    uint32_t refill_min = 8, tri_weight = 2;
+    int blocks_per_sm[3] = { 0, 0, 0 };
+    // ray-batch staging
+    tray_ray* d_rays = nullptr; tray_hit* d_hits = nullptr; uint64_t batch_cap = 0;
+    // frame state (compact local order)
+    uint32_t fw = 0, fh = 0, fshard = 0, fshards = 1;
+    uint64_t f_items = 0, f_cap = 0;
+    bool f_has_bounce = false, f_has_rgba = false, f_has_rays = false;
+    tray_hit* d_primary = nullptr; tray_hit* d_bounce = nullptr; tray_ray* d_brays = nullptr; uchar4* d_rgba = nullptr;
+    void* d_untiled = nullptr; uint64_t untiled_cap = 0;
+    tray::TraceParams last_params;
+    tray_counters cnt_primary{}, cnt_bounce{};
+};
+
+namespace {
+
+using namespace tray;
+
+typedef void (*kernel_fn)(const TraceParams);
+
+template <int SRC, bool TLAS, bool COUNT>
+kernel_fn pick_stride(uint32_t stride) {
+    return stride == 64 ? (kernel_fn)trace_kernel<SRC, TLAS, COUNT, 64> : (kernel_fn)trace_kernel<SRC, TLAS, COUNT, 48>;
+}
+template <int SRC>
+kernel_fn pick(bool tlas, bool count, uint32_t stride) {
+    if (tlas) return count ? pick_stride<SRC, true, true>(stride) : pick_stride<SRC, true, false>(stride);
+    return count ? pick_stride<SRC, false, true>(stride) : pick_stride<SRC, false, false>(stride);
+}
+kernel_fn pick_kernel(int src, bool tlas, bool count, uint32_t stride) {
+    switch (src) {
+        case SRC_BUFFER: return pick<SRC_BUFFER>(tlas, count, stride);
+        case SRC_PRIMARY: return pick<SRC_PRIMARY>(tlas, count, stride);
+        default: return pick<SRC_BOUNCE>(tlas, count, stride);
+    }
+}
+
+uint64_t local_items(uint32_t w, uint32_t h, uint32_t shard, uint32_t shards) {
+    const uint64_t tiles = (uint64_t)((w + 31) / 32) * ((h + 7) / 8);
+    if (shard >= tiles) return 0;
+    return ((tiles - shard + shards - 1) / shards) * 256ull;
+}
+
+void base_params(const tray_scene* s, TraceParams& P) {
+    memset(&P, 0, sizeof P);
+    P.nodes = s->d_nodes; P.tris = s->d_tris; P.blas_offsets = s->d_blas; P.tlas_start = s->tlas_start;
+    P.cursor = s->d_cursor; P.overflow = s->d_overflow;
+    P.refill_min = s->refill_min; P.tri_weight = s->tri_weight;
+    P.shard_count = 1;
+}
+
+// one launch: reset the cursor, run the persistent grid
+int launch(tray_scene* s, int src, TraceParams& P, cudaStream_t st, int counter_slot) {
+    kernel_fn k = pick_kernel(src, s->tlas, s->counting, s->tri_stride);
+    if (s->blocks_per_sm[src] == 0) {
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, BLOCK_THREADS, 0));
+        s->blocks_per_sm[src] = nb > 0 ? nb : 1;
+        int cap = env_int("TRAY_CUDA_BLOCKS_PER_SM", 0);
+        if (cap > 0 && cap < s->blocks_per_sm[src]) s->blocks_per_sm[src] = cap;
+    }
+    P.counters = s->d_cursor + 1 + 5 * counter_slot;
+    CU(cudaMemsetAsync(s->d_cursor, 0, sizeof(unsigned long long), st));
+    if (s->counting) CU(cudaMemsetAsync(P.counters, 0, 5 * sizeof(unsigned long long), st));
+    unsigned long long warps_needed = (P.n_work + 31) / 32;
+    unsigned long long blocks_needed = (warps_needed + (BLOCK_THREADS / 32) - 1) / (BLOCK_THREADS / 32);
+    unsigned long long grid = (unsigned long long)s->sm_count * s->blocks_per_sm[src];
+    if (blocks_needed < grid) grid = blocks_needed;
+    if (grid == 0) return TRAY_OK;
+    k<<<(unsigned)grid, BLOCK_THREADS, 0, st>>>(P);
+    CU(cudaGetLastError());
+    return TRAY_OK;
+}
+
+int read_counters(tray_scene* s, int slot, tray_counters* out) {
+    unsigned long long c[5];
+    CU(cudaMemcpyAsync(c, s->d_cursor + 1 + 5 * slot, sizeof c, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    out->rays = c[0]; out->nodes = c[1]; out->tris = c[2]; out->instances = c[3]; out->hits = c[4];
+    return TRAY_OK;
+}
+
+int check_overflow(tray_scene* s) {
+    uint32_t f = 0;
+    CU(cudaMemcpyAsync(&f, s->d_overflow, 4, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (f) {
+        cudaMemsetAsync(s->d_overflow, 0, 4, s->stream);
+        return fail(TRAY_ERR_OVERFLOW, "traversal stack overflow: BVH needs more than %d stack entries", STACK_SMEM + STACK_SPILL);
+    }
+    return TRAY_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* tray_cuda_last_error(void) { return g_err; }
+unsigned tray_cuda_abi_version(void) { return TRAY_CUDA_ABI_VERSION; }
+
+int tray_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+void tray_cuda_scene_destroy(tray_scene* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_blas); cudaFree(s->d_cursor); cudaFree(s->d_overflow);
+    cudaFree(s->d_rays); cudaFree(s->d_hits);
+    cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba); cudaFree(s->d_untiled);
+    for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris, uint64_t n_tris, uint32_t tri_stride,
+                           const uint32_t* blas_offsets, uint32_t n_instances, uint32_t tlas_start,
+                           int device, tray_scene** out) {
+    if (!out) return fail(TRAY_ERR_ARG, "out_scene is NULL");
+    *out = nullptr;
+    if ((n_nodes && !nodes) || (n_tris && !tris)) return fail(TRAY_ERR_ARG, "NULL node / triangle buffer");
+    if (tri_stride != 48 && tri_stride != 64) return fail(TRAY_ERR_ARG, "tri_stride must be 48 or 64 (got %u)", tri_stride);
+    if (n_instances && !blas_offsets) return fail(TRAY_ERR_ARG, "n_instances > 0 but blas_offsets is NULL");
+    if (n_instances && tlas_start >= n_nodes) return fail(TRAY_ERR_ARG, "tlas_start %u outside %llu nodes", tlas_start, (unsigned long long)n_nodes);
+    if (n_nodes >= 0xffffffffull || n_tris >= 0xffffffffull) return fail(TRAY_ERR_ARG, "node / triangle indices are 32-bit");
+    const int ndev = tray_cuda_device_count();
+    if (ndev == 0) return fail(TRAY_ERR_NO_DEVICE, "no CUDA device (tray_cuda has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TRAY_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    tray_scene* s = new (std::nothrow) tray_scene();
+    if (!s) return fail(TRAY_ERR_ARG, "out of host memory");
+    s->device = device; s->n_nodes = n_nodes; s->n_tris = n_tris; s->tri_stride = tri_stride;
+    s->n_instances = n_instances; s->tlas_start = tlas_start; s->tlas = n_instances > 0;
+    s->refill_min = (uint32_t)env_int("TRAY_CUDA_REFILL_MIN", 8);
+    s->tri_weight = (uint32_t)env_int("TRAY_CUDA_TRI_WEIGHT", 2);
+    int rc = TRAY_OK;
+    auto body = [&]() -> int {
+        cudaDeviceProp prop;
+        CU(cudaGetDeviceProperties(&prop, device));
+        s->sm_count = prop.multiProcessorCount;
+        s->l2_bytes = (uint64_t)prop.l2CacheSize;
+        CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        for (auto& e : s->ev) CU(cudaEventCreate(&e));
+        const size_t nb = (size_t)(n_nodes ? n_nodes : 1) * 80, tb = (size_t)(n_tris ? n_tris : 1) * tri_stride;
+        CU(cudaMalloc(&s->d_nodes, nb));
+        CU(cudaMalloc(&s->d_tris, tb));
+        CU(cudaMalloc(&s->d_blas, (size_t)(n_instances ? n_instances : 1) * 4));
+        CU(cudaMalloc(&s->d_cursor, 16 * sizeof(unsigned long long)));
+        CU(cudaMalloc(&s->d_overflow, 4));
+        CU(cudaMemsetAsync(s->d_cursor, 0, 16 * sizeof(unsigned long long), s->stream));
+        CU(cudaMemsetAsync(s->d_overflow, 0, 4, s->stream));
+        s->device_bytes = nb + tb + (size_t)n_instances * 4;
+        if (n_nodes) CU(cudaMemcpyAsync(s->d_nodes, nodes, (size_t)n_nodes * 80, cudaMemcpyHostToDevice, s->stream));
+        if (n_tris) CU(cudaMemcpyAsync(s->d_tris, tris, (size_t)n_tris * tri_stride, cudaMemcpyHostToDevice, s->stream));
+        if (n_instances) CU(cudaMemcpyAsync(s->d_blas, blas_offsets, (size_t)n_instances * 4, cudaMemcpyHostToDevice, s->stream));
+        // keep the node array hot in the 126 MB L2: persisting access-policy window on the scene stream
+        if (env_int("TRAY_CUDA_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0 && n_nodes) {
+            size_t want = (size_t)prop.persistingL2CacheMaxSize;
+            if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess) {
+                cudaStreamAttrValue attr; memset(&attr, 0, sizeof attr);
+                size_t win = (size_t)n_nodes * 80;
+                if (win > (size_t)prop.accessPolicyMaxWindowSize) win = (size_t)prop.accessPolicyMaxWindowSize;
+                attr.accessPolicyWindow.base_ptr = s->d_nodes;
+                attr.accessPolicyWindow.num_bytes = win;
+                double ratio = (double)want / (double)win;
+                attr.accessPolicyWindow.hitRatio = (float)(ratio > 1.0 ? 1.0 : ratio);
+                attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+                attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+                if (cudaStreamSetAttribute(s->stream, cudaStreamAttributeAccessPolicyWindow, &attr) == cudaSuccess)
+                    s->l2_persist = win < want ? win : want;
+                else cudaGetLastError();
+            } else cudaGetLastError();
+        }
+        CU(cudaStreamSynchronize(s->stream));
+        return TRAY_OK;
+    };
+    rc = body();
+    if (rc != TRAY_OK) { tray_cuda_scene_destroy(s); return rc; }
+    *out = s;
+    return TRAY_OK;
+}
+
+int tray_cuda_scene_info(const tray_scene* s, tray_scene_info* o) {
+    if (!s || !o) return fail(TRAY_ERR_ARG, "NULL argument");
+    memset(o, 0, sizeof *o);
+    o->n_nodes = s->n_nodes; o->n_tris = s->n_tris; o->tri_stride = s->tri_stride; o->n_instances = s->n_instances;
+    o->tlas_start = s->tlas_start; o->is_tlas = s->tlas; o->device = s->device; o->sm_count = (uint32_t)s->sm_count;
+    o->device_bytes = s->device_bytes; o->l2_bytes = s->l2_bytes; o->l2_persist_bytes = s->l2_persist;
+    return TRAY_OK;
+}
+
+int tray_cuda_set_counting(tray_scene* s, int enabled) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    if (s->counting != (enabled != 0)) { s->counting = enabled != 0; s->blocks_per_sm[0] = s->blocks_per_sm[1] = s->blocks_per_sm[2] = 0; }
+    return TRAY_OK;
+}
+
+int tray_cuda_sync(tray_scene* s) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    return check_overflow(s);
+}
+
+int tray_cuda_trace_device(tray_scene* s, const tray_ray* d_rays, uint64_t n, tray_hit* d_hits, void* stream, float* ms_kernel) {
+    if (!s || (n && (!d_rays || !d_hits))) return fail(TRAY_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    TraceParams P; base_params(s, P);
+    P.rays_in = d_rays; P.n_work = n; P.hits_out = d_hits;
+    if (ms_kernel) CU(cudaEventRecord(s->ev[0], st));
+    int rc = launch(s, SRC_BUFFER, P, st, 0);
+    if (rc) return rc;
+    if (ms_kernel) {
+        CU(cudaEventRecord(s->ev[1], st));
+        CU(cudaEventSynchronize(s->ev[1]));
+        CU(cudaEventElapsedTime(ms_kernel, s->ev[0], s->ev[1]));
+    }
+    return TRAY_OK;
+}
+
+int tray_cuda_trace(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, float* ms_kernel, float* ms_total) {
+    if (!s || (n && (!rays || !hits))) return fail(TRAY_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    const auto t0 = std::chrono::steady_clock::now();
+    if (n > s->batch_cap) {
+        cudaFree(s->d_rays); cudaFree(s->d_hits); s->d_rays = nullptr; s->d_hits = nullptr; s->batch_cap = 0;
+        CU(cudaMalloc(&s->d_rays, n * sizeof(tray_ray)));
+        CU(cudaMalloc(&s->d_hits, n * sizeof(tray_hit)));
+        s->batch_cap = n;
+    }
+    if (n) CU(cudaMemcpyAsync(s->d_rays, rays, n * sizeof(tray_ray), cudaMemcpyHostToDevice, s->stream));
+    float k = 0.f;
+    int rc = tray_cuda_trace_device(s, s->d_rays, n, s->d_hits, s->stream, &k);
+    if (rc) return rc;
+    if (n) CU(cudaMemcpyAsync(hits, s->d_hits, n * sizeof(tray_hit), cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->counting) { rc = read_counters(s, 0, &s->cnt_primary); if (rc) return rc; memset(&s->cnt_bounce, 0, sizeof s->cnt_bounce); }
+    rc = check_overflow(s);
+    if (rc) return rc;
+    if (ms_kernel) *ms_kernel = k;
+    if (ms_total) *ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return TRAY_OK;
+}
+
+uint64_t tray_cuda_shard_pixels(uint32_t w, uint32_t h, uint32_t shard, uint32_t shards) {
+    if (shards == 0) shards = 1;
+    const uint32_t tx = (w + 31) / 32, ty = (h + 7) / 8;
+    uint64_t n = 0;
+    for (uint64_t k = shard; k < (uint64_t)tx * ty; k += shards) {
+        const uint32_t x0 = (uint32_t)(k % tx) * 32, y0 = (uint32_t)(k / tx) * 8;
+        const uint32_t cw = x0 + 32 <= w ? 32 : w - x0, ch = y0 + 8 <= h ? 8 : h - y0;
+        n += (uint64_t)cw * ch;
+    }
+    return n;
+}
+
+int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t h, uint32_t frame_count, uint32_t flags,
+                     uint32_t shard, uint32_t shards, float* ms_primary, float* ms_bounce) {
+    if (!s || !view) return fail(TRAY_ERR_ARG, "NULL argument");
+    if (shards == 0) shards = 1;
+    if (w == 0 || h == 0 || shard >= shards) return fail(TRAY_ERR_ARG, "bad frame size / shard (%ux%u, %u of %u)", w, h, shard, shards);
+    CU(cudaSetDevice(s->device));
+    const bool want_count = (flags & TRAY_RENDER_COUNTERS) != 0;
+    if (want_count != s->counting) tray_cuda_set_counting(s, want_count);
+    const uint64_t items = local_items(w, h, shard, shards);
+    const bool bounce = (flags & TRAY_RENDER_BOUNCE) != 0, rgba = (flags & TRAY_RENDER_RGBA) != 0;
+    const bool keep_rays = (flags & TRAY_RENDER_KEEP_RAYS) != 0;
+    if (items > s->f_cap || (bounce && !s->d_bounce) || (rgba && !s->d_rgba) || (keep_rays && !s->d_brays)) {
+        const uint64_t cap = items > s->f_cap ? items : s->f_cap;
+        cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba);
+        s->d_primary = nullptr; s->d_bounce = nullptr; s->d_brays = nullptr; s->d_rgba = nullptr; s->f_cap = 0;
+        const uint64_t c1 = cap ? cap : 1;
+        CU(cudaMalloc(&s->d_primary, c1 * sizeof(tray_hit)));
+        CU(cudaMalloc(&s->d_bounce, c1 * sizeof(tray_hit)));
+        CU(cudaMalloc(&s->d_rgba, c1 * sizeof(uchar4)));
+        if (keep_rays) CU(cudaMalloc(&s->d_brays, c1 * sizeof(tray_ray)));
+        CU(cudaMemsetAsync(s->d_primary, 0xff, c1 * sizeof(tray_hit), s->stream));
+        CU(cudaMemsetAsync(s->d_bounce, 0xff, c1 * sizeof(tray_hit), s->stream));
+        CU(cudaMemsetAsync(s->d_rgba, 0, c1 * sizeof(uchar4), s->stream));
+        s->f_cap = cap;
+    }
+    s->fw = w; s->fh = h; s->fshard = shard; s->fshards = shards; s->f_items = items;
+    s->f_has_bounce = bounce; s->f_has_rgba = rgba; s->f_has_rays = keep_rays && bounce;
+
+    TraceParams P; base_params(s, P);
+    P.flags = flags; P.view = *view; P.width = w; P.height = h; P.frame_count = frame_count;
+    P.shard_index = shard; P.shard_count = shards; P.tiles_x = (w + 31) / 32; P.n_work = items;
+    P.hits_out = s->d_primary;
+    P.rgba_out = (rgba && !bounce) ? s->d_rgba : nullptr;
+    s->last_params = P;
+    const bool timed = ms_primary || ms_bounce;
+    if (timed) CU(cudaEventRecord(s->ev[0], s->stream));
+    int rc = launch(s, SRC_PRIMARY, P, s->stream, 0);
+    if (rc) return rc;
+    if (timed) CU(cudaEventRecord(s->ev[1], s->stream));
+    if (bounce) {
+        TraceParams B = P;
+        B.primary_in = s->d_primary; B.hits_out = s->d_bounce;
+        B.rgba_out = rgba ? s->d_rgba : nullptr;
+        B.rays_out = keep_rays ? s->d_brays : nullptr;
+        rc = launch(s, SRC_BOUNCE, B, s->stream, 1);
+        if (rc) return rc;
+        if (timed) CU(cudaEventRecord(s->ev[2], s->stream));
+    }
+    if (timed) {
+        CU(cudaStreamSynchronize(s->stream));
+        float a = 0.f, b = 0.f;
+        CU(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
+        if (bounce) CU(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
+        if (ms_primary) *ms_primary = a;
+        if (ms_bounce) *ms_bounce = b;
+    }
+    if (s->counting) {
+        rc = read_counters(s, 0, &s->cnt_primary); if (rc) return rc;
+        if (bounce) { rc = read_counters(s, 1, &s->cnt_bounce); if (rc) return rc; }
+        else memset(&s->cnt_bounce, 0, sizeof s->cnt_bounce);
+    }
+    return TRAY_OK;
+}
+
+int tray_cuda_counters(tray_scene* s, tray_counters* primary, tray_counters* bounce) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    if (primary) *primary = s->cnt_primary;
+    if (bounce) *bounce = s->cnt_bounce;
+    return TRAY_OK;
+}
+
+int tray_cuda_frame_device_ptrs(tray_scene* s, void** d_primary, void** d_bounce, void** d_rgba) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    if (d_primary) *d_primary = s->d_primary;
+    if (d_bounce) *d_bounce = s->d_bounce;
+    if (d_rgba) *d_rgba = s->d_rgba;
+    return TRAY_OK;
+}
+
+}  // extern "C"
+
+namespace {
+template <typename T>
+int download(tray_scene* s, const T* d_src, T* host_dst) {
+    const uint64_t n = (uint64_t)s->fw * s->fh, bytes = n * sizeof(T);
+    if (bytes > s->untiled_cap) {
+        cudaFree(s->d_untiled); s->d_untiled = nullptr; s->untiled_cap = 0;
+        CU(cudaMalloc(&s->d_untiled, bytes));
+        s->untiled_cap = bytes;
+    }
+    if (s->fshards > 1) {
+        // keep the caller's pixels of other shards: start from what the caller holds
+        CU(cudaMemcpyAsync(s->d_untiled, host_dst, bytes, cudaMemcpyHostToDevice, s->stream));
+    }
+    if (s->f_items) {
+        const unsigned grid = (unsigned)((s->f_items + 255) / 256);
+        tray::untile_kernel<T><<<grid, 256, 0, s->stream>>>(s->last_params, d_src, (T*)s->d_untiled);
+        CU(cudaGetLastError());
+    }
+    CU(cudaMemcpyAsync(host_dst, s->d_untiled, bytes, cudaMemcpyDeviceToHost, s->stream));
+    CU(cudaStreamSynchronize(s->stream));
+    return TRAY_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int tray_cuda_frame_download(tray_scene* s, tray_hit* primary, tray_hit* bounce, tray_ray* bounce_rays, uint8_t* rgba) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    if (s->fw == 0) return fail(TRAY_ERR_ARG, "no frame has been rendered");
+    CU(cudaSetDevice(s->device));
+    int rc;
+    if (primary) { rc = download<tray_hit>(s, s->d_primary, primary); if (rc) return rc; }
+    if (bounce) {
+        if (!s->f_has_bounce) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_BOUNCE");
+        rc = download<tray_hit>(s, s->d_bounce, bounce); if (rc) return rc;
+    }
+    if (bounce_rays) {
+        if (!s->f_has_rays) return fail(TRAY_ERR_ARG, "last frame was rendered without the keep-bounce-rays flag (0x8)");
+        rc = download<tray_ray>(s, s->d_brays, bounce_rays); if (rc) return rc;
+    }
+    if (rgba) {
+        if (!s->f_has_rgba) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA");
+        rc = download<uchar4>(s, s->d_rgba, (uchar4*)rgba); if (rc) return rc;
+    }
+    return check_overflow(s);
+}
+
+int tray_cuda_start(const void* bvh_bytes, uint64_t bvh_len, const void* instance_bytes, uint64_t instance_len,
+                    const void* tri_bytes, uint64_t tri_len, uint32_t tri_stride, uint32_t tlas_start, int use_tlas,
+                    const tray_view* view, uint32_t width, uint32_t height, float render_time_s, int benchmark,
+                    int animate, int device, float* out_min_ms, float* out_mean_ms, uint32_t* out_frames) {
+    if (!view) return fail(TRAY_ERR_ARG, "NULL view");
+    // the reference asserts these strides at src/rt_gpu/mod.rs:70,86,105,107
+    if (bvh_len % 80 != 0) return fail(TRAY_ERR_ARG, "bvh_bytes length %llu is not a multiple of 80", (unsigned long long)bvh_len);
+    if (tri_stride == 0 || tri_len % tri_stride != 0) return fail(TRAY_ERR_ARG, "tri_bytes length is not a multiple of tri_stride");
+    if (instance_len % 4 != 0) return fail(TRAY_ERR_ARG, "instance_bytes length is not a multiple of 4");
+    tray_scene* s = nullptr;
+    int rc = tray_cuda_scene_create(bvh_bytes, bvh_len / 80, tri_bytes, tri_len / tri_stride, tri_stride,
+                                    use_tlas ? (const uint32_t*)instance_bytes : nullptr,
+                                    use_tlas ? (uint32_t)(instance_len / 4) : 0u, tlas_start, device, &s);
+    if (rc) return rc;
+    const uint32_t flags = TRAY_RENDER_BOUNCE | TRAY_RENDER_RGBA;
+    float min_ms = 3.402823466e+38f; double sum = 0; uint32_t frames = 0, frame_count = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        if (benchmark) {   // untimed warm-up dispatch right before the timed one (rt_gpu_software.rs:289-295)
+            rc = tray_cuda_render(s, view, width, height, frame_count, flags, 0, 1, nullptr, nullptr);
+            if (rc) break;
+        }
+        float a = 0.f, b = 0.f;
+        rc = tray_cuda_render(s, view, width, height, frame_count, flags, 0, 1, &a, &b);
+        if (rc) break;
+        const float ms = a + b;
+        if (ms < min_ms) min_ms = ms;
+        sum += ms; frames++;
+        if (animate) frame_count = frames;                                   // rt_cpu.rs:95-97
+        const float el = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
+        if (el > render_time_s) break;                                       // rt_cpu.rs:98-100, rt_gpu_software.rs:354-359
+    }
+    if (!rc) rc = tray_cuda_sync(s);
+    tray_cuda_scene_destroy(s);
+    if (rc) return rc;
+    if (out_min_ms) *out_min_ms = min_ms;
+    if (out_mean_ms) *out_mean_ms = frames ? (float)(sum / frames) : 0.f;
+    if (out_frames) *out_frames = frames;
+    return TRAY_OK;
+}
+
+}  // extern "C"

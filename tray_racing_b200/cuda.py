@@ -1,0 +1,217 @@
+"""ctypes binding of libtray_cuda.so (include/tray_cuda.h) — the product path.
+
+There is no CPU fallback: if the shared library is missing, or there is no CUDA device, every entry
+point raises.  Nothing here imports or calls the oracle."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .host import HIT_DTYPE, RAY_DTYPE, TrayView
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtray_cuda.so")
+
+RENDER_BOUNCE, RENDER_RGBA, RENDER_COUNTERS, RENDER_KEEP_RAYS = 1, 2, 4, 8
+
+EXPORTS = (
+    "tray_cuda_device_count", "tray_cuda_abi_version", "tray_cuda_scene_create", "tray_cuda_scene_destroy",
+    "tray_cuda_scene_info", "tray_cuda_trace", "tray_cuda_trace_device", "tray_cuda_render",
+    "tray_cuda_shard_pixels", "tray_cuda_frame_download", "tray_cuda_frame_device_ptrs", "tray_cuda_sync",
+    "tray_cuda_counters", "tray_cuda_set_counting", "tray_cuda_start", "tray_cuda_last_error",
+)
+
+
+class TrayCudaError(RuntimeError):
+    pass
+
+
+class Counters(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays", "nodes", "tris", "instances", "hits")]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class SceneInfo(C.Structure):
+    _fields_ = [("n_nodes", C.c_uint64), ("n_tris", C.c_uint64), ("tri_stride", C.c_uint32), ("n_instances", C.c_uint32),
+                ("tlas_start", C.c_uint32), ("is_tlas", C.c_uint32), ("device", C.c_int32), ("sm_count", C.c_uint32),
+                ("device_bytes", C.c_uint64), ("l2_bytes", C.c_uint64), ("l2_persist_bytes", C.c_uint64)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+_lib = None
+
+
+def _as_u8(buf) -> np.ndarray:
+    if isinstance(buf, (bytes, bytearray, memoryview)):
+        return np.frombuffer(buf, dtype=np.uint8)
+    return np.ascontiguousarray(buf).view(np.uint8).reshape(-1)
+
+
+def lib() -> C.CDLL:
+    """Load libtray_cuda.so; fail loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise TrayCudaError(f"{LIB_PATH} is missing — the CUDA extension is not built and there is no fallback; "
+                                "run `python -c 'import __graft_entry__ as g; g.build()'`")
+        L = C.CDLL(LIB_PATH)
+        vp, u64, u32, i32, f32p = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.POINTER(C.c_float)
+        L.tray_cuda_device_count.restype = i32
+        L.tray_cuda_abi_version.restype = C.c_uint
+        L.tray_cuda_last_error.restype = C.c_char_p
+        L.tray_cuda_scene_create.restype = i32
+        L.tray_cuda_scene_create.argtypes = [vp, u64, vp, u64, u32, vp, u32, u32, i32, C.POINTER(vp)]
+        L.tray_cuda_scene_destroy.argtypes = [vp]
+        L.tray_cuda_scene_destroy.restype = None
+        L.tray_cuda_scene_info.restype = i32
+        L.tray_cuda_scene_info.argtypes = [vp, C.POINTER(SceneInfo)]
+        L.tray_cuda_trace.restype = i32
+        L.tray_cuda_trace.argtypes = [vp, vp, u64, vp, f32p, f32p]
+        L.tray_cuda_trace_device.restype = i32
+        L.tray_cuda_trace_device.argtypes = [vp, vp, u64, vp, vp, f32p]
+        L.tray_cuda_render.restype = i32
+        L.tray_cuda_render.argtypes = [vp, C.POINTER(TrayView), u32, u32, u32, u32, u32, u32, f32p, f32p]
+        L.tray_cuda_shard_pixels.restype = u64
+        L.tray_cuda_shard_pixels.argtypes = [u32, u32, u32, u32]
+        L.tray_cuda_frame_download.restype = i32
+        L.tray_cuda_frame_download.argtypes = [vp, vp, vp, vp, vp]
+        L.tray_cuda_frame_device_ptrs.restype = i32
+        L.tray_cuda_frame_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+        L.tray_cuda_sync.restype = i32
+        L.tray_cuda_sync.argtypes = [vp]
+        L.tray_cuda_counters.restype = i32
+        L.tray_cuda_counters.argtypes = [vp, C.POINTER(Counters), C.POINTER(Counters)]
+        L.tray_cuda_set_counting.restype = i32
+        L.tray_cuda_set_counting.argtypes = [vp, i32]
+        L.tray_cuda_start.restype = i32
+        L.tray_cuda_start.argtypes = [vp, u64, vp, u64, vp, u64, u32, u32, i32, C.POINTER(TrayView), u32, u32,
+                                      C.c_float, i32, i32, i32, f32p, f32p, C.POINTER(u32)]
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise TrayCudaError(f"tray_cuda error {rc}: {lib().tray_cuda_last_error().decode(errors='replace')}")
+
+
+def device_count() -> int:
+    return lib().tray_cuda_device_count()
+
+
+def shard_pixels(w: int, h: int, shard: int = 0, shards: int = 1) -> int:
+    return lib().tray_cuda_shard_pixels(w, h, shard, shards)
+
+
+class TrayCudaScene:
+    """A CWBVH resident on one GPU.  Batch-grain `Traversable` (reference traversable/src/lib.rs:13-28):
+    `traverse(rays) -> hits`, plus the frame operator of the render loop (reference src/rt_cpu/rt_cpu.rs:35-91)."""
+
+    def __init__(self, bvh_bytes, tri_bytes, tri_stride=48, blas_offsets=None, tlas_start=0, device=0):
+        nodes = _as_u8(bvh_bytes)
+        tris = _as_u8(tri_bytes)
+        if nodes.size % 80:
+            raise ValueError("bvh_bytes length is not a multiple of 80")        # reference src/rt_gpu/mod.rs:70,105
+        if tris.size % tri_stride:
+            raise ValueError("tri_bytes length is not a multiple of tri_stride")  # reference src/rt_gpu/mod.rs:86,107
+        blas = None if blas_offsets is None else np.ascontiguousarray(blas_offsets, dtype=np.uint32)
+        h = C.c_void_p()
+        _check(lib().tray_cuda_scene_create(nodes.ctypes.data, nodes.size // 80, tris.ctypes.data, tris.size // tri_stride,
+                                            tri_stride, None if blas is None else blas.ctypes.data,
+                                            0 if blas is None else blas.size, tlas_start, device, C.byref(h)))
+        self._h = h
+        self.tri_stride = tri_stride
+        self.frame_size = None
+
+    @classmethod
+    def from_packed(cls, p, device=0) -> "TrayCudaScene":
+        return cls(p.bvh_bytes, p.tri_bytes, p.tri_stride, p.blas_offsets if p.use_tlas else None, p.tlas_start, device)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
+            _lib.tray_cuda_scene_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def info(self) -> dict:
+        i = SceneInfo()
+        _check(lib().tray_cuda_scene_info(self._h, C.byref(i)))
+        return i.as_dict()
+
+    # ---- Traversable::traverse at batch grain -----------------------------------------------
+    def traverse(self, rays: np.ndarray, timings: dict | None = None) -> np.ndarray:
+        rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
+        hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
+        k, t = C.c_float(), C.c_float()
+        _check(lib().tray_cuda_trace(self._h, rays.ctypes.data, rays.shape[0], hits.ctypes.data, C.byref(k), C.byref(t)))
+        if timings is not None:
+            timings["ms_kernel"], timings["ms_total"] = k.value, t.value
+        return hits
+
+    def traverse_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, stream: int = 0, timed: bool = False):
+        k = C.c_float()
+        _check(lib().tray_cuda_trace_device(self._h, d_rays_ptr, n, d_hits_ptr, stream or None, C.byref(k) if timed else None))
+        return k.value if timed else None
+
+    def set_counting(self, on: bool):
+        _check(lib().tray_cuda_set_counting(self._h, int(on)))
+
+    def counters(self):
+        a, b = Counters(), Counters()
+        _check(lib().tray_cuda_counters(self._h, C.byref(a), C.byref(b)))
+        return a.as_dict(), b.as_dict()
+
+    # ---- frame operator ------------------------------------------------------------------------
+    def render(self, view: TrayView, width: int, height: int, frame_count: int = 0, flags: int = RENDER_BOUNCE | RENDER_RGBA,
+               shard: int = 0, shards: int = 1, timed: bool = True):
+        a, b = C.c_float(), C.c_float()
+        _check(lib().tray_cuda_render(self._h, C.byref(view), width, height, frame_count, flags, shard, shards,
+                                      C.byref(a) if timed else None, C.byref(b) if timed else None))
+        self.frame_size = (width, height)
+        return (a.value, b.value) if timed else None
+
+    def download(self, primary=False, bounce=False, bounce_rays=False, rgba=False, into: dict | None = None) -> dict:
+        w, h = self.frame_size
+        out = into if into is not None else {}
+        def buf(name, want, dtype, shape):
+            if not want:
+                return None
+            if name not in out:
+                out[name] = np.zeros(shape, dtype=dtype)
+            return out[name]
+        p = buf("primary", primary, HIT_DTYPE, w * h)
+        b = buf("bounce", bounce, HIT_DTYPE, w * h)
+        r = buf("bounce_rays", bounce_rays, RAY_DTYPE, w * h)
+        g = buf("rgba", rgba, np.uint8, (h, w, 4))
+        _check(lib().tray_cuda_frame_download(self._h, None if p is None else p.ctypes.data, None if b is None else b.ctypes.data,
+                                              None if r is None else r.ctypes.data, None if g is None else g.ctypes.data))
+        return out
+
+    def frame_device_ptrs(self):
+        a, b, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _check(lib().tray_cuda_frame_device_ptrs(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def sync(self):
+        _check(lib().tray_cuda_sync(self._h))
+
+
+def start(bvh_bytes, instance_bytes, tri_bytes, tlas_start, view: TrayView, width=1920, height=1080, render_time=1.0,
+          benchmark=True, animate=False, use_tlas=False, tri_stride=48, device=0):
+    """`rt_gpu_software::start(.., bvh_bytes, instance_bytes, tri_bytes, tlas_start) -> f32`
+    (reference src/rt_gpu/rt_gpu_software.rs:24-32).  Returns (min_ms, mean_ms, frames); the reference returns min_ms."""
+    nodes = _as_u8(bvh_bytes)
+    inst = _as_u8(instance_bytes)
+    tris = _as_u8(tri_bytes)
+    mn, mean, frames = C.c_float(), C.c_float(), C.c_uint32()
+    _check(lib().tray_cuda_start(nodes.ctypes.data, nodes.size, inst.ctypes.data, inst.size, tris.ctypes.data, tris.size,
+                                 tri_stride, tlas_start, int(use_tlas), C.byref(view), width, height, float(render_time),
+                                 int(benchmark), int(animate), device, C.byref(mn), C.byref(mean), C.byref(frames)))
+    return mn.value, mean.value, frames.value
