@@ -57,6 +57,7 @@ struct TraceParams {
     unsigned long long* __restrict__ cursor;      // work cursor
     unsigned long long* __restrict__ counters;    // rays, nodes, tris, instances, hits (COUNT builds)
     uint32_t* __restrict__ overflow;
+    uint32_t k4b;                                 // 0x4B000000, passed at run time (see byte_f32)
     uint32_t refill_min;                          // idle lanes needed before a partial warp refills
     uint32_t tri_weight;                          // vote: triangle phase when n_tri * tri_weight >= n_node
 };
@@ -80,8 +81,17 @@ __device__ __forceinline__ void normalize3(float& x, float& y, float& z) {   // 
 }
 // byte J of w as an exact float: PRMT builds 0x4B0000bb = 2^23 + byte, FADD removes 2^23 (no I2F: the
 // conversion pipe is quarter-rate).
-template <int J> __device__ __forceinline__ float byte_f32(uint32_t w) {
-    return __fsub_rn(__uint_as_float(__byte_perm(w, 0x4B000000u, 0x7440 + J)), 8388608.0f);
+// `k4b` must be a RUNTIME register holding 0x4B000000 (it comes in through the kernel parameters): SASS PRMT
+// takes one immediate, and with the selector as that immediate no per-use MOV of the selector is needed.
+template <int J> __device__ __forceinline__ float byte_f32(uint32_t w, uint32_t k4b) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(k4b), "n"(0x7440 + J));
+    return __fsub_rn(__uint_as_float(r), 8388608.0f);
+}
+template <int J> __device__ __forceinline__ uint32_t byte_u32(uint32_t w) {
+    uint32_t r;
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "n"(0x4440 + J));
+    return r;
 }
 
 // ---- per-ray constants ---------------------------------------------------------------------------
@@ -104,20 +114,20 @@ __device__ __forceinline__ void prepare_ray(RayConst& r, float ox, float oy, flo
 template <int J>
 __device__ __forceinline__ uint32_t child_test(uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz,
                                                float ax, float ay, float az, float bx, float by, float bz, float tmax,
-                                               uint32_t child_bits4, uint32_t bit_index4) {
+                                               uint32_t child_bits4, uint32_t bit_index4, uint32_t k4b) {
     // tmin3 = q_near * adj_inv + adj_org, tmax3 = q_far * adj_inv + adj_org: mul, then add (query.hlsl:285-286)
-    const float tnx = add(mul(byte_f32<J>(nx), ax), bx), tfx = add(mul(byte_f32<J>(fx), ax), bx);
-    const float tny = add(mul(byte_f32<J>(ny), ay), by), tfy = add(mul(byte_f32<J>(fy), ay), by);
-    const float tnz = add(mul(byte_f32<J>(nz), az), bz), tfz = add(mul(byte_f32<J>(fz), az), bz);
+    const float tnx = add(mul(byte_f32<J>(nx, k4b), ax), bx), tfx = add(mul(byte_f32<J>(fx, k4b), ax), bx);
+    const float tny = add(mul(byte_f32<J>(ny, k4b), ay), by), tfy = add(mul(byte_f32<J>(fy, k4b), ay), by);
+    const float tnz = add(mul(byte_f32<J>(nz, k4b), az), bz), tfz = add(mul(byte_f32<J>(fz, k4b), az), bz);
     const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), BOX_EPS_);      // query.hlsl:288
     const float tfar = fminf(fminf(fminf(tfx, tfy), tfz), tmax);          // query.hlsl:289
-    const uint32_t child_bits = (child_bits4 >> (8 * J)) & 0xffu;
-    const uint32_t bit_index = (bit_index4 >> (8 * J)) & 0xffu;
-    return tmin <= tfar ? (child_bits << bit_index) : 0u;                 // query.hlsl:291-298
+    // child_bits << bit_index (query.hlsl:291-298); bit_index bytes are < 32, so the shifter's wrap is harmless
+    const uint32_t contrib = byte_u32<J>(child_bits4) << ((bit_index4 >> (8 * J)) & 31u);
+    return tmin <= tfar ? contrib : 0u;
 }
 
 __device__ __forceinline__ uint32_t node_test(const RayConst& r, float tmax, const uint4& n0, const uint4& n1,
-                                              const uint4& n2, const uint4& n3, const uint4& n4) {
+                                              const uint4& n2, const uint4& n3, const uint4& n4, uint32_t k4b) {
     const uint32_t e = n0.w;
     // adj_inv = 2^(e-127) * inv_dir ; adj_org = (p - origin) * inv_dir  (CPU path: cached reciprocal; SURVEY §8c vi)
     const float ax = mul(__uint_as_float((e & 0xffu) << 23), r.ix);
@@ -141,10 +151,10 @@ __device__ __forceinline__ uint32_t node_test(const RayConst& r, float tmax, con
         const uint32_t nx = sx ? hix : lox, fx = sx ? lox : hix;                   // query.hlsl:266-273
         const uint32_t ny = sy ? hiy : loy, fy = sy ? loy : hiy;
         const uint32_t nz = sz ? hiz : loz, fz = sz ? loz : hiz;
-        mask |= child_test<0>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4);
-        mask |= child_test<1>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4);
-        mask |= child_test<2>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4);
-        mask |= child_test<3>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4);
+        mask |= child_test<0>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b);
+        mask |= child_test<1>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b);
+        mask |= child_test<2>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b);
+        mask |= child_test<3>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b);
     }
     return mask;
 }
@@ -280,12 +290,18 @@ __device__ __forceinline__ uchar4 shade(float col) {                           /
 }
 
 // ---- the kernel ---------------------------------------------------------------------------------
+// Per-lane state is kept NORMALISED between steps: a lane is exactly one of
+//   TRI   tri_y != 0                         next action: test one triangle (or enter one TLAS instance)
+//   NODE  tri_y == 0, cur_y has node bits    next action: fetch + test one node
+//   IDLE  tri_y == 0, cur_y == 0             no ray; waits for the next refill
+// so one pair of ballots per iteration drives everything (refill, phase vote, exit).
 template <int SRC, bool TLAS, bool COUNT, int TRI_STRIDE>
 __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
     uint2 spill[STACK_SPILL];
     const unsigned lane = threadIdx.x & 31u;
     uint2* const my_stack = s_stack + threadIdx.x;
+    const uint32_t k4b = P.k4b;
 
     RayConst r;
     float best_t = 0.f;
@@ -294,8 +310,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
     int sp = 0;
     uint32_t tlas_sp = INVALID, bvh_off = 0;
     unsigned long long item = 0;
-    uint32_t px = 0, py = 0;
-    bool active = false;
     bool exhausted = false;                      // warp-uniform
     unsigned long long c_rays = 0, c_nodes = 0, c_tris = 0, c_insts = 0, c_hits = 0;
 
@@ -305,99 +319,97 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
         else { atomicOr(P.overflow, 1u); return; }
         sp++;
     };
-    auto pop = [&]() -> uint2 {
-        sp--;
-        return sp < STACK_SMEM ? my_stack[sp * BLOCK_THREADS] : spill[sp - STACK_SMEM];
+    // called when the lane has neither triangles nor nodes left in hand: pop the stack, or retire the ray
+    // (query.hlsl:417-427; tlas:480-486; the popped-triangle-group case is query.hlsl:389-393)
+    auto pop_or_retire = [&]() {
+        if (sp == 0) {
+            tray_hit h;
+            h.t = best_prim != INVALID ? best_t : __int_as_float(0x7f800000);   // RayHit::none()
+            h.prim = best_prim;
+            P.hits_out[item] = h;
+            if (SRC != SRC_BUFFER && P.rgba_out) {
+                float col;
+                if (SRC == SRC_PRIMARY) col = __fdiv_rn(1.0f, h.t);                                  // rt_cpu.rs:59
+                else col = h.t < F32_MAX_ ? __fdiv_rn(h.t, add(1.0f, h.t)) : 1.0f;                   // rt_cpu.rs:82-87
+                P.rgba_out[item] = shade(col);
+            }
+            if (COUNT && best_prim != INVALID) c_hits++;
+            cur_x = 0; cur_y = 0;                                                                    // IDLE
+        } else {
+            if (TLAS && (uint32_t)sp == tlas_sp) { tlas_sp = INVALID; bvh_off = P.tlas_start; }
+            sp--;
+            const uint2 e = sp < STACK_SMEM ? my_stack[sp * BLOCK_THREADS] : spill[sp - STACK_SMEM];
+            if (e.y & 0xff000000u) { cur_x = e.x; cur_y = e.y; }
+            else { tri_x = e.x; tri_y = e.y; cur_x = 0; cur_y = 0; }
+        }
     };
 
     for (;;) {
+        const bool want_tri = tri_y != 0u;
+        const bool want_node = !want_tri && cur_y >= 0x01000000u;
+        const unsigned m_tri = __ballot_sync(FULL, want_tri), m_node = __ballot_sync(FULL, want_node);
+        const unsigned busy = m_tri | m_node;
+
         // ---- refill idle lanes from the global cursor (persistent warps + ray replacement) ----
-        const unsigned idle = __ballot_sync(FULL, !active);
-        if (idle != 0u && !exhausted && ((unsigned)__popc(idle) >= P.refill_min || idle == FULL)) {
-            const int n_idle = __popc(idle);
-            const int leader = __ffs(idle) - 1;
-            unsigned long long base = 0;
-            if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)n_idle);
-            base = __shfl_sync(FULL, base, leader);
-            if (base + (unsigned long long)n_idle >= P.n_work) exhausted = true;
-            if (!active) {
-                item = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
-                if (item < P.n_work) {
-                    float ox, oy, oz, dx, dy, dz, tmin = 0.0f, tmax = F32_MAX_;
-                    bool go = true;
-                    if (SRC == SRC_BUFFER) {
-                        const float4* rp = reinterpret_cast<const float4*>(P.rays_in + item);
-                        const float4 a = __ldg(rp), b = __ldg(rp + 1);
-                        ox = a.x; oy = a.y; oz = a.z; tmin = a.w; dx = b.x; dy = b.y; dz = b.z; tmax = b.w;
-                    } else {
-                        go = item_to_pixel(P, item, px, py);
-                        if (go) {
-                            primary_dir(P, px, py, dx, dy, dz);
-                            ox = P.view.eye[0]; oy = P.view.eye[1]; oz = P.view.eye[2];
-                            if (SRC == SRC_BOUNCE) {
-                                const tray_hit ph = P.primary_in[item];
-                                tray_ray br; br.origin[0] = br.origin[1] = br.origin[2] = br.tmin = 0.f;
-                                br.dir[0] = br.dir[1] = br.dir[2] = br.tmax = 0.f;
-                                if (ph.t < F32_MAX_) {                                   // rt_cpu.rs:61
-                                    float bx, by, bz, ex, ey, ez;
-                                    bounce_ray<TRI_STRIDE>(P, px, py, dx, dy, dz, ph.t, ph.prim, bx, by, bz, ex, ey, ez);
-                                    ox = bx; oy = by; oz = bz; dx = ex; dy = ey; dz = ez;
-                                    br.origin[0] = ox; br.origin[1] = oy; br.origin[2] = oz; br.tmin = 0.f;
-                                    br.dir[0] = dx; br.dir[1] = dy; br.dir[2] = dz; br.tmax = F32_MAX_;
-                                } else {
-                                    go = false;
-                                    tray_hit miss; miss.t = __int_as_float(0x7f800000); miss.prim = INVALID;
-                                    P.hits_out[item] = miss;
-                                    if (P.rgba_out) P.rgba_out[item] = shade(__fdiv_rn(1.0f, ph.t));   // rt_cpu.rs:59
+        if (busy != FULL) {
+            if (!exhausted && ((unsigned)__popc(~busy) >= P.refill_min || busy == 0u)) {
+                const unsigned idle = ~busy;
+                const int n_idle = __popc(idle);
+                const int leader = __ffs(idle) - 1;
+                unsigned long long base = 0;
+                if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)n_idle);
+                base = __shfl_sync(FULL, base, leader);
+                if (base + (unsigned long long)n_idle >= P.n_work) exhausted = true;
+                if ((idle >> lane) & 1u) {
+                    item = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
+                    if (item < P.n_work) {
+                        float ox, oy, oz, dx, dy, dz, tmin = 0.0f, tmax = F32_MAX_;
+                        bool go = true;
+                        if (SRC == SRC_BUFFER) {
+                            const float4* rp = reinterpret_cast<const float4*>(P.rays_in + item);
+                            const float4 a = __ldg(rp), b = __ldg(rp + 1);
+                            ox = a.x; oy = a.y; oz = a.z; tmin = a.w; dx = b.x; dy = b.y; dz = b.z; tmax = b.w;
+                        } else {
+                            uint32_t px, py;
+                            go = item_to_pixel(P, item, px, py);
+                            if (go) {
+                                primary_dir(P, px, py, dx, dy, dz);
+                                ox = P.view.eye[0]; oy = P.view.eye[1]; oz = P.view.eye[2];
+                                if (SRC == SRC_BOUNCE) {
+                                    const tray_hit ph = P.primary_in[item];
+                                    tray_ray br; br.origin[0] = br.origin[1] = br.origin[2] = br.tmin = 0.f;
+                                    br.dir[0] = br.dir[1] = br.dir[2] = br.tmax = 0.f;
+                                    if (ph.t < F32_MAX_) {                                   // rt_cpu.rs:61
+                                        float bx, by, bz, ex, ey, ez;
+                                        bounce_ray<TRI_STRIDE>(P, px, py, dx, dy, dz, ph.t, ph.prim, bx, by, bz, ex, ey, ez);
+                                        ox = bx; oy = by; oz = bz; dx = ex; dy = ey; dz = ez;
+                                        br.origin[0] = ox; br.origin[1] = oy; br.origin[2] = oz; br.tmin = 0.f;
+                                        br.dir[0] = dx; br.dir[1] = dy; br.dir[2] = dz; br.tmax = F32_MAX_;
+                                    } else {
+                                        go = false;
+                                        tray_hit miss; miss.t = __int_as_float(0x7f800000); miss.prim = INVALID;
+                                        P.hits_out[item] = miss;
+                                        if (P.rgba_out) P.rgba_out[item] = shade(__fdiv_rn(1.0f, ph.t));   // rt_cpu.rs:59
+                                    }
+                                    if (P.rays_out) P.rays_out[item] = br;
                                 }
-                                if (P.rays_out) P.rays_out[item] = br;
                             }
                         }
-                    }
-                    if (go) {
-                        prepare_ray(r, ox, oy, oz, dx, dy, dz, tmin);
-                        best_t = tmax; best_prim = INVALID;
-                        cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp = 0;   // root group, query.hlsl:343
-                        tlas_sp = INVALID; bvh_off = TLAS ? P.tlas_start : 0u;
-                        active = true;
-                        if (COUNT) c_rays++;
+                        if (go) {
+                            prepare_ray(r, ox, oy, oz, dx, dy, dz, tmin);
+                            best_t = tmax; best_prim = INVALID;
+                            cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp = 0;   // root group, query.hlsl:343
+                            tlas_sp = INVALID; bvh_off = TLAS ? P.tlas_start : 0u;
+                            if (COUNT) c_rays++;
+                        }
                     }
                 }
+                continue;                                    // re-vote with the new rays
             }
-        }
-        if (__ballot_sync(FULL, active) == 0u) {
-            if (exhausted) break;
-            continue;
-        }
-
-        // ---- cheap transitions: pop the stack, or retire the ray (query.hlsl:417-427) ----
-        if (active && tri_y == 0u && (cur_y & 0xff000000u) == 0u) {
-            if (sp == 0) {
-                tray_hit h;
-                h.t = best_prim != INVALID ? best_t : __int_as_float(0x7f800000);   // RayHit::none()
-                h.prim = best_prim;
-                P.hits_out[item] = h;
-                if (SRC != SRC_BUFFER && P.rgba_out) {
-                    float col;
-                    if (SRC == SRC_PRIMARY) col = __fdiv_rn(1.0f, h.t);                                  // rt_cpu.rs:59
-                    else col = h.t < F32_MAX_ ? __fdiv_rn(h.t, add(1.0f, h.t)) : 1.0f;                   // rt_cpu.rs:82-87
-                    P.rgba_out[item] = shade(col);
-                }
-                if (COUNT && best_prim != INVALID) c_hits++;
-                active = false;
-            } else {
-                if (TLAS && (uint32_t)sp == tlas_sp) { tlas_sp = INVALID; bvh_off = P.tlas_start; }     // tlas:480-486
-                const uint2 e = pop();
-                cur_x = e.x; cur_y = e.y;
-                if ((cur_y & 0xff000000u) == 0u) { tri_x = cur_x; tri_y = cur_y; cur_x = 0; cur_y = 0; }  // query.hlsl:389-393
-            }
+            if (busy == 0u) break;                           // cursor exhausted and nothing in flight
         }
 
         // ---- warp vote: node step or triangle step ----
-        const bool want_tri = active && tri_y != 0u;
-        const bool want_node = active && tri_y == 0u && (cur_y & 0xff000000u) != 0u;
-        const unsigned m_tri = __ballot_sync(FULL, want_tri), m_node = __ballot_sync(FULL, want_node);
-        if ((m_tri | m_node) == 0u) continue;
         const bool tri_phase = m_node == 0u || (unsigned)__popc(m_tri) * P.tri_weight >= (unsigned)__popc(m_node);
 
         if (!tri_phase) {
@@ -411,10 +423,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
                 const uint4* np = P.nodes + (size_t)(bvh_off + cur_x + rel) * 5u;              // :373, tlas:383
                 const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                 if (COUNT) c_nodes++;
-                const uint32_t hitmask = node_test(r, best_t, n0, n1, n2, n3, n4);             // :380
+                const uint32_t hitmask = node_test(r, best_t, n0, n1, n2, n3, n4, k4b);        // :380
                 cur_x = n1.x; tri_x = n1.y;                                                    // :383-384
                 cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386
                 tri_y = hitmask & 0x00ffffffu;                                                 // :387
+                if (tri_y == 0u && cur_y < 0x01000000u) pop_or_retire();
             }
         } else {
             if (want_tri) {
@@ -433,6 +446,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
                     if (COUNT) c_tris++;
                     const float t = tri_test<TRI_STRIDE>(r, best_t, P.tris, g);
                     if (t < best_t) { best_t = t; best_prim = g; }          // CPU tie rule: first of equal t wins (§8a a11)
+                    if (tri_y == 0u && cur_y < 0x01000000u) pop_or_retire();
                 }
             }
         }

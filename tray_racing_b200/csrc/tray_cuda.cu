@@ -56,7 +56,7 @@ struct tray_scene {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
     bool counting = false;
-    uint32_t refill_min = 8, tri_weight = 2;
+    uint32_t refill_min = 8, tri_weight = 4;
     int blocks_per_sm[3] = { 0, 0, 0 };
     // ray-batch staging
     tray_ray* d_rays = nullptr; tray_hit* d_hits = nullptr; uint64_t batch_cap = 0;
@@ -103,7 +103,7 @@ void base_params(const tray_scene* s, TraceParams& P) {
     memset(&P, 0, sizeof P);
     P.nodes = s->d_nodes; P.tris = s->d_tris; P.blas_offsets = s->d_blas; P.tlas_start = s->tlas_start;
     P.cursor = s->d_cursor; P.overflow = s->d_overflow;
-    P.refill_min = s->refill_min; P.tri_weight = s->tri_weight;
+    P.refill_min = s->refill_min; P.tri_weight = s->tri_weight; P.k4b = 0x4B000000u;
     P.shard_count = 1;
 }
 
@@ -193,7 +193,7 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
     s->device = device; s->n_nodes = n_nodes; s->n_tris = n_tris; s->tri_stride = tri_stride;
     s->n_instances = n_instances; s->tlas_start = tlas_start; s->tlas = n_instances > 0;
     s->refill_min = (uint32_t)env_int("TRAY_CUDA_REFILL_MIN", 8);
-    s->tri_weight = (uint32_t)env_int("TRAY_CUDA_TRI_WEIGHT", 2);
+    s->tri_weight = (uint32_t)env_int("TRAY_CUDA_TRI_WEIGHT", 4);
     int rc = TRAY_OK;
     auto body = [&]() -> int {
         cudaDeviceProp prop;
