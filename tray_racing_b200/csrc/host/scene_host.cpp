@@ -237,13 +237,18 @@ void gen_caldera(tray_mesh* m, uint64_t seed, double size) {
     for (uint32_t k = 0; k < blobs; k++) {
         g.begin_object();
         uint64_t want = (uint64_t)(wgt[k] / wsum * (double)remaining);
-        int nl = std::max(3, (int)std::sqrt((double)want / 4.0));
+        int nl = std::max(3, (int)std::lround((1.0 + std::sqrt(1.0 + (double)want)) / 2.0));   // 4 nl (nl - 1) ~ want
         double s = r.logrange(1.0, 10.0);
         double x = r.range(-195, 195), z = r.range(-195, 195);
         double y = -30 + 40 * fbm(x * 0.012, z * 0.012, seed + 99, 6) + (r.uni() < 0.8 ? s * 0.7 : r.range(5, 28));
         uint64_t sd = r.next();
         g.sphere({ x, y, z }, s, nl, 2 * nl, [sd](V3 d) { return 0.3 * (vnoise(d.x * 4 + 3, d.z * 4 + d.y * 3.1, sd) - 0.5); });
     }
+    while (m->count() < target) {   // top up the last object, then trim to the exact count
+        double s = r.logrange(1.0, 6.0);
+        g.sphere({ r.range(-150, 150), r.range(0, 20), r.range(-150, 150) }, s, 40, 80, [](V3) { return 0.0; });
+    }
+    truncate_to(m, target);
     set_cam(m, { -40.0, 32.0, 84.0 }, { 30.0, -30.0, 0.0 }, 75);
 }
 

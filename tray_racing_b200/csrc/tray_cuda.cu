@@ -212,6 +212,7 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
         CU(cudaMemsetAsync(s->d_overflow, 0, 4, s->stream));
         s->device_bytes = nb + tb + (size_t)n_instances * 4;
         if (n_nodes) CU(cudaMemcpyAsync(s->d_nodes, nodes, (size_t)n_nodes * 80, cudaMemcpyHostToDevice, s->stream));
+        else CU(cudaMemsetAsync(s->d_nodes, 0, 80, s->stream));   // empty scene: a root with no children, every ray misses
         if (n_tris) CU(cudaMemcpyAsync(s->d_tris, tris, (size_t)n_tris * tri_stride, cudaMemcpyHostToDevice, s->stream));
         if (n_instances) CU(cudaMemcpyAsync(s->d_blas, blas_offsets, (size_t)n_instances * 4, cudaMemcpyHostToDevice, s->stream));
         // keep the node array hot in the 126 MB L2: persisting access-policy window on the scene stream
