@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py — the headline measurement of the tray_cuda backend (contract: see the task's bench.py section).
+
+Metric (BASELINE.json): Mrays/s, primary + 1-spp diffuse-bounce rays, on the 2.88 M-triangle hairball-like scene
+(config C3), with the achieved fraction of the memory roofline and the host-CPU restatement of rt_cpu beside it.
+
+A "step" is one frame of the reference's render loop body (reference src/rt_cpu/rt_cpu.rs:35-91): generate the
+primary rays of this rank's image tiles, closest-hit traversal, one cosine bounce ray per hit pixel, second
+traversal, RGBA8 — then the framebuffer gather to rank 0 (the path's one exchange step) and its assembly.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (under torchrun for N > 1)
+  python bench.py --impl reference ...                          the reference's CPU algorithm (oracle port) on host cores
+
+Weak scaling: the frame holds ~N x 1920x1080 pixels (same camera, finer sampling), tiles interleaved over N ranks,
+BVH replicated, so every GPU traces the same number of rays as at N = 1.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCENE, SEED = "hairball", 3
+BASE_W, BASE_H = 1920, 1080
+METRIC, UNIT = "Mrays/s primary+diffuse", "Mrays/s"
+TRI_STRIDE = 48
+
+
+def frame_size(n_gpus: int):
+    s = n_gpus ** 0.5
+    return int(round(BASE_W * s / 8)) * 8, int(round(BASE_H * s / 8)) * 8
+
+
+def workload_name(w, h, n):
+    return f"C3 hairball-like 2.88M-tri soup, {w}x{h} ({n} x 1920x1080 px), primary + 1spp diffuse bounce, ploc-style CWBVH"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.2 and len(r) >= 9] or [r for _, r in self.rows if len(r) >= 9]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        return json.load(open(p))["primary_kernel_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def build_scene(nthreads=0):
+    from tray_racing_b200 import host
+    mesh = host.Mesh.generate(SCENE, SEED, 1.0)
+    packed = host.PackedScene(mesh, use_tlas=False, tri_stride=TRI_STRIDE, nthreads=nthreads)
+    return mesh, packed
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_run(packed, mesh, seconds_budget: float, frames_min: int, w=960, h=540):
+    """The oracle (C restatement of rt_cpu) timed on this host's cores on a bounded sample of the workload:
+    the same scene and camera at w x h (a 2x2-decimated 1080p frame), primary + bounce, all host threads."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from tray_racing_b200 import host
+    orc = ob.Oracle.from_packed(packed)
+    view = host.view_from_camera(mesh.camera, w, h)
+    threads = ob.lib().orc_max_threads()
+    orc.render(view, w, h, 0)                      # warm-up frame (page in the BVH)
+    times, rays = [], 0
+    t_start = time.perf_counter()
+    while len(times) < frames_min or (time.perf_counter() - t_start) < seconds_budget:
+        t0 = time.perf_counter()
+        r = orc.render(view, w, h, 0)
+        times.append(time.perf_counter() - t0)
+        rays = r["primary_totals"]["rays"] + r["bounce_totals"]["rays"]
+        if len(times) >= 64:
+            break
+    mean = sum(times) / len(times)
+    return {"value": rays / mean / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{len(times)} frames of the same scene+camera at {w}x{h} ({rays} rays/frame, primary+bounce), mean frame time",
+            "ms_per_frame": mean * 1e3, "rays_per_frame": rays}, times
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU algorithm for this path.  The Rust reference cannot be built in this
+    image (no cargo/rustc; arithmetic in an un-vendored crate), so this is the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    mesh, packed = build_scene()
+    w, h = frame_size(args.gpus)
+    sw, sh = 960, 540
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    from tray_racing_b200 import host
+    orc = ob.Oracle.from_packed(packed)
+    view = host.view_from_camera(mesh.camera, sw, sh)
+    threads = ob.lib().orc_max_threads()
+    for _ in range(args.warmup):
+        orc.render(view, sw, sh, 0)
+    t0 = time.perf_counter()
+    rays = 0
+    for _ in range(args.steps):
+        r = orc.render(view, sw, sh, 0)
+        rays += r["primary_totals"]["rays"] + r["bounce_totals"]["rays"]
+    dt = time.perf_counter() - t0
+    val = rays / dt / 1e6
+    sample = f"each step = one {sw}x{sh} frame (2x2-decimated 1080p) of the same scene+camera, primary+bounce"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(w, h, args.gpus), "sample": sample, "n_tris": packed.n_tris, "n_nodes": packed.n_nodes},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from tray_racing_b200 import cuda, host
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs `python -m torch.distributed.run --nproc-per-node {args.gpus} bench.py ...`")
+        raise SystemExit(f"WORLD_SIZE {world} != --gpus {args.gpus}")
+    if not torch.cuda.is_available() or cuda.device_count() == 0:
+        raise SystemExit("bench.py needs a CUDA device: tray_cuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    ncpu = os.cpu_count() or 8
+    mesh, packed = build_scene(nthreads=max(1, ncpu // world))
+    w, h = frame_size(world)
+    view = host.view_from_camera(mesh.camera, w, h)
+    scene = cuda.TrayCudaScene.from_packed(packed, device=local_rank)
+    # one explicit (non-default) torch stream carries the kernels, the NCCL gather, the untile and the timing events
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    assert stream.cuda_stream != 0
+    scene.set_stream(stream.cuda_stream)
+    flags = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA
+    n_items = cuda.local_items(w, h, rank, world)
+    max_items = cuda.local_items(w, h, 0, world)
+
+    # one counting frame (outside the timed region): rays and algorithmic bytes per step
+    scene.render(view, w, h, 0, flags | cuda.RENDER_COUNTERS, rank, world)
+    cp, cb = scene.counters()
+    scene.render(view, w, h, 0, flags, rank, world)       # switch back to the non-counting kernels
+    _, _, d_rgba = scene.frame_device_ptrs()
+    rgba_local = torch.as_tensor(cuda.DeviceArray(d_rgba, (max_items,), "<i4", scene), device="cuda")
+    gathered = [torch.empty(max_items, dtype=rgba_local.dtype, device="cuda") for _ in range(world)] if (rank == 0 and world > 1) else None
+    frame = torch.zeros(h * w, dtype=torch.int32, device="cuda") if rank == 0 else None
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+
+    def step():
+        scene.render(view, w, h, 0, flags, rank, world, timed=False)
+        if world > 1:
+            dist.gather(rgba_local, gathered, dst=0)
+            if rank == 0:
+                for s in range(world):
+                    scene.untile_rgba(gathered[s].data_ptr(), w, h, s, world, frame.data_ptr())
+        else:
+            scene.untile_rgba(d_rgba, w, h, 0, 1, frame.data_ptr())
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        flush_buf.fill_(1)
+        step()
+    sync_all()
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    sync_all()
+    t_wall0 = time.time()
+    for k in range(args.steps):
+        flush_buf.fill_(k & 0xff)                       # L2 flush between timed iterations (not in the timed span)
+        ev[k][0].record(stream)
+        step()
+        ev[k][1].record(stream)
+    sync_all()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    rays_step = torch.tensor([cp["rays"] + cb["rays"], cp["rays"], cb["rays"]], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(rays_step, op=dist.ReduceOp.SUM)
+    total_ms = float(total_ms.item())
+    rays_all, rays_p, rays_b = (float(x) for x in rays_step.tolist())
+    value = rays_all * args.steps / (total_ms * 1e-3) / 1e6
+
+    # ---- dominant kernel alone (this rank): live CUDA-event duration of primary and bounce launches ----
+    kp, kb = [], []
+    for _ in range(max(5, min(args.steps, 20))):
+        flush_buf.fill_(3)
+        a, b = scene.render(view, w, h, 0, flags, rank, world, timed=True)
+        kp.append(a); kb.append(b)
+    kp_ms, kb_ms = sum(kp) / len(kp), sum(kb) / len(kb)
+    bytes_p = 80 * cp["nodes"] + TRI_STRIDE * cp["tris"] + 8 * cp["rays"]
+    bytes_b = 80 * cb["nodes"] + TRI_STRIDE * cb["tris"] + 8 * cb["rays"] + 8 * cp["rays"]
+    peak, peak_src = measured_peaks()
+    dominant = "primary" if kp_ms >= kb_ms else "bounce"
+    ach = (bytes_p / kp_ms if dominant == "primary" else bytes_b / kb_ms) / 1e6      # GB/s
+
+    # ---- end to end through the public API with HOST buffers (per rank: view in, its RGBA shard out) ----
+    host_rgba = torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy()
+    into = {"rgba": host_rgba}
+    e2e_steps = max(3, min(args.steps, 10))
+    scene.render(view, w, h, 0, flags, rank, world, timed=False); scene.download(rgba=True, into=into)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        scene.render(view, w, h, 0, flags, rank, world, timed=False)      # view (160 B) + frame params go in by value
+        scene.download(rgba=True, into=into)                              # untile + D2H of this rank's pixels, synchronous
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = rays_all * e2e_steps / float(e2e_s.item()) / 1e6
+
+    if rank == 0:
+        cpu_base, _ = cpu_oracle_run(packed, mesh, seconds_budget=10.0, frames_min=3) if world == 1 else (None, None)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(w, h, world), "n_tris": packed.n_tris, "n_nodes": packed.n_nodes,
+                       "working_set_mb": round(packed.working_set_bytes() / 1e6, 1), "tri_stride": TRI_STRIDE,
+                       "rays_per_step": {"primary": rays_p, "bounce": rays_b},
+                       "l2": "flushed between timed steps (256 MiB device write)", "parallelism": f"tile-sharded x{world}, BVH replicated",
+                       "exchange": "NCCL gather of RGBA8 shards to rank 0 + untile" if world > 1 else "untile only (single GPU)"},
+            "mrays_s": {"primary_kernel": cp["rays"] / kp_ms / 1e3, "bounce_kernel": (cb["rays"] / kb_ms / 1e3) if cb["rays"] else None,
+                        "note": "rank-0 shard, kernel alone, CUDA events"},
+            "roofline": {"bound": "hbm", "kernel": f"trace_kernel<{dominant}>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
+                         "algorithmic_bytes_per_launch": bytes_p if dominant == "primary" else bytes_b,
+                         "bytes_per_ray": (bytes_p / cp["rays"]) if dominant == "primary" else (bytes_b / max(1, cb["rays"])),
+                         "ms_per_launch": kp_ms if dominant == "primary" else kb_ms,
+                         "nodes_per_ray": cp["nodes"] / cp["rays"], "tris_per_ray": cp["tris"] / cp["rays"]},
+            "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 160 * world, "d2h_bytes_per_step": w * h * 4,
+                    "note": "tray_cuda_render + tray_cuda_frame_download(rgba) per rank, pinned host frame, wall clock"},
+            "gpu_launches": args.steps * world * 3,     # per step: 2 traversal kernels per rank + one untile per shard on rank 0
+            "clocks": clocks,
+        }
+        if cpu_base is not None:
+            line["cpu_baseline"] = cpu_base
+        print(json.dumps(line), flush=True)
+    scene.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -176,7 +176,8 @@ int tray_cuda_trace_device(tray_scene* scene, const tray_ray* d_rays, uint64_t n
 /* Render the pixels of one frame that belong to shard `shard_index` of `shard_count`
  * (interleaved 32x8-pixel tiles: tile k belongs to shard k % shard_count; 0/1 = whole frame).
  * Rays are generated on the device from `view` (rt_cpu.rs:38-55); bounce rays per rt_cpu.rs:61-80.
- * Results stay on the device (fetch them with tray_cuda_frame_download); returns after the
+ * Results stay on the device in compact per-shard buffers (tile order; every shard's buffers have the size of
+ * shard 0's, so they can be gathered) — fetch them with tray_cuda_frame_download; returns after the
  * kernels have been enqueued on the scene stream unless a timing pointer is non-NULL.
  *   ms_primary / ms_bounce   CUDA-event time of the primary / bounce traversal kernel (NULL ok)   */
 int tray_cuda_render(tray_scene* scene, const tray_view* view, uint32_t width, uint32_t height,
@@ -187,7 +188,7 @@ int tray_cuda_render(tray_scene* scene, const tray_view* view, uint32_t width, u
 uint64_t tray_cuda_shard_pixels(uint32_t width, uint32_t height, uint32_t shard_index, uint32_t shard_count);
 
 /* Copy the last rendered frame to HOST buffers, each width*height entries in row-major pixel order
- * (pixels of other shards are left untouched).  Any pointer may be NULL.  `bounce_rays` receives the
+ * (pixels that belong to other shards are written as zero bytes).  Any pointer may be NULL.  `bounce_rays` receives the
  * generated bounce rays (tmax = 0 where the primary ray missed) so a checker can trace the very
  * same rays.                                                                                      */
 int tray_cuda_frame_download(tray_scene* scene, tray_hit* primary, tray_hit* bounce,
@@ -196,6 +197,16 @@ int tray_cuda_frame_download(tray_scene* scene, tray_hit* primary, tray_hit* bou
 /* Device pointers of the last frame's buffers, for a caller that gathers them itself (NCCL / peer
  * copy).  Layout: row-major full-frame arrays, see tray_cuda_frame_download.                        */
 int tray_cuda_frame_device_ptrs(tray_scene* scene, void** d_primary, void** d_bounce, void** d_rgba);
+
+/* Assemble a row-major width x height RGBA8 frame on the device from the compact buffer of ONE shard
+ * (`d_compact` = that shard's rgba in local order, e.g. as received from another GPU by an NCCL gather).
+ * Enqueued on the scene stream; pixels of other shards in `d_frame` are left untouched.              */
+int tray_cuda_untile_rgba(tray_scene* scene, const void* d_compact, uint32_t width, uint32_t height,
+                          uint32_t shard_index, uint32_t shard_count, void* d_frame);
+
+/* Run all subsequent work of this scene on `stream` (a cudaStream_t as void*; NULL restores the scene's own
+ * stream) — lets a host that already owns a stream (torch, NCCL) order its collectives after the kernels. */
+int tray_cuda_scene_set_stream(tray_scene* scene, void* stream);
 
 /* Wait for everything enqueued on the scene stream. */
 int tray_cuda_sync(tray_scene* scene);

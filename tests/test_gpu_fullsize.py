@@ -51,7 +51,7 @@ def test_c4_c5_properties_and_sampled_oracle(name, seed, w, h):
         acc = {}
         for s in range(8):                                                  # 8-way tile shards == whole frame
             sc.render(view, w, h, 0, flags, shard=s, shards=8)
-            sc.download(primary=True, bounce=True, into=acc)
+            sc.download(primary=True, bounce=True, into=acc, merge=True)
         for k in ("primary", "bounce"):
             assert (acc[k]["prim"] == a[k]["prim"]).all() and (bits(acc[k]["t"]) == bits(a[k]["t"])).all()
     finally:

@@ -129,7 +129,7 @@ def test_tile_shards_reassemble_the_frame(cornell):
             acc = {}
             for s in range(shards):
                 sc.render(view, w, h, 0, FLAGS, shard=s, shards=shards)
-                sc.download(primary=True, bounce=True, rgba=True, into=acc)
+                sc.download(primary=True, bounce=True, rgba=True, into=acc, merge=True)
             for k in ("primary", "bounce"):
                 assert (acc[k]["prim"] == full[k]["prim"]).all() and (bits(acc[k]["t"]) == bits(full[k]["t"])).all()
             assert (acc["rgba"] == full["rgba"]).all()

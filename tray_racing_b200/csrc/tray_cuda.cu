@@ -52,7 +52,8 @@ struct tray_scene {
     uint32_t* d_blas = nullptr;
     unsigned long long* d_cursor = nullptr;     // [0] cursor, then 2 x 5 counters
     uint32_t* d_overflow = nullptr;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;          // the stream work is enqueued on
+    cudaStream_t own_stream = nullptr;      // created with the scene
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
     bool counting = false;
@@ -170,7 +171,7 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     cudaFree(s->d_rays); cudaFree(s->d_hits);
     cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba); cudaFree(s->d_untiled);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
-    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
 
@@ -200,7 +201,8 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
         CU(cudaGetDeviceProperties(&prop, device));
         s->sm_count = prop.multiProcessorCount;
         s->l2_bytes = (uint64_t)prop.l2CacheSize;
-        CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+        s->stream = s->own_stream;
         for (auto& e : s->ev) CU(cudaEventCreate(&e));
         const size_t nb = (size_t)(n_nodes ? n_nodes : 1) * 80, tb = (size_t)(n_tris ? n_tris : 1) * tri_stride;
         CU(cudaMalloc(&s->d_nodes, nb));
@@ -254,6 +256,28 @@ int tray_cuda_scene_info(const tray_scene* s, tray_scene_info* o) {
 int tray_cuda_set_counting(tray_scene* s, int enabled) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
     if (s->counting != (enabled != 0)) { s->counting = enabled != 0; s->blocks_per_sm[0] = s->blocks_per_sm[1] = s->blocks_per_sm[2] = 0; }
+    return TRAY_OK;
+}
+
+int tray_cuda_scene_set_stream(tray_scene* s, void* stream) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    s->stream = stream ? (cudaStream_t)stream : s->own_stream;
+    return TRAY_OK;
+}
+
+int tray_cuda_untile_rgba(tray_scene* s, const void* d_compact, uint32_t w, uint32_t h, uint32_t shard, uint32_t shards, void* d_frame) {
+    if (!s || !d_compact || !d_frame) return fail(TRAY_ERR_ARG, "NULL argument");
+    if (shards == 0) shards = 1;
+    if (w == 0 || h == 0 || shard >= shards) return fail(TRAY_ERR_ARG, "bad frame size / shard");
+    CU(cudaSetDevice(s->device));
+    TraceParams P; base_params(s, P);
+    P.width = w; P.height = h; P.shard_index = shard; P.shard_count = shards; P.tiles_x = (w + 31) / 32;
+    P.n_work = local_items(w, h, shard, shards);
+    if (P.n_work == 0) return TRAY_OK;
+    tray::untile_kernel<uchar4><<<(unsigned)((P.n_work + 255) / 256), 256, 0, s->stream>>>(P, (const uchar4*)d_compact, (uchar4*)d_frame);
+    CU(cudaGetLastError());
     return TRAY_OK;
 }
 
@@ -326,10 +350,11 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     const bool want_count = (flags & TRAY_RENDER_COUNTERS) != 0;
     if (want_count != s->counting) tray_cuda_set_counting(s, want_count);
     const uint64_t items = local_items(w, h, shard, shards);
+    const uint64_t items_cap = local_items(w, h, 0, shards);   // every shard's buffers have the size of the largest (gather)
     const bool bounce = (flags & TRAY_RENDER_BOUNCE) != 0, rgba = (flags & TRAY_RENDER_RGBA) != 0;
     const bool keep_rays = (flags & TRAY_RENDER_KEEP_RAYS) != 0;
-    if (items > s->f_cap || (bounce && !s->d_bounce) || (rgba && !s->d_rgba) || (keep_rays && !s->d_brays)) {
-        const uint64_t cap = items > s->f_cap ? items : s->f_cap;
+    if (items_cap > s->f_cap || (bounce && !s->d_bounce) || (rgba && !s->d_rgba) || (keep_rays && !s->d_brays)) {
+        const uint64_t cap = items_cap > s->f_cap ? items_cap : s->f_cap;
         cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba);
         s->d_primary = nullptr; s->d_bounce = nullptr; s->d_brays = nullptr; s->d_rgba = nullptr; s->f_cap = 0;
         const uint64_t c1 = cap ? cap : 1;
@@ -407,10 +432,7 @@ int download(tray_scene* s, const T* d_src, T* host_dst) {
         CU(cudaMalloc(&s->d_untiled, bytes));
         s->untiled_cap = bytes;
     }
-    if (s->fshards > 1) {
-        // keep the caller's pixels of other shards: start from what the caller holds
-        CU(cudaMemcpyAsync(s->d_untiled, host_dst, bytes, cudaMemcpyHostToDevice, s->stream));
-    }
+    if (s->fshards > 1) CU(cudaMemsetAsync(s->d_untiled, 0, bytes, s->stream));   // pixels of other shards read as zero
     if (s->f_items) {
         const unsigned grid = (unsigned)((s->f_items + 255) / 256);
         tray::untile_kernel<T><<<grid, 256, 0, s->stream>>>(s->last_params, d_src, (T*)s->d_untiled);

@@ -21,6 +21,7 @@ EXPORTS = (
     "tray_cuda_scene_info", "tray_cuda_trace", "tray_cuda_trace_device", "tray_cuda_render",
     "tray_cuda_shard_pixels", "tray_cuda_frame_download", "tray_cuda_frame_device_ptrs", "tray_cuda_sync",
     "tray_cuda_counters", "tray_cuda_set_counting", "tray_cuda_start", "tray_cuda_last_error",
+    "tray_cuda_untile_rgba", "tray_cuda_scene_set_stream",
 )
 
 
@@ -85,6 +86,10 @@ def lib() -> C.CDLL:
         L.tray_cuda_frame_device_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
         L.tray_cuda_sync.restype = i32
         L.tray_cuda_sync.argtypes = [vp]
+        L.tray_cuda_untile_rgba.restype = i32
+        L.tray_cuda_untile_rgba.argtypes = [vp, vp, u32, u32, u32, u32, vp]
+        L.tray_cuda_scene_set_stream.restype = i32
+        L.tray_cuda_scene_set_stream.argtypes = [vp, vp]
         L.tray_cuda_counters.restype = i32
         L.tray_cuda_counters.argtypes = [vp, C.POINTER(Counters), C.POINTER(Counters)]
         L.tray_cuda_set_counting.restype = i32
@@ -175,11 +180,15 @@ class TrayCudaScene:
         _check(lib().tray_cuda_render(self._h, C.byref(view), width, height, frame_count, flags, shard, shards,
                                       C.byref(a) if timed else None, C.byref(b) if timed else None))
         self.frame_size = (width, height)
+        self.frame_shard = (shard, shards)
         return (a.value, b.value) if timed else None
 
-    def download(self, primary=False, bounce=False, bounce_rays=False, rgba=False, into: dict | None = None) -> dict:
+    def download(self, primary=False, bounce=False, bounce_rays=False, rgba=False, into: dict | None = None,
+                 merge: bool = False) -> dict:
+        """Last frame -> host arrays in row-major pixel order.  Pixels of other shards come back as zeros; with
+        merge=True only this shard's pixels of the arrays already in `into` are overwritten."""
         w, h = self.frame_size
-        out = into if into is not None else {}
+        out = into if (into is not None and not merge) else {}
         def buf(name, want, dtype, shape):
             if not want:
                 return None
@@ -192,6 +201,17 @@ class TrayCudaScene:
         g = buf("rgba", rgba, np.uint8, (h, w, 4))
         _check(lib().tray_cuda_frame_download(self._h, None if p is None else p.ctypes.data, None if b is None else b.ctypes.data,
                                               None if r is None else r.ctypes.data, None if g is None else g.ctypes.data))
+        if merge and into is not None:
+            shard, shards = self.frame_shard
+            own = shard_mask(w, h, shard, shards)
+            for k, v in out.items():
+                if k not in into:
+                    into[k] = v
+                elif k == "rgba":
+                    into[k][own.reshape(h, w)] = v[own.reshape(h, w)]
+                else:
+                    into[k][own] = v[own]
+            return into
         return out
 
     def frame_device_ptrs(self):
@@ -201,6 +221,36 @@ class TrayCudaScene:
 
     def sync(self):
         _check(lib().tray_cuda_sync(self._h))
+
+    def set_stream(self, cuda_stream: int):
+        """Enqueue this scene's work on a caller-owned cudaStream_t (0 restores the scene's own stream)."""
+        _check(lib().tray_cuda_scene_set_stream(self._h, cuda_stream or None))
+
+    def untile_rgba(self, d_compact: int, width: int, height: int, shard: int, shards: int, d_frame: int):
+        _check(lib().tray_cuda_untile_rgba(self._h, d_compact, width, height, shard, shards, d_frame))
+
+
+def shard_mask(width: int, height: int, shard: int, shards: int) -> np.ndarray:
+    """bool[h*w]: pixels owned by `shard` — 32x8-pixel tiles, tile k (row-major) belongs to shard k % shards."""
+    y, x = np.divmod(np.arange(width * height), width)
+    k = (y // 8) * ((width + 31) // 32) + x // 32
+    return (k % shards) == shard
+
+
+def local_items(width: int, height: int, shard: int = 0, shards: int = 1) -> int:
+    """Entries of a shard's compact (tile-ordered) frame buffers: its 32x8 tiles x 256."""
+    tiles = ((width + 31) // 32) * ((height + 7) // 8)
+    return 0 if shard >= tiles else ((tiles - shard + shards - 1) // shards) * 256
+
+
+class DeviceArray:
+    """Zero-copy view of device memory owned by libtray_cuda for consumers of __cuda_array_interface__
+    (torch.as_tensor(DeviceArray(...), device="cuda")) — used to hand shard buffers to NCCL."""
+
+    def __init__(self, ptr: int, shape, typestr: str, owner=None):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 3, "strides": None}
+        self._owner = owner
 
 
 def start(bvh_bytes, instance_bytes, tri_bytes, tlas_start, view: TrayView, width=1920, height=1080, render_time=1.0,
