@@ -1,9 +1,11 @@
 // traverse.cuh — sm_100a device code: 8-wide CWBVH closest-hit traversal + ray/triangle intersection.
 //
-// One kernel template serves the three ray sources of the path:
-//   SRC_BUFFER   rays read from a buffer            — Traversable::traverse at batch grain (traversable/src/lib.rs:20)
-//   SRC_PRIMARY  rays generated from the camera     — src/rt_cpu/rt_cpu.rs:38-55, rt_gpu_software.hlsl:69-80
-//   SRC_BOUNCE   1-spp cosine bounce from a hit     — src/rt_cpu/rt_cpu.rs:61-80, rt_gpu_software.hlsl:105-128
+// Three kernels make a frame (src/rt_cpu/rt_cpu.rs:35-91, rt_gpu_software.hlsl:47-144):
+//   raygen_primary_kernel  pixel -> ray, one thread per pixel, fully coalesced   — rt_cpu.rs:38-55
+//   trace_kernel           closest hit for a buffer of rays (the hot kernel)     — Traversable::traverse, batch grain
+//   raygen_bounce_kernel   hit -> 1-spp cosine bounce ray, COMPACTED to hit pixels — rt_cpu.rs:61-80
+// Ray generation is full-width SIMD work with IEEE divisions; keeping it out of the traversal kernel makes the
+// per-lane refill of that kernel two 16-byte loads, so idle lanes can be refilled eagerly.
 //
 // Execution model (B200: 148 SMs, 4 schedulers each; no tensor cores — this is pointer chasing + FP32/ALU):
 //   * persistent warps: the grid is sized to the resident-CTA capacity of the chip; idle lanes pull new rays
@@ -34,32 +36,33 @@ constexpr float F32_MAX_ = 3.402823466e+38f;
 constexpr float F32_EPS_ = 1.1920929e-7f;     // sampling.hlsl:3
 constexpr float BOX_EPS_ = 0.0001f;           // query.hlsl:274
 
-enum RaySource { SRC_BUFFER = 0, SRC_PRIMARY = 1, SRC_BOUNCE = 2 };
+struct FrameParams {
+    tray_view view;
+    uint32_t width, height, frame_count;
+    uint32_t shard_index, shard_count, tiles_x;   // tiles_x = ceil(width / 32)
+    uint32_t n_items;                             // padded local pixel count of this shard (multiple of 256)
+};
+
+enum ShadeMode { SHADE_NONE = 0, SHADE_PRIMARY = 1, SHADE_BOUNCE = 2 };
 
 struct TraceParams {
     const uint4* __restrict__ nodes;          // 5 x uint4 per node
     const uint4* __restrict__ tris;           // 3 or 4 x uint4 per triangle
     const uint32_t* __restrict__ blas_offsets;
     uint32_t tlas_start;
-    uint32_t flags;
-    // SRC_BUFFER
-    const tray_ray* __restrict__ rays_in;
-    unsigned long long n_work;                // work items: rays, or padded local pixels
-    // SRC_PRIMARY / SRC_BOUNCE
-    tray_view view;
-    uint32_t width, height, frame_count;
-    uint32_t shard_index, shard_count, tiles_x;   // tiles_x = ceil(width / 32)
-    const tray_hit* __restrict__ primary_in;      // SRC_BOUNCE: primary hits, local order
-    // outputs (local order)
+    const tray_ray* __restrict__ rays;        // n_work rays
+    const uint32_t* __restrict__ ray_item;    // optional: output slot of ray i (compacted bounce rays); NULL = i
+    uint32_t n_work;
+    const uint32_t* __restrict__ n_work_dev;  // optional: ray count produced on the device (overrides n_work)
     tray_hit* __restrict__ hits_out;
-    tray_ray* __restrict__ rays_out;              // optional: the generated bounce rays
-    uchar4* __restrict__ rgba_out;                // optional
-    unsigned long long* __restrict__ cursor;      // work cursor
-    unsigned long long* __restrict__ counters;    // rays, nodes, tris, instances, hits (COUNT builds)
+    uchar4* __restrict__ rgba_out;            // optional
+    uint32_t shade_mode;
+    uint32_t* __restrict__ cursor;            // work cursor
+    unsigned long long* __restrict__ counters;// rays, nodes, tris, instances, hits (COUNT builds)
     uint32_t* __restrict__ overflow;
-    uint32_t k4b;                                 // 0x4B000000, passed at run time (see byte_f32)
-    uint32_t refill_min;                          // idle lanes needed before a partial warp refills
-    uint32_t tri_weight;                          // vote: triangle phase when n_tri * tri_weight >= n_node
+    uint32_t k4b;                             // 0x4B000000, passed at run time (see byte_f32)
+    uint32_t refill_min;                      // idle lanes needed before a partial warp refills
+    uint32_t tri_weight;                      // vote: triangle phase when n_tri * tri_weight >= n_node
 };
 
 // ---- exact float helpers (no contraction, IEEE rounding) --------------------------------------
@@ -98,6 +101,7 @@ template <int J> __device__ __forceinline__ uint32_t byte_u32(uint32_t w) {
 struct RayConst {
     float ox, oy, oz, dx, dy, dz, ix, iy, iz, tmin;
     uint32_t oct_inv4;
+    bool wide;      // |1/d| >= 2^64 on some axis: 2^23 * adj_inv could overflow, use the unfused node test
 };
 
 __device__ __forceinline__ void prepare_ray(RayConst& r, float ox, float oy, float oz, float dx, float dy, float dz, float tmin) {
@@ -108,6 +112,7 @@ __device__ __forceinline__ void prepare_ray(RayConst& r, float ox, float oy, flo
     r.ix = __fdiv_rn(1.0f, r.dx); r.iy = __fdiv_rn(1.0f, r.dy); r.iz = __fdiv_rn(1.0f, r.dz);   // Ray::inv_direction
     r.oct_inv4 = (r.dx < 0.0f ? 0u : 0x04040404u) | (r.dy < 0.0f ? 0u : 0x02020202u) |
                  (r.dz < 0.0f ? 0u : 0x01010101u);                                              // query.hlsl:314-326
+    r.wide = !(fmaxf(fmaxf(fabsf(r.ix), fabsf(r.iy)), fabsf(r.iz)) < 1.8446744e19f);
 }
 
 // ---- node test: CwBvhNode::intersect_ray, twin query.hlsl:213-303 -------------------------------
@@ -159,6 +164,83 @@ __device__ __forceinline__ uint32_t node_test(const RayConst& r, float tmax, con
     return mask;
 }
 
+
+// ---- packed f32x2 helpers (Blackwell FFMA2 / FADD2: two IEEE-rounded results per issue slot) --------
+__device__ __forceinline__ unsigned long long pack2(uint32_t lo, uint32_t hi) {
+    unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
+}
+__device__ __forceinline__ unsigned long long pack2f(float lo, float hi) { return pack2(__float_as_uint(lo), __float_as_uint(hi)); }
+__device__ __forceinline__ void unpack2f(unsigned long long v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+    unsigned long long r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+template <int J> __device__ __forceinline__ uint32_t byte_biased(uint32_t w, uint32_t k4b) {   // 0x4B0000bb = 2^23 + byte
+    uint32_t r; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(w), "r"(k4b), "n"(0x7440 + J)); return r;
+}
+
+// Fast node test, BIT-IDENTICAL to node_test: with f = 2^23 + q (exact, straight out of PRMT) and C = 2^23 * A
+// (exact: a power-of-two scaling),  fma(f, A, -C) rounds the exact real value (f - 2^23) * A = q * A once, i.e. it
+// IS fl(q * A) — the conversion FADD and the FMUL collapse into one FFMA with no change of rounding.  The
+// following "+ adj_org" stays a separate, separately rounded add (query.hlsl:285-286).  (near, far) of one child
+// and axis travel as an f32x2 pair: FFMA2 + FADD2 = 2 issue slots for what took 6.
+// Requires 2^23 * A finite: rays with |1/d| >= 2^64 take node_test instead (RayConst::wide).
+template <int J>
+__device__ __forceinline__ uint32_t child_test_fast(uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz,
+                                                    unsigned long long AX, unsigned long long AY, unsigned long long AZ,
+                                                    unsigned long long CX, unsigned long long CY, unsigned long long CZ,
+                                                    unsigned long long BX, unsigned long long BY, unsigned long long BZ,
+                                                    float tmax, uint32_t child_bits4, uint32_t bit_index4, uint32_t k4b) {
+    float tnx, tfx, tny, tfy, tnz, tfz;
+    unpack2f(fadd2(ffma2(pack2(byte_biased<J>(nx, k4b), byte_biased<J>(fx, k4b)), AX, CX), BX), tnx, tfx);
+    unpack2f(fadd2(ffma2(pack2(byte_biased<J>(ny, k4b), byte_biased<J>(fy, k4b)), AY, CY), BY), tny, tfy);
+    unpack2f(fadd2(ffma2(pack2(byte_biased<J>(nz, k4b), byte_biased<J>(fz, k4b)), AZ, CZ), BZ), tnz, tfz);
+    const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), BOX_EPS_);
+    const float tfar = fminf(fminf(fminf(tfx, tfy), tfz), tmax);
+    const uint32_t contrib = byte_u32<J>(child_bits4) << ((bit_index4 >> (8 * J)) & 31u);
+    return tmin <= tfar ? contrib : 0u;
+}
+
+__device__ __forceinline__ uint32_t node_test_fast(const RayConst& r, float tmax, const uint4& n0, const uint4& n1,
+                                                   const uint4& n2, const uint4& n3, const uint4& n4, uint32_t k4b) {
+    const uint32_t e = n0.w;
+    const float ax = mul(__uint_as_float((e & 0xffu) << 23), r.ix);
+    const float ay = mul(__uint_as_float(((e >> 8) & 0xffu) << 23), r.iy);
+    const float az = mul(__uint_as_float(((e >> 16) & 0xffu) << 23), r.iz);
+    const float bx = mul(sub(__uint_as_float(n0.x), r.ox), r.ix);
+    const float by = mul(sub(__uint_as_float(n0.y), r.oy), r.iy);
+    const float bz = mul(sub(__uint_as_float(n0.z), r.oz), r.iz);
+    const float cx = mul(ax, -8388608.0f), cy = mul(ay, -8388608.0f), cz = mul(az, -8388608.0f);   // -2^23 * A, exact
+    const unsigned long long AX = pack2f(ax, ax), AY = pack2f(ay, ay), AZ = pack2f(az, az);
+    const unsigned long long CX = pack2f(cx, cx), CY = pack2f(cy, cy), CZ = pack2f(cz, cz);
+    const unsigned long long BX = pack2f(bx, bx), BY = pack2f(by, by), BZ = pack2f(bz, bz);
+    const bool sx = r.dx < 0.0f, sy = r.dy < 0.0f, sz = r.dz < 0.0f;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const uint32_t meta4 = i == 0 ? n1.z : n1.w;
+        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
+        const uint32_t bit_index4 = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t lox = i == 0 ? n2.x : n2.y, hix = i == 0 ? n2.z : n2.w;
+        const uint32_t loy = i == 0 ? n3.x : n3.y, hiy = i == 0 ? n3.z : n3.w;
+        const uint32_t loz = i == 0 ? n4.x : n4.y, hiz = i == 0 ? n4.z : n4.w;
+        const uint32_t nx = sx ? hix : lox, fx = sx ? lox : hix;
+        const uint32_t ny = sy ? hiy : loy, fy = sy ? loy : hiy;
+        const uint32_t nz = sz ? hiz : loz, fz = sz ? loz : hiz;
+        mask |= child_test_fast<0>(nx, fx, ny, fy, nz, fz, AX, AY, AZ, CX, CY, CZ, BX, BY, BZ, tmax, child_bits4, bit_index4, k4b);
+        mask |= child_test_fast<1>(nx, fx, ny, fy, nz, fz, AX, AY, AZ, CX, CY, CZ, BX, BY, BZ, tmax, child_bits4, bit_index4, k4b);
+        mask |= child_test_fast<2>(nx, fx, ny, fy, nz, fz, AX, AY, AZ, CX, CY, CZ, BX, BY, BZ, tmax, child_bits4, bit_index4, k4b);
+        mask |= child_test_fast<3>(nx, fx, ny, fy, nz, fz, AX, AY, AZ, CX, CY, CZ, BX, BY, BZ, tmax, child_bits4, bit_index4, k4b);
+    }
+    return mask;
+}
+
 // ---- triangle test: RtTriangle::intersect, twin query.hlsl:89-129; returns t or +inf -------------
 template <int TRI_STRIDE>
 __device__ __forceinline__ float tri_test(const RayConst& r, float tmax, const uint4* __restrict__ tris, uint32_t prim) {
@@ -192,8 +274,8 @@ __device__ __forceinline__ float tri_test(const RayConst& r, float tmax, const u
 // ---- work item -> pixel ------------------------------------------------------------------------
 // Local work item j of shard s: 256 consecutive items form one 32x8-pixel tile (tile k = s + (j/256)*S in
 // row-major tile order), 32 consecutive items form one 8x4 sub-tile — the footprint of one warp fetch.
-__device__ __forceinline__ bool item_to_pixel(const TraceParams& P, unsigned long long j, uint32_t& px, uint32_t& py) {
-    const uint32_t local_tile = (uint32_t)(j >> 8), w = (uint32_t)j & 255u;
+__device__ __forceinline__ bool item_to_pixel(const FrameParams& P, uint32_t j, uint32_t& px, uint32_t& py) {
+    const uint32_t local_tile = j >> 8, w = j & 255u;
     const uint32_t k = P.shard_index + local_tile * P.shard_count;
     const uint32_t sub = w >> 5, l = w & 31u;
     px = (k % P.tiles_x) * 32u + (sub & 3u) * 8u + (l & 7u);
@@ -208,7 +290,7 @@ __device__ __forceinline__ void mat4_mul(const float* m, float x, float y, float
 }
 
 // pixel -> primary ray direction (src/rt_cpu/rt_cpu.rs:38-55)
-__device__ __forceinline__ void primary_dir(const TraceParams& P, uint32_t px, uint32_t py, float& dx, float& dy, float& dz) {
+__device__ __forceinline__ void primary_dir(const FrameParams& P, uint32_t px, uint32_t py, float& dx, float& dy, float& dz) {
     const float uvx = __fdiv_rn((float)px, (float)P.width);
     const float uvy = sub(1.0f, __fdiv_rn((float)py, (float)P.height));
     const float ndcx = sub(mul(uvx, 2.0f), 1.0f), ndcy = sub(mul(uvy, 2.0f), 1.0f);
@@ -249,9 +331,10 @@ __device__ __forceinline__ void sincos_tau(float u, float& s, float& c) {
 
 // bounce ray from a primary hit (src/rt_cpu/rt_cpu.rs:61-76; basis sampling.hlsl:39-51)
 template <int TRI_STRIDE>
-__device__ __forceinline__ void bounce_ray(const TraceParams& P, uint32_t px, uint32_t py, float pdx, float pdy, float pdz,
-                                           float t, uint32_t prim, float& ox, float& oy, float& oz, float& dx, float& dy, float& dz) {
-    const uint4* rec = P.tris + (size_t)prim * (TRI_STRIDE / 16);
+__device__ __forceinline__ void bounce_ray(const FrameParams& P, const uint4* __restrict__ tris, uint32_t px, uint32_t py,
+                                           float pdx, float pdy, float pdz, float t, uint32_t prim,
+                                           float& ox, float& oy, float& oz, float& dx, float& dy, float& dz) {
+    const uint4* rec = tris + (size_t)prim * (TRI_STRIDE / 16);
     float nx, ny, nz;
     if (TRI_STRIDE == 64) {
         const uint4 g = __ldg(rec + 3);
@@ -289,19 +372,82 @@ __device__ __forceinline__ uchar4 shade(float col) {                           /
     return make_uchar4(v, v, v, 255);
 }
 
-// ---- the kernel ---------------------------------------------------------------------------------
+// ---- ray generation ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) raygen_primary_kernel(const __grid_constant__ FrameParams F, tray_ray* __restrict__ rays) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= F.n_items) return;
+    uint32_t px, py;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);   // pixel outside the frame: tmax = 0
+    if (item_to_pixel(F, j, px, py)) {
+        float dx, dy, dz; primary_dir(F, px, py, dx, dy, dz);
+        a = make_float4(F.view.eye[0], F.view.eye[1], F.view.eye[2], 0.0f);            // Ray::new(eye, dir, 0.0, f32::MAX)
+        b = make_float4(dx, dy, dz, F32_MAX_);
+    }
+    float4* out = reinterpret_cast<float4*>(rays + j);
+    out[0] = a; out[1] = b;
+}
+
+// One thread per pixel of the shard.  Hit pixels append their bounce ray to a compact list (warp-aggregated
+// atomicAdd; `ray_item` remembers the pixel); missed pixels get their final results here.
+template <int TRI_STRIDE>
+__global__ void __launch_bounds__(256) raygen_bounce_kernel(const __grid_constant__ FrameParams F, const uint4* __restrict__ tris,
+                                                            const tray_hit* __restrict__ primary, tray_ray* __restrict__ rays,
+                                                            uint32_t* __restrict__ ray_item, uint32_t* __restrict__ n_rays,
+                                                            tray_hit* __restrict__ bounce_out, uchar4* __restrict__ rgba_out,
+                                                            tray_ray* __restrict__ rays_by_item) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t px = 0, py = 0;
+    bool shoot = false;
+    tray_hit ph; ph.t = __int_as_float(0x7f800000); ph.prim = INVALID;
+    if (j < F.n_items && item_to_pixel(F, j, px, py)) {
+        ph = primary[j];
+        shoot = ph.t < F32_MAX_;                                                      // rt_cpu.rs:61
+    }
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (shoot) {
+        float pdx, pdy, pdz; primary_dir(F, px, py, pdx, pdy, pdz);
+        float ox, oy, oz, dx, dy, dz;
+        bounce_ray<TRI_STRIDE>(F, tris, px, py, pdx, pdy, pdz, ph.t, ph.prim, ox, oy, oz, dx, dy, dz);
+        a = make_float4(ox, oy, oz, 0.0f); b = make_float4(dx, dy, dz, F32_MAX_);
+    }
+    const unsigned m = __ballot_sync(FULL, shoot);
+    if (m) {
+        const int leader = __ffs(m) - 1;
+        uint32_t base = 0;
+        if ((int)lane == leader) base = atomicAdd(n_rays, (uint32_t)__popc(m));
+        base = __shfl_sync(FULL, base, leader);
+        if (shoot) {
+            const uint32_t slot = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
+            float4* out = reinterpret_cast<float4*>(rays + slot);
+            out[0] = a; out[1] = b;
+            ray_item[slot] = j;
+        }
+    }
+    if (j < F.n_items) {
+        if (!shoot) {
+            tray_hit miss; miss.t = __int_as_float(0x7f800000); miss.prim = INVALID;
+            bounce_out[j] = miss;
+            if (rgba_out) rgba_out[j] = shade(__fdiv_rn(1.0f, ph.t));                   // rt_cpu.rs:59 (1/inf = 0)
+        }
+        if (rays_by_item) { float4* o2 = reinterpret_cast<float4*>(rays_by_item + j); o2[0] = a; o2[1] = b; }
+    }
+}
+
+// ---- the traversal kernel ---------------------------------------------------------------------------
 // Per-lane state is kept NORMALISED between steps: a lane is exactly one of
 //   TRI   tri_y != 0                         next action: test one triangle (or enter one TLAS instance)
 //   NODE  tri_y == 0, cur_y has node bits    next action: fetch + test one node
 //   IDLE  tri_y == 0, cur_y == 0             no ray; waits for the next refill
 // so one pair of ballots per iteration drives everything (refill, phase vote, exit).
-template <int SRC, bool TLAS, bool COUNT, int TRI_STRIDE>
+template <bool TLAS, bool COUNT, int TRI_STRIDE>
 __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
     uint2 spill[STACK_SPILL];
     const unsigned lane = threadIdx.x & 31u;
     uint2* const my_stack = s_stack + threadIdx.x;
     const uint32_t k4b = P.k4b;
+    const uint32_t n_work = P.n_work_dev ? *P.n_work_dev : P.n_work;
 
     RayConst r;
     float best_t = 0.f;
@@ -309,7 +455,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
     uint32_t cur_x = 0, cur_y = 0, tri_x = 0, tri_y = 0;
     int sp = 0;
     uint32_t tlas_sp = INVALID, bvh_off = 0;
-    unsigned long long item = 0;
+    uint32_t ray_idx = 0;
     bool exhausted = false;                      // warp-uniform
     unsigned long long c_rays = 0, c_nodes = 0, c_tris = 0, c_insts = 0, c_hits = 0;
 
@@ -326,10 +472,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
             tray_hit h;
             h.t = best_prim != INVALID ? best_t : __int_as_float(0x7f800000);   // RayHit::none()
             h.prim = best_prim;
+            const uint32_t item = P.ray_item ? __ldg(P.ray_item + ray_idx) : ray_idx;
             P.hits_out[item] = h;
-            if (SRC != SRC_BUFFER && P.rgba_out) {
+            if (P.rgba_out) {
                 float col;
-                if (SRC == SRC_PRIMARY) col = __fdiv_rn(1.0f, h.t);                                  // rt_cpu.rs:59
+                if (P.shade_mode == SHADE_PRIMARY) col = __fdiv_rn(1.0f, h.t);                       // rt_cpu.rs:59
                 else col = h.t < F32_MAX_ ? __fdiv_rn(h.t, add(1.0f, h.t)) : 1.0f;                   // rt_cpu.rs:82-87
                 P.rgba_out[item] = shade(col);
             }
@@ -354,54 +501,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
         if (busy != FULL) {
             if (!exhausted && ((unsigned)__popc(~busy) >= P.refill_min || busy == 0u)) {
                 const unsigned idle = ~busy;
-                const int n_idle = __popc(idle);
+                const uint32_t n_idle = (uint32_t)__popc(idle);
                 const int leader = __ffs(idle) - 1;
-                unsigned long long base = 0;
-                if ((int)lane == leader) base = atomicAdd(P.cursor, (unsigned long long)n_idle);
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(P.cursor, n_idle);
                 base = __shfl_sync(FULL, base, leader);
-                if (base + (unsigned long long)n_idle >= P.n_work) exhausted = true;
+                if (base + n_idle >= n_work) exhausted = true;
                 if ((idle >> lane) & 1u) {
-                    item = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
-                    if (item < P.n_work) {
-                        float ox, oy, oz, dx, dy, dz, tmin = 0.0f, tmax = F32_MAX_;
-                        bool go = true;
-                        if (SRC == SRC_BUFFER) {
-                            const float4* rp = reinterpret_cast<const float4*>(P.rays_in + item);
-                            const float4 a = __ldg(rp), b = __ldg(rp + 1);
-                            ox = a.x; oy = a.y; oz = a.z; tmin = a.w; dx = b.x; dy = b.y; dz = b.z; tmax = b.w;
-                        } else {
-                            uint32_t px, py;
-                            go = item_to_pixel(P, item, px, py);
-                            if (go) {
-                                primary_dir(P, px, py, dx, dy, dz);
-                                ox = P.view.eye[0]; oy = P.view.eye[1]; oz = P.view.eye[2];
-                                if (SRC == SRC_BOUNCE) {
-                                    const tray_hit ph = P.primary_in[item];
-                                    tray_ray br; br.origin[0] = br.origin[1] = br.origin[2] = br.tmin = 0.f;
-                                    br.dir[0] = br.dir[1] = br.dir[2] = br.tmax = 0.f;
-                                    if (ph.t < F32_MAX_) {                                   // rt_cpu.rs:61
-                                        float bx, by, bz, ex, ey, ez;
-                                        bounce_ray<TRI_STRIDE>(P, px, py, dx, dy, dz, ph.t, ph.prim, bx, by, bz, ex, ey, ez);
-                                        ox = bx; oy = by; oz = bz; dx = ex; dy = ey; dz = ez;
-                                        br.origin[0] = ox; br.origin[1] = oy; br.origin[2] = oz; br.tmin = 0.f;
-                                        br.dir[0] = dx; br.dir[1] = dy; br.dir[2] = dz; br.tmax = F32_MAX_;
-                                    } else {
-                                        go = false;
-                                        tray_hit miss; miss.t = __int_as_float(0x7f800000); miss.prim = INVALID;
-                                        P.hits_out[item] = miss;
-                                        if (P.rgba_out) P.rgba_out[item] = shade(__fdiv_rn(1.0f, ph.t));   // rt_cpu.rs:59
-                                    }
-                                    if (P.rays_out) P.rays_out[item] = br;
-                                }
-                            }
-                        }
-                        if (go) {
-                            prepare_ray(r, ox, oy, oz, dx, dy, dz, tmin);
-                            best_t = tmax; best_prim = INVALID;
-                            cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp = 0;   // root group, query.hlsl:343
-                            tlas_sp = INVALID; bvh_off = TLAS ? P.tlas_start : 0u;
-                            if (COUNT) c_rays++;
-                        }
+                    ray_idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
+                    if (base < n_work && ray_idx < n_work) {
+                        const float4* rp = reinterpret_cast<const float4*>(P.rays + ray_idx);
+                        const float4 a = __ldg(rp), b = __ldg(rp + 1);
+                        prepare_ray(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w);
+                        best_t = b.w; best_prim = INVALID;
+                        cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp = 0;   // root group, query.hlsl:343
+                        tlas_sp = INVALID; bvh_off = TLAS ? P.tlas_start : 0u;
+                        if (COUNT) c_rays++;
                     }
                 }
                 continue;                                    // re-vote with the new rays
@@ -423,7 +538,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
                 const uint4* np = P.nodes + (size_t)(bvh_off + cur_x + rel) * 5u;              // :373, tlas:383
                 const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                 if (COUNT) c_nodes++;
-                const uint32_t hitmask = node_test(r, best_t, n0, n1, n2, n3, n4, k4b);        // :380
+                const uint32_t hitmask = r.wide ? node_test(r, best_t, n0, n1, n2, n3, n4, k4b)
+                                                : node_test_fast(r, best_t, n0, n1, n2, n3, n4, k4b);   // :380
                 cur_x = n1.x; tri_x = n1.y;                                                    // :383-384
                 cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386
                 tri_y = hitmask & 0x00ffffffu;                                                 // :387
@@ -468,11 +584,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
 
 // compact local order -> row-major frame (one thread per local work item)
 template <typename T>
-__global__ void untile_kernel(const TraceParams P, const T* __restrict__ src, T* __restrict__ dst) {
-    const unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= P.n_work) return;
+__global__ void untile_kernel(const __grid_constant__ FrameParams F, const T* __restrict__ src, T* __restrict__ dst) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= F.n_items) return;
     uint32_t px, py;
-    if (item_to_pixel(P, j, px, py)) dst[(size_t)py * P.width + px] = src[j];
+    if (item_to_pixel(F, j, px, py)) dst[(size_t)py * F.width + px] = src[j];
 }
 
 }  // namespace tray

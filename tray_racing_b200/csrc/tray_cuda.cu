@@ -50,7 +50,7 @@ struct tray_scene {
     uint4* d_nodes = nullptr;
     uint4* d_tris = nullptr;
     uint32_t* d_blas = nullptr;
-    unsigned long long* d_cursor = nullptr;     // [0] cursor, then 2 x 5 counters
+    unsigned long long* d_cursor = nullptr;     // [0] cursor (u32), [1..10] 2 x 5 counters, [11] bounce-ray count (u32)
     uint32_t* d_overflow = nullptr;
     cudaStream_t stream = nullptr;          // the stream work is enqueued on
     cudaStream_t own_stream = nullptr;      // created with the scene
@@ -58,16 +58,20 @@ struct tray_scene {
     uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
     bool counting = false;
     uint32_t refill_min = 8, tri_weight = 4;
-    int blocks_per_sm[3] = { 0, 0, 0 };
+    int blocks_per_sm = 0;
     // ray-batch staging
     tray_ray* d_rays = nullptr; tray_hit* d_hits = nullptr; uint64_t batch_cap = 0;
     // frame state (compact local order)
     uint32_t fw = 0, fh = 0, fshard = 0, fshards = 1;
     uint64_t f_items = 0, f_cap = 0;
     bool f_has_bounce = false, f_has_rgba = false, f_has_rays = false;
-    tray_hit* d_primary = nullptr; tray_hit* d_bounce = nullptr; tray_ray* d_brays = nullptr; uchar4* d_rgba = nullptr;
+    tray_hit* d_primary = nullptr; tray_hit* d_bounce = nullptr; uchar4* d_rgba = nullptr;
+    tray_ray* d_prays = nullptr;             // generated primary rays, local order
+    tray_ray* d_brays = nullptr;             // generated bounce rays, COMPACT (hit pixels only)
+    uint32_t* d_bitem = nullptr;             // local item of compact bounce ray i
+    tray_ray* d_brays_item = nullptr;        // optional: bounce rays by local item (TRAY_RENDER_KEEP_RAYS)
     void* d_untiled = nullptr; uint64_t untiled_cap = 0;
-    tray::TraceParams last_params;
+    tray::FrameParams last_frame;
     tray_counters cnt_primary{}, cnt_bounce{};
 };
 
@@ -77,21 +81,13 @@ using namespace tray;
 
 typedef void (*kernel_fn)(const TraceParams);
 
-template <int SRC, bool TLAS, bool COUNT>
+template <bool TLAS, bool COUNT>
 kernel_fn pick_stride(uint32_t stride) {
-    return stride == 64 ? (kernel_fn)trace_kernel<SRC, TLAS, COUNT, 64> : (kernel_fn)trace_kernel<SRC, TLAS, COUNT, 48>;
+    return stride == 64 ? (kernel_fn)trace_kernel<TLAS, COUNT, 64> : (kernel_fn)trace_kernel<TLAS, COUNT, 48>;
 }
-template <int SRC>
-kernel_fn pick(bool tlas, bool count, uint32_t stride) {
-    if (tlas) return count ? pick_stride<SRC, true, true>(stride) : pick_stride<SRC, true, false>(stride);
-    return count ? pick_stride<SRC, false, true>(stride) : pick_stride<SRC, false, false>(stride);
-}
-kernel_fn pick_kernel(int src, bool tlas, bool count, uint32_t stride) {
-    switch (src) {
-        case SRC_BUFFER: return pick<SRC_BUFFER>(tlas, count, stride);
-        case SRC_PRIMARY: return pick<SRC_PRIMARY>(tlas, count, stride);
-        default: return pick<SRC_BOUNCE>(tlas, count, stride);
-    }
+kernel_fn pick_kernel(bool tlas, bool count, uint32_t stride) {
+    if (tlas) return count ? pick_stride<true, true>(stride) : pick_stride<true, false>(stride);
+    return count ? pick_stride<false, true>(stride) : pick_stride<false, false>(stride);
 }
 
 uint64_t local_items(uint32_t w, uint32_t h, uint32_t shard, uint32_t shards) {
@@ -103,32 +99,39 @@ uint64_t local_items(uint32_t w, uint32_t h, uint32_t shard, uint32_t shards) {
 void base_params(const tray_scene* s, TraceParams& P) {
     memset(&P, 0, sizeof P);
     P.nodes = s->d_nodes; P.tris = s->d_tris; P.blas_offsets = s->d_blas; P.tlas_start = s->tlas_start;
-    P.cursor = s->d_cursor; P.overflow = s->d_overflow;
+    P.cursor = (uint32_t*)s->d_cursor; P.overflow = s->d_overflow;
     P.refill_min = s->refill_min; P.tri_weight = s->tri_weight; P.k4b = 0x4B000000u;
-    P.shard_count = 1;
 }
 
-// one launch: reset the cursor, run the persistent grid
-int launch(tray_scene* s, int src, TraceParams& P, cudaStream_t st, int counter_slot) {
-    kernel_fn k = pick_kernel(src, s->tlas, s->counting, s->tri_stride);
-    if (s->blocks_per_sm[src] == 0) {
+// one launch: reset the cursor, run the persistent grid (sized to the chip, or to the work if that is smaller)
+int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot) {
+    kernel_fn k = pick_kernel(s->tlas, s->counting, s->tri_stride);
+    if (s->blocks_per_sm == 0) {
         int nb = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, BLOCK_THREADS, 0));
-        s->blocks_per_sm[src] = nb > 0 ? nb : 1;
+        s->blocks_per_sm = nb > 0 ? nb : 1;
         int cap = env_int("TRAY_CUDA_BLOCKS_PER_SM", 0);
-        if (cap > 0 && cap < s->blocks_per_sm[src]) s->blocks_per_sm[src] = cap;
+        if (cap > 0 && cap < s->blocks_per_sm) s->blocks_per_sm = cap;
     }
     P.counters = s->d_cursor + 1 + 5 * counter_slot;
     CU(cudaMemsetAsync(s->d_cursor, 0, sizeof(unsigned long long), st));
     if (s->counting) CU(cudaMemsetAsync(P.counters, 0, 5 * sizeof(unsigned long long), st));
-    unsigned long long warps_needed = (P.n_work + 31) / 32;
-    unsigned long long blocks_needed = (warps_needed + (BLOCK_THREADS / 32) - 1) / (BLOCK_THREADS / 32);
-    unsigned long long grid = (unsigned long long)s->sm_count * s->blocks_per_sm[src];
+    const uint64_t warps_needed = ((uint64_t)P.n_work + 31) / 32;
+    const uint64_t blocks_needed = (warps_needed + (BLOCK_THREADS / 32) - 1) / (BLOCK_THREADS / 32);
+    uint64_t grid = (uint64_t)s->sm_count * s->blocks_per_sm;
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid == 0) return TRAY_OK;
     k<<<(unsigned)grid, BLOCK_THREADS, 0, st>>>(P);
     CU(cudaGetLastError());
     return TRAY_OK;
+}
+
+void frame_params(FrameParams& F, const tray_view* view, uint32_t w, uint32_t h, uint32_t frame_count, uint32_t shard, uint32_t shards) {
+    memset(&F, 0, sizeof F);
+    if (view) F.view = *view;
+    F.width = w; F.height = h; F.frame_count = frame_count;
+    F.shard_index = shard; F.shard_count = shards; F.tiles_x = (w + 31) / 32;
+    F.n_items = (uint32_t)local_items(w, h, shard, shards);
 }
 
 int read_counters(tray_scene* s, int slot, tray_counters* out) {
@@ -170,6 +173,7 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_blas); cudaFree(s->d_cursor); cudaFree(s->d_overflow);
     cudaFree(s->d_rays); cudaFree(s->d_hits);
     cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba); cudaFree(s->d_untiled);
+    cudaFree(s->d_prays); cudaFree(s->d_bitem); cudaFree(s->d_brays_item);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
@@ -255,7 +259,7 @@ int tray_cuda_scene_info(const tray_scene* s, tray_scene_info* o) {
 
 int tray_cuda_set_counting(tray_scene* s, int enabled) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
-    if (s->counting != (enabled != 0)) { s->counting = enabled != 0; s->blocks_per_sm[0] = s->blocks_per_sm[1] = s->blocks_per_sm[2] = 0; }
+    if (s->counting != (enabled != 0)) { s->counting = enabled != 0; s->blocks_per_sm = 0; }
     return TRAY_OK;
 }
 
@@ -272,11 +276,9 @@ int tray_cuda_untile_rgba(tray_scene* s, const void* d_compact, uint32_t w, uint
     if (shards == 0) shards = 1;
     if (w == 0 || h == 0 || shard >= shards) return fail(TRAY_ERR_ARG, "bad frame size / shard");
     CU(cudaSetDevice(s->device));
-    TraceParams P; base_params(s, P);
-    P.width = w; P.height = h; P.shard_index = shard; P.shard_count = shards; P.tiles_x = (w + 31) / 32;
-    P.n_work = local_items(w, h, shard, shards);
-    if (P.n_work == 0) return TRAY_OK;
-    tray::untile_kernel<uchar4><<<(unsigned)((P.n_work + 255) / 256), 256, 0, s->stream>>>(P, (const uchar4*)d_compact, (uchar4*)d_frame);
+    FrameParams F; frame_params(F, nullptr, w, h, 0, shard, shards);
+    if (F.n_items == 0) return TRAY_OK;
+    tray::untile_kernel<uchar4><<<(F.n_items + 255) / 256, 256, 0, s->stream>>>(F, (const uchar4*)d_compact, (uchar4*)d_frame);
     CU(cudaGetLastError());
     return TRAY_OK;
 }
@@ -292,11 +294,14 @@ int tray_cuda_trace_device(tray_scene* s, const tray_ray* d_rays, uint64_t n, tr
     if (!s || (n && (!d_rays || !d_hits))) return fail(TRAY_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
-    TraceParams P; base_params(s, P);
-    P.rays_in = d_rays; P.n_work = n; P.hits_out = d_hits;
     if (ms_kernel) CU(cudaEventRecord(s->ev[0], st));
-    int rc = launch(s, SRC_BUFFER, P, st, 0);
-    if (rc) return rc;
+    const uint64_t chunk = 1ull << 30;                    // ray indices are 32-bit inside the kernel
+    for (uint64_t off = 0; off < n; off += chunk) {
+        TraceParams P; base_params(s, P);
+        P.rays = d_rays + off; P.n_work = (uint32_t)(n - off < chunk ? n - off : chunk); P.hits_out = d_hits + off;
+        int rc = launch(s, P, st, 0);
+        if (rc) return rc;
+    }
     if (ms_kernel) {
         CU(cudaEventRecord(s->ev[1], st));
         CU(cudaEventSynchronize(s->ev[1]));
@@ -346,47 +351,66 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     if (!s || !view) return fail(TRAY_ERR_ARG, "NULL argument");
     if (shards == 0) shards = 1;
     if (w == 0 || h == 0 || shard >= shards) return fail(TRAY_ERR_ARG, "bad frame size / shard (%ux%u, %u of %u)", w, h, shard, shards);
+    if ((uint64_t)((w + 31) / 32) * ((h + 7) / 8) * 256ull >= 0x80000000ull) return fail(TRAY_ERR_ARG, "frame too large");
     CU(cudaSetDevice(s->device));
     const bool want_count = (flags & TRAY_RENDER_COUNTERS) != 0;
     if (want_count != s->counting) tray_cuda_set_counting(s, want_count);
-    const uint64_t items = local_items(w, h, shard, shards);
     const uint64_t items_cap = local_items(w, h, 0, shards);   // every shard's buffers have the size of the largest (gather)
     const bool bounce = (flags & TRAY_RENDER_BOUNCE) != 0, rgba = (flags & TRAY_RENDER_RGBA) != 0;
     const bool keep_rays = (flags & TRAY_RENDER_KEEP_RAYS) != 0;
-    if (items_cap > s->f_cap || (bounce && !s->d_bounce) || (rgba && !s->d_rgba) || (keep_rays && !s->d_brays)) {
+    if (items_cap > s->f_cap || (keep_rays && !s->d_brays_item)) {
         const uint64_t cap = items_cap > s->f_cap ? items_cap : s->f_cap;
         cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba);
-        s->d_primary = nullptr; s->d_bounce = nullptr; s->d_brays = nullptr; s->d_rgba = nullptr; s->f_cap = 0;
+        cudaFree(s->d_prays); cudaFree(s->d_bitem); cudaFree(s->d_brays_item);
+        s->d_primary = nullptr; s->d_bounce = nullptr; s->d_brays = nullptr; s->d_rgba = nullptr;
+        s->d_prays = nullptr; s->d_bitem = nullptr; s->d_brays_item = nullptr; s->f_cap = 0;
         const uint64_t c1 = cap ? cap : 1;
         CU(cudaMalloc(&s->d_primary, c1 * sizeof(tray_hit)));
         CU(cudaMalloc(&s->d_bounce, c1 * sizeof(tray_hit)));
         CU(cudaMalloc(&s->d_rgba, c1 * sizeof(uchar4)));
-        if (keep_rays) CU(cudaMalloc(&s->d_brays, c1 * sizeof(tray_ray)));
+        CU(cudaMalloc(&s->d_prays, c1 * sizeof(tray_ray)));
+        CU(cudaMalloc(&s->d_brays, c1 * sizeof(tray_ray)));
+        CU(cudaMalloc(&s->d_bitem, c1 * sizeof(uint32_t)));
+        if (keep_rays) CU(cudaMalloc(&s->d_brays_item, c1 * sizeof(tray_ray)));
         CU(cudaMemsetAsync(s->d_primary, 0xff, c1 * sizeof(tray_hit), s->stream));
         CU(cudaMemsetAsync(s->d_bounce, 0xff, c1 * sizeof(tray_hit), s->stream));
         CU(cudaMemsetAsync(s->d_rgba, 0, c1 * sizeof(uchar4), s->stream));
         s->f_cap = cap;
     }
-    s->fw = w; s->fh = h; s->fshard = shard; s->fshards = shards; s->f_items = items;
+    FrameParams F; frame_params(F, view, w, h, frame_count, shard, shards);
+    s->fw = w; s->fh = h; s->fshard = shard; s->fshards = shards; s->f_items = F.n_items;
     s->f_has_bounce = bounce; s->f_has_rgba = rgba; s->f_has_rays = keep_rays && bounce;
-
-    TraceParams P; base_params(s, P);
-    P.flags = flags; P.view = *view; P.width = w; P.height = h; P.frame_count = frame_count;
-    P.shard_index = shard; P.shard_count = shards; P.tiles_x = (w + 31) / 32; P.n_work = items;
-    P.hits_out = s->d_primary;
-    P.rgba_out = (rgba && !bounce) ? s->d_rgba : nullptr;
-    s->last_params = P;
+    s->last_frame = F;
+    if (F.n_items == 0) { if (ms_primary) *ms_primary = 0.f; if (ms_bounce) *ms_bounce = 0.f; return TRAY_OK; }
+    const unsigned gen_grid = (F.n_items + 255) / 256;
+    uint32_t* d_nbrays = (uint32_t*)(s->d_cursor + 11);
     const bool timed = ms_primary || ms_bounce;
+
+    // ---- primary: generate rays, trace ----
     if (timed) CU(cudaEventRecord(s->ev[0], s->stream));
-    int rc = launch(s, SRC_PRIMARY, P, s->stream, 0);
+    tray::raygen_primary_kernel<<<gen_grid, 256, 0, s->stream>>>(F, s->d_prays);
+    CU(cudaGetLastError());
+    TraceParams P; base_params(s, P);
+    P.rays = s->d_prays; P.n_work = F.n_items; P.hits_out = s->d_primary;
+    P.rgba_out = (rgba && !bounce) ? s->d_rgba : nullptr; P.shade_mode = SHADE_PRIMARY;
+    int rc = launch(s, P, s->stream, 0);
     if (rc) return rc;
     if (timed) CU(cudaEventRecord(s->ev[1], s->stream));
+
+    // ---- bounce: generate + compact rays of hit pixels, trace ----
     if (bounce) {
-        TraceParams B = P;
-        B.primary_in = s->d_primary; B.hits_out = s->d_bounce;
-        B.rgba_out = rgba ? s->d_rgba : nullptr;
-        B.rays_out = keep_rays ? s->d_brays : nullptr;
-        rc = launch(s, SRC_BOUNCE, B, s->stream, 1);
+        CU(cudaMemsetAsync(d_nbrays, 0, sizeof(uint32_t), s->stream));
+        if (s->tri_stride == 64)
+            tray::raygen_bounce_kernel<64><<<gen_grid, 256, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays,
+                                                                            s->d_bounce, rgba ? s->d_rgba : nullptr, keep_rays ? s->d_brays_item : nullptr);
+        else
+            tray::raygen_bounce_kernel<48><<<gen_grid, 256, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays,
+                                                                            s->d_bounce, rgba ? s->d_rgba : nullptr, keep_rays ? s->d_brays_item : nullptr);
+        CU(cudaGetLastError());
+        TraceParams B; base_params(s, B);
+        B.rays = s->d_brays; B.ray_item = s->d_bitem; B.n_work = F.n_items; B.n_work_dev = d_nbrays;   // count stays on the device
+        B.hits_out = s->d_bounce; B.rgba_out = rgba ? s->d_rgba : nullptr; B.shade_mode = SHADE_BOUNCE;
+        rc = launch(s, B, s->stream, 1);
         if (rc) return rc;
         if (timed) CU(cudaEventRecord(s->ev[2], s->stream));
     }
@@ -402,6 +426,9 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
         rc = read_counters(s, 0, &s->cnt_primary); if (rc) return rc;
         if (bounce) { rc = read_counters(s, 1, &s->cnt_bounce); if (rc) return rc; }
         else memset(&s->cnt_bounce, 0, sizeof s->cnt_bounce);
+        // rays generated for pixels outside the frame (tmax = 0) are not rays of the workload
+        const uint64_t pad = (uint64_t)F.n_items - tray_cuda_shard_pixels(w, h, shard, shards);
+        s->cnt_primary.rays -= pad; s->cnt_primary.nodes -= pad;
     }
     return TRAY_OK;
 }
@@ -435,7 +462,7 @@ int download(tray_scene* s, const T* d_src, T* host_dst) {
     if (s->fshards > 1) CU(cudaMemsetAsync(s->d_untiled, 0, bytes, s->stream));   // pixels of other shards read as zero
     if (s->f_items) {
         const unsigned grid = (unsigned)((s->f_items + 255) / 256);
-        tray::untile_kernel<T><<<grid, 256, 0, s->stream>>>(s->last_params, d_src, (T*)s->d_untiled);
+        tray::untile_kernel<T><<<grid, 256, 0, s->stream>>>(s->last_frame, d_src, (T*)s->d_untiled);
         CU(cudaGetLastError());
     }
     CU(cudaMemcpyAsync(host_dst, s->d_untiled, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -458,7 +485,7 @@ int tray_cuda_frame_download(tray_scene* s, tray_hit* primary, tray_hit* bounce,
     }
     if (bounce_rays) {
         if (!s->f_has_rays) return fail(TRAY_ERR_ARG, "last frame was rendered without the keep-bounce-rays flag (0x8)");
-        rc = download<tray_ray>(s, s->d_brays, bounce_rays); if (rc) return rc;
+        rc = download<tray_ray>(s, s->d_brays_item, bounce_rays); if (rc) return rc;
     }
     if (rgba) {
         if (!s->f_has_rgba) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA");
