@@ -35,6 +35,14 @@ constexpr uint32_t INVALID = 0xffffffffu;
 constexpr float F32_MAX_ = 3.402823466e+38f;
 constexpr float F32_EPS_ = 1.1920929e-7f;     // sampling.hlsl:3
 constexpr float BOX_EPS_ = 0.0001f;           // query.hlsl:274
+#ifndef TRAY_I2F_Z
+#define TRAY_I2F_Z 1
+#endif
+#ifndef TRAY_I2F_Y
+#define TRAY_I2F_Y 0
+#endif
+constexpr int I2F_Y = TRAY_I2F_Y;             // 0: no y-plane bytes via I2F.U8, 1: children 0-3 only, 2: all children
+constexpr bool I2F_Z = TRAY_I2F_Z != 0;       // convert the z-plane bytes on the XU pipe (I2F.U8) instead of PRMT+bias
 
 struct FrameParams {
     tray_view view;
@@ -61,6 +69,7 @@ struct TraceParams {
     unsigned long long* __restrict__ counters;// rays, nodes, tris, instances, hits (COUNT builds)
     uint32_t* __restrict__ overflow;
     uint32_t k4b;                             // 0x4B000000, passed at run time (see byte_f32)
+    float zero;                               // 0.0f, passed at run time (see child_test_fast)
     uint32_t refill_min;                      // idle lanes needed before a partial warp refills
     uint32_t tri_weight;                      // vote: triangle phase when n_tri * tri_weight >= n_node
 };
@@ -189,24 +198,57 @@ template <int J> __device__ __forceinline__ uint32_t byte_biased(uint32_t w, uin
 // following "+ adj_org" stays a separate, separately rounded add (query.hlsl:285-286).  (near, far) of one child
 // and axis travel as an f32x2 pair: FFMA2 + FADD2 = 2 issue slots for what took 6.
 // Requires 2^23 * A finite: rays with |1/d| >= 2^64 take node_test instead (RayConst::wide).
-template <int J>
-__device__ __forceinline__ uint32_t child_test_fast(uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz,
-                                                    unsigned long long AX, unsigned long long AY, unsigned long long AZ,
-                                                    unsigned long long CX, unsigned long long CY, unsigned long long CZ,
-                                                    unsigned long long BX, unsigned long long BY, unsigned long long BZ,
-                                                    float tmax, uint32_t child_bits4, uint32_t bit_index4, uint32_t k4b) {
+// byte J of w as an exact float on the conversion (XU) pipe: I2F.U8 with a byte selector.  Quarter-rate, but
+// that pipe is otherwise idle here, so a few conversions per child run there concurrently with the ALU pipe.
+template <int J> __device__ __forceinline__ float byte_i2f(uint32_t w) { return (float)((w >> (8 * J)) & 0xffu); }
+
+template <int J, bool YI2F>
+__device__ __forceinline__ void child_test_fast(uint32_t& mask, uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz,
+                                                unsigned long long AX, unsigned long long AY, unsigned long long AZ,
+                                                unsigned long long CX, unsigned long long CY, unsigned long long CZ,
+                                                unsigned long long BX, unsigned long long BY, unsigned long long BZ,
+                                                unsigned long long Z0, float tmax, uint32_t child_bits4, uint32_t bit_index4, uint32_t k4b) {
     float tnx, tfx, tny, tfy, tnz, tfz;
     unpack2f(fadd2(ffma2(pack2(byte_biased<J>(nx, k4b), byte_biased<J>(fx, k4b)), AX, CX), BX), tnx, tfx);
-    unpack2f(fadd2(ffma2(pack2(byte_biased<J>(ny, k4b), byte_biased<J>(fy, k4b)), AY, CY), BY), tny, tfy);
-    unpack2f(fadd2(ffma2(pack2(byte_biased<J>(nz, k4b), byte_biased<J>(fz, k4b)), AZ, CZ), BZ), tnz, tfz);
+    if (YI2F) unpack2f(fadd2(ffma2(pack2f(byte_i2f<J>(ny), byte_i2f<J>(fy)), AY, Z0), BY), tny, tfy);
+    else unpack2f(fadd2(ffma2(pack2(byte_biased<J>(ny, k4b), byte_biased<J>(fy, k4b)), AY, CY), BY), tny, tfy);
+    if (I2F_Z) {
+        // z pair through I2F.U8: q is already the plain float, fma(q, A, 0) = fl(q * A)  (Z0 is a run-time zero so
+        // that the assembler cannot turn fma+add back into one fused op)
+        unpack2f(fadd2(ffma2(pack2f(byte_i2f<J>(nz), byte_i2f<J>(fz)), AZ, Z0), BZ), tnz, tfz);
+    } else {
+        unpack2f(fadd2(ffma2(pack2(byte_biased<J>(nz, k4b), byte_biased<J>(fz, k4b)), AZ, CZ), BZ), tnz, tfz);
+    }
     const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), BOX_EPS_);
     const float tfar = fminf(fminf(fminf(tfx, tfy), tfz), tmax);
     const uint32_t contrib = byte_u32<J>(child_bits4) << ((bit_index4 >> (8 * J)) & 31u);
-    return tmin <= tfar ? contrib : 0u;
+    // if (tmin <= tfar) mask |= contrib   — as one compare + one predicated OR
+    asm("{.reg .pred p; setp.le.f32 p, %1, %2; @p or.b32 %0, %0, %3;}" : "+r"(mask) : "f"(tmin), "f"(tfar), "r"(contrib));
+}
+
+struct NodeConsts { unsigned long long AX, AY, AZ, CX, CY, CZ, BX, BY, BZ, Z0; };
+
+template <int I>
+__device__ __forceinline__ void node_half_fast(uint32_t& mask, const RayConst& r, float tmax, const NodeConsts& c, uint32_t meta4,
+                                               uint32_t lox, uint32_t hix, uint32_t loy, uint32_t hiy, uint32_t loz, uint32_t hiz,
+                                               uint32_t k4b) {
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;                 // query.hlsl:251
+    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
+    const uint32_t bit_index4 = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const bool sx = r.dx < 0.0f, sy = r.dy < 0.0f, sz = r.dz < 0.0f;
+    const uint32_t nx = sx ? hix : lox, fx = sx ? lox : hix;                          // query.hlsl:266-273
+    const uint32_t ny = sy ? hiy : loy, fy = sy ? loy : hiy;
+    const uint32_t nz = sz ? hiz : loz, fz = sz ? loz : hiz;
+    constexpr bool YI = I2F_Y == 2 || (I2F_Y == 1 && I == 0);
+    child_test_fast<0, YI>(mask, nx, fx, ny, fy, nz, fz, c.AX, c.AY, c.AZ, c.CX, c.CY, c.CZ, c.BX, c.BY, c.BZ, c.Z0, tmax, child_bits4, bit_index4, k4b);
+    child_test_fast<1, YI>(mask, nx, fx, ny, fy, nz, fz, c.AX, c.AY, c.AZ, c.CX, c.CY, c.CZ, c.BX, c.BY, c.BZ, c.Z0, tmax, child_bits4, bit_index4, k4b);
+    child_test_fast<2, YI>(mask, nx, fx, ny, fy, nz, fz, c.AX, c.AY, c.AZ, c.CX, c.CY, c.CZ, c.BX, c.BY, c.BZ, c.Z0, tmax, child_bits4, bit_index4, k4b);
+    child_test_fast<3, YI>(mask, nx, fx, ny, fy, nz, fz, c.AX, c.AY, c.AZ, c.CX, c.CY, c.CZ, c.BX, c.BY, c.BZ, c.Z0, tmax, child_bits4, bit_index4, k4b);
 }
 
 __device__ __forceinline__ uint32_t node_test_fast(const RayConst& r, float tmax, const uint4& n0, const uint4& n1,
-                                                   const uint4& n2, const uint4& n3, const uint4& n4, uint32_t k4b) {
+                                                   const uint4& n2, const uint4& n3, const uint4& n4, uint32_t k4b, float zero) {
     const uint32_t e = n0.w;
     const float ax = mul(__uint_as_float((e & 0xffu) << 23), r.ix);
     const float ay = mul(__uint_as_float(((e >> 8) & 0xffu) << 23), r.iy);
@@ -215,29 +257,13 @@ __device__ __forceinline__ uint32_t node_test_fast(const RayConst& r, float tmax
     const float by = mul(sub(__uint_as_float(n0.y), r.oy), r.iy);
     const float bz = mul(sub(__uint_as_float(n0.z), r.oz), r.iz);
     const float cx = mul(ax, -8388608.0f), cy = mul(ay, -8388608.0f), cz = mul(az, -8388608.0f);   // -2^23 * A, exact
-    const unsigned long long AX = pack2f(ax, ax), AY = pack2f(ay, ay), AZ = pack2f(az, az);
-    const unsigned long long CX = pack2f(cx, cx), CY = pack2f(cy, cy), CZ = pack2f(cz, cz);
-    const unsigned long long BX = pack2f(bx, bx), BY = pack2f(by, by), BZ = pack2f(bz, bz);
-    const bool sx = r.dx < 0.0f, sy = r.dy < 0.0f, sz = r.dz < 0.0f;
+    NodeConsts c;
+    c.AX = pack2f(ax, ax); c.AY = pack2f(ay, ay); c.AZ = pack2f(az, az);
+    c.CX = pack2f(cx, cx); c.CY = pack2f(cy, cy); c.CZ = pack2f(cz, cz);
+    c.BX = pack2f(bx, bx); c.BY = pack2f(by, by); c.BZ = pack2f(bz, bz); c.Z0 = pack2f(zero, zero);
     uint32_t mask = 0;
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-        const uint32_t meta4 = i == 0 ? n1.z : n1.w;
-        const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-        const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xffu;
-        const uint32_t bit_index4 = (meta4 ^ (r.oct_inv4 & inner_mask4)) & 0x1f1f1f1fu;
-        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-        const uint32_t lox = i == 0 ? n2.x : n2.y, hix = i == 0 ? n2.z : n2.w;
-        const uint32_t loy = i == 0 ? n3.x : n3.y, hiy = i == 0 ? n3.z : n3.w;
-        const uint32_t loz = i == 0 ? n4.x : n4.y, hiz = i == 0 ? n4.z : n4.w;
-        const uint32_t nx = sx ? hix : lox, fx = sx ? lox : hix;
-        const uint32_t ny = sy ? hiy : loy, fy = sy ? loy : hiy;
-        const uint32_t nz = sz ? hiz : loz, fz = sz ? loz : hiz;
-        mask |= child_test_fast<0>(nx, fx, ny, fy, nz, fz, AX, AY, AZ, CX, CY, CZ, BX, BY, BZ, tmax, child_bits4, bit_index4, k4b);
-        mask |= child_test_fast<1>(nx, fx, ny, fy, nz, fz, AX, AY, AZ, CX, CY, CZ, BX, BY, BZ, tmax, child_bits4, bit_index4, k4b);
-        mask |= child_test_fast<2>(nx, fx, ny, fy, nz, fz, AX, AY, AZ, CX, CY, CZ, BX, BY, BZ, tmax, child_bits4, bit_index4, k4b);
-        mask |= child_test_fast<3>(nx, fx, ny, fy, nz, fz, AX, AY, AZ, CX, CY, CZ, BX, BY, BZ, tmax, child_bits4, bit_index4, k4b);
-    }
+    node_half_fast<0>(mask, r, tmax, c, n1.z, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, k4b);
+    node_half_fast<1>(mask, r, tmax, c, n1.w, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, k4b);
     return mask;
 }
 
@@ -539,7 +565,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
                 const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                 if (COUNT) c_nodes++;
                 const uint32_t hitmask = r.wide ? node_test(r, best_t, n0, n1, n2, n3, n4, k4b)
-                                                : node_test_fast(r, best_t, n0, n1, n2, n3, n4, k4b);   // :380
+                                                : node_test_fast(r, best_t, n0, n1, n2, n3, n4, k4b, P.zero);   // :380
                 cur_x = n1.x; tri_x = n1.y;                                                    // :383-384
                 cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386
                 tri_y = hitmask & 0x00ffffffu;                                                 // :387

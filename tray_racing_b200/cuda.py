@@ -12,7 +12,7 @@ import numpy as np
 from .host import HIT_DTYPE, RAY_DTYPE, TrayView
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtray_cuda.so")
+LIB_PATH = os.environ.get("TRAY_CUDA_LIB") or os.path.join(_HERE, "libtray_cuda.so")   # override: A/B builds only
 
 RENDER_BOUNCE, RENDER_RGBA, RENDER_COUNTERS, RENDER_KEEP_RAYS = 1, 2, 4, 8
 
