@@ -267,6 +267,8 @@ def run_ours(args):
     bytes_p = 80 * cp["nodes"] + TRI_STRIDE * cp["tris"] + 8 * cp["rays"]
     bytes_b = 80 * cb["nodes"] + TRI_STRIDE * cb["tris"] + 8 * cb["rays"] + 8 * cp["rays"]
     peak, peak_src = measured_peaks()
+    l2_peak = cuda.bandwidth_probe(48 << 20, 50, local_rank)          # streaming read of an L2-resident 48 MiB buffer
+    hbm_read = cuda.bandwidth_probe(2048 << 20, 8, local_rank)        # same kernel, buffer >> L2
     dominant = "primary" if kp_ms >= kb_ms else "bounce"
     ach = (bytes_p / kp_ms if dominant == "primary" else bytes_b / kb_ms) / 1e6      # GB/s
 
@@ -301,6 +303,7 @@ def run_ours(args):
                         "note": "rank-0 shard, kernel alone, CUDA events"},
             "roofline": {"bound": "hbm", "kernel": f"trace_kernel<{dominant}>", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
+                         "l2_peak_gbs_measured_here": l2_peak, "frac_of_l2_peak": ach / l2_peak, "hbm_read_gbs_measured_here": hbm_read,
                          "algorithmic_bytes_per_launch": bytes_p if dominant == "primary" else bytes_b,
                          "bytes_per_ray": (bytes_p / cp["rays"]) if dominant == "primary" else (bytes_b / max(1, cb["rays"])),
                          "ms_per_launch": kp_ms if dominant == "primary" else kb_ms,

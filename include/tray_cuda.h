@@ -231,6 +231,11 @@ int tray_cuda_start(const void* bvh_bytes, uint64_t bvh_len,
                     float render_time_s, int benchmark, int animate, int device,
                     float* out_min_ms, float* out_mean_ms, uint32_t* out_frames);
 
+/* Roofline denominators measured on this device: streaming 16-byte read bandwidth (GB/s) over a buffer of `bytes`
+ * swept `iters` times by a chip-filling grid.  A buffer well under the L2 size measures L2 bandwidth (the roof the
+ * node array lives under), one much larger than L2 measures HBM read bandwidth.                   */
+int tray_cuda_bandwidth_probe(int device, uint64_t bytes, int iters, float* out_gbs);
+
 const char* tray_cuda_last_error(void);
 
 #ifdef __cplusplus

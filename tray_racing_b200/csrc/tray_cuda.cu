@@ -57,7 +57,7 @@ struct tray_scene {
     cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
     uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
     bool counting = false;
-    uint32_t refill_min = 8, tri_weight = 4;
+    uint32_t refill_min = 4, tri_weight = 4;
     int blocks_per_sm = 0;
     // ray-batch staging
     tray_ray* d_rays = nullptr; tray_hit* d_hits = nullptr; uint64_t batch_cap = 0;
@@ -155,7 +155,42 @@ int check_overflow(tray_scene* s) {
 
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(512) bandwidth_kernel(const uint4* __restrict__ buf, uint64_t n16, int iters, uint32_t* out) {
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (int it = 0; it < iters; it++)
+        for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) {
+            const uint4 v = __ldcg(buf + i);                // L2-cached, bypass L1: this measures the L2 / HBM pipe
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) out[0] = acc.x;   // never true in practice; keeps the loads alive
+}
+}  // namespace
+
 extern "C" {
+
+int tray_cuda_bandwidth_probe(int device, uint64_t bytes, int iters, float* out_gbs) {
+    if (!out_gbs || bytes < 4096 || iters < 1) return fail(TRAY_ERR_ARG, "bad argument");
+    if (tray_cuda_device_count() == 0) return fail(TRAY_ERR_NO_DEVICE, "no CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    uint4* buf = nullptr; uint32_t* out = nullptr;
+    const uint64_t n16 = bytes / 16;
+    CU(cudaMalloc(&buf, n16 * 16)); CU(cudaMalloc(&out, 4));
+    CU(cudaMemset(buf, 0x5a, n16 * 16));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 4;
+    bandwidth_kernel<<<grid, 512>>>(buf, n16, 2, out);      // warm-up: brings the buffer into L2 when it fits
+    CU(cudaEventRecord(e0));
+    bandwidth_kernel<<<grid, 512>>>(buf, n16, iters, out);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, e0, e1));
+    *out_gbs = (float)((double)n16 * 16.0 * iters / (ms * 1e-3) / 1e9);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(out);
+    return TRAY_OK;
+}
 
 const char* tray_cuda_last_error(void) { return g_err; }
 unsigned tray_cuda_abi_version(void) { return TRAY_CUDA_ABI_VERSION; }
@@ -197,7 +232,7 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
     if (!s) return fail(TRAY_ERR_ARG, "out of host memory");
     s->device = device; s->n_nodes = n_nodes; s->n_tris = n_tris; s->tri_stride = tri_stride;
     s->n_instances = n_instances; s->tlas_start = tlas_start; s->tlas = n_instances > 0;
-    s->refill_min = (uint32_t)env_int("TRAY_CUDA_REFILL_MIN", 8);
+    s->refill_min = (uint32_t)env_int("TRAY_CUDA_REFILL_MIN", 4);
     s->tri_weight = (uint32_t)env_int("TRAY_CUDA_TRI_WEIGHT", 4);
     int rc = TRAY_OK;
     auto body = [&]() -> int {

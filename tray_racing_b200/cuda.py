@@ -21,7 +21,7 @@ EXPORTS = (
     "tray_cuda_scene_info", "tray_cuda_trace", "tray_cuda_trace_device", "tray_cuda_render",
     "tray_cuda_shard_pixels", "tray_cuda_frame_download", "tray_cuda_frame_device_ptrs", "tray_cuda_sync",
     "tray_cuda_counters", "tray_cuda_set_counting", "tray_cuda_start", "tray_cuda_last_error",
-    "tray_cuda_untile_rgba", "tray_cuda_scene_set_stream",
+    "tray_cuda_untile_rgba", "tray_cuda_scene_set_stream", "tray_cuda_bandwidth_probe",
 )
 
 
@@ -90,6 +90,8 @@ def lib() -> C.CDLL:
         L.tray_cuda_untile_rgba.argtypes = [vp, vp, u32, u32, u32, u32, vp]
         L.tray_cuda_scene_set_stream.restype = i32
         L.tray_cuda_scene_set_stream.argtypes = [vp, vp]
+        L.tray_cuda_bandwidth_probe.restype = i32
+        L.tray_cuda_bandwidth_probe.argtypes = [i32, u64, i32, f32p]
         L.tray_cuda_counters.restype = i32
         L.tray_cuda_counters.argtypes = [vp, C.POINTER(Counters), C.POINTER(Counters)]
         L.tray_cuda_set_counting.restype = i32
@@ -108,6 +110,13 @@ def _check(rc: int):
 
 def device_count() -> int:
     return lib().tray_cuda_device_count()
+
+
+def bandwidth_probe(nbytes: int, iters: int = 20, device: int = 0) -> float:
+    """Streaming-read GB/s over an `nbytes` buffer: << L2 size measures L2, >> L2 measures HBM."""
+    g = C.c_float()
+    _check(lib().tray_cuda_bandwidth_probe(device, int(nbytes), int(iters), C.byref(g)))
+    return g.value
 
 
 def shard_pixels(w: int, h: int, shard: int = 0, shards: int = 1) -> int:
