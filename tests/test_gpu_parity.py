@@ -96,6 +96,68 @@ def test_traverse_random_rays(cornell):
         sc.close()
 
 
+def test_tiny_direction_components_take_the_unfused_node_test(cornell, monkeypatch):
+    """The fused node test (fma(2^23 + q, A, -2^23 A) == fl(q A)) needs 2^23 * A finite.  Rays with |1/d| >= 2^64 on an
+    axis, and scenes with node scales >= 2^40, fall back to the unfused test; both paths must match the oracle, and
+    forcing the unfused path everywhere must not change a single bit."""
+    p = host.PackedScene(cornell)
+    orc = ob.Oracle.from_packed(p)
+    rays = random_rays(60000, 21, axis_fraction=0.0)
+    rng = np.random.default_rng(3)
+    tiny = rng.choice([1e-20, -1e-20, 1e-25, -3e-30, 1e-37, -1e-38, 1e-42], size=len(rays)).astype(np.float32)
+    ax = rng.integers(0, 3, size=len(rays))
+    rays["d"][np.arange(len(rays)), ax] = tiny                       # not renormalised on purpose: t scales, parity must hold
+    ref = orc.trace(rays)
+    assert (ref["prim"] != ob.INVALID_PRIM).sum() > 1000
+    results = []
+    for force in ("0", "1"):
+        monkeypatch.setenv("TRAY_CUDA_FORCE_EXACT", force)
+        sc = cuda.TrayCudaScene.from_packed(p)
+        try:
+            results.append(sc.traverse(rays))
+            plain = random_rays(50000, 22)
+            assert_hits_identical(sc.traverse(plain), orc.trace(plain), f"force_exact={force}")
+        finally:
+            sc.close()
+    assert_hits_identical(results[0], ref, "tiny components")
+    assert_hits_identical(results[1], ref, "tiny components, unfused everywhere")
+
+
+def test_huge_scene_scale_falls_back_to_unfused_test():
+    """A scene 2^50 units across has node scales >= 2^40 and is traversed with the unfused test.  (At that size the
+    triangle test itself overflows f32 in the reference arithmetic, so nothing is hit — what matters is that the
+    kernel agrees with the oracle and produces no spurious hit out of an overflowed 2^23 * A.)"""
+    m = host.Mesh.generate("soup", 5, 0.002)
+    tris = (m.tris() * np.float32(2.0 ** 50)).astype(np.float32)
+    nodes, pidx, _ = host.build_cwbvh(tris)
+    assert nodes[:, 12:15].max() >= 167
+    rec = host.tri_records(tris[pidx])
+    rays = random_rays(20000, 23, lo=-1, hi=1)
+    rays["o"] *= np.float32(2.0 ** 50)
+    sc = cuda.TrayCudaScene(nodes, rec)
+    try:
+        got = sc.traverse(rays)
+    finally:
+        sc.close()
+    ref = ob.Oracle(nodes, rec).trace(rays)
+    assert_hits_identical(got, ref)
+    # a merely large scene (2^30 units, node scales ~2^23) still uses the fused test and still matches
+    tris = (m.tris() * np.float32(2.0 ** 30)).astype(np.float32)
+    nodes, pidx, _ = host.build_cwbvh(tris)
+    assert nodes[:, 12:15].max() < 167
+    rec = host.tri_records(tris[pidx])
+    rays = random_rays(20000, 24, lo=-1, hi=1)
+    rays["o"] *= np.float32(2.0 ** 30)
+    sc = cuda.TrayCudaScene(nodes, rec)
+    try:
+        got = sc.traverse(rays)
+    finally:
+        sc.close()
+    ref = ob.Oracle(nodes, rec).trace(rays)
+    assert (ref["prim"] != ob.INVALID_PRIM).sum() > 100
+    assert_hits_identical(got, ref)
+
+
 def test_degenerate_scenes():
     """One triangle (root with a single leaf child), coincident triangles (tie rule), empty scene."""
     one = np.array([[0, 0, 0, 1, 0, 0, 0, 1, 0]], dtype=np.float32)

@@ -69,6 +69,7 @@ struct TraceParams {
     unsigned long long* __restrict__ counters;// rays, nodes, tris, instances, hits (COUNT builds)
     uint32_t* __restrict__ overflow;
     uint32_t k4b;                             // 0x4B000000, passed at run time (see byte_f32)
+    uint32_t force_exact;                     // scene has node scales >= 2^40: always take the unfused node test
     float zero;                               // 0.0f, passed at run time (see child_test_fast)
     uint32_t refill_min;                      // idle lanes needed before a partial warp refills
     uint32_t tri_weight;                      // vote: triangle phase when n_tri * tri_weight >= n_node
@@ -564,7 +565,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
                 const uint4* np = P.nodes + (size_t)(bvh_off + cur_x + rel) * 5u;              // :373, tlas:383
                 const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                 if (COUNT) c_nodes++;
-                const uint32_t hitmask = r.wide ? node_test(r, best_t, n0, n1, n2, n3, n4, k4b)
+                const uint32_t hitmask = (r.wide || P.force_exact) ? node_test(r, best_t, n0, n1, n2, n3, n4, k4b)
                                                 : node_test_fast(r, best_t, n0, n1, n2, n3, n4, k4b, P.zero);   // :380
                 cur_x = n1.x; tri_x = n1.y;                                                    // :383-384
                 cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386

@@ -47,6 +47,7 @@ struct tray_scene {
     uint64_t n_nodes = 0, n_tris = 0;
     uint32_t tri_stride = 48, n_instances = 0, tlas_start = 0;
     bool tlas = false;
+    bool force_exact = false;                // some node scale >= 2^40: 2^23 * adj_inv could overflow in the fused node test
     uint4* d_nodes = nullptr;
     uint4* d_tris = nullptr;
     uint32_t* d_blas = nullptr;
@@ -100,7 +101,7 @@ void base_params(const tray_scene* s, TraceParams& P) {
     memset(&P, 0, sizeof P);
     P.nodes = s->d_nodes; P.tris = s->d_tris; P.blas_offsets = s->d_blas; P.tlas_start = s->tlas_start;
     P.cursor = (uint32_t*)s->d_cursor; P.overflow = s->d_overflow;
-    P.refill_min = s->refill_min; P.tri_weight = s->tri_weight; P.k4b = 0x4B000000u;
+    P.refill_min = s->refill_min; P.tri_weight = s->tri_weight; P.k4b = 0x4B000000u; P.force_exact = s->force_exact ? 1u : 0u;
 }
 
 // one launch: reset the cursor, run the persistent grid (sized to the chip, or to the work if that is smaller)
@@ -233,6 +234,11 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
     s->device = device; s->n_nodes = n_nodes; s->n_tris = n_tris; s->tri_stride = tri_stride;
     s->n_instances = n_instances; s->tlas_start = tlas_start; s->tlas = n_instances > 0;
     s->refill_min = (uint32_t)env_int("TRAY_CUDA_REFILL_MIN", 4);
+    s->force_exact = env_int("TRAY_CUDA_FORCE_EXACT", 0) != 0;
+    for (uint64_t i = 0; i < n_nodes && !s->force_exact; i++) {
+        const uint8_t* e = (const uint8_t*)nodes + i * 80 + 12;
+        if (e[0] >= 167 || e[1] >= 167 || e[2] >= 167) s->force_exact = true;   // scale = 2^(e-127) >= 2^40
+    }
     s->tri_weight = (uint32_t)env_int("TRAY_CUDA_TRI_WEIGHT", 4);
     int rc = TRAY_OK;
     auto body = [&]() -> int {
