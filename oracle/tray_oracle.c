@@ -172,7 +172,8 @@ static inline int closer(float t, float tmax) {
 }
 
 /* ---- CwBvh::ray_traverse / ray_traverse_tlas_blas; twins query.hlsl:328-438, query_tlas.hlsl:333-500 */
-static int trace_one(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_count* cnt) {
+static int trace_one(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_count* cnt, uint8_t* oplog) {
+    uint32_t n_ops = 0;   /* optional step log: 'N' node fetch+test, 'T' triangle test, 'I' instance entry */
     prep_ray r; prepare_ray(ray, &r);
     uint32_t stack[ORC_STACK][2];
     uint32_t size = 0;
@@ -202,6 +203,7 @@ static int trace_one(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_c
             uint32_t child_node_index = child_index_base + relative_index;                /* :373 */
             const uint8_t* node = s->nodes + (uint64_t)(bvh_offset + child_node_index) * 80u;  /* tlas:383 */
             n_nodes++;                                                     /* PROFILE_RT aabb_hit_count/8, :377-379 */
+            if (oplog) oplog[n_ops++] = 'N';
             uint32_t hitmask = node_intersect(node, &r, best_t);           /* :380 */
             uint32_t imask = node[15];                                     /* :381 */
             cur_x = load_u32(node + 16);                                   /* :383 */
@@ -230,10 +232,12 @@ static int trace_one(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_c
                 tlas_stack_size = size;                                           /* tlas:431 */
                 bvh_offset = s->blas_offsets[global];                             /* tlas:439 */
                 n_insts++;
+                if (oplog) oplog[n_ops++] = 'I';
                 cur_x = 0; cur_y = 0x80000000u;                                   /* tlas:443 */
                 break;
             }
             n_tris++;                                                      /* PROFILE_RT tri_hit_count, :407-409 */
+            if (oplog) oplog[n_ops++] = 'T';
             float t = tri_intersect(s->tris + (uint64_t)global * s->tri_stride, s->tri_stride, &r, best_t);
             if (closer(t, best_t)) { best_t = t; best_prim = global; }     /* :410-413 with the CPU tie rule */
         }
@@ -264,12 +268,28 @@ int orc_trace(const orc_scene* s, const orc_ray* rays, uint64_t n, orc_hit* hits
 #pragma omp parallel for schedule(dynamic, 2048) num_threads(nthreads) reduction(+:tn,tt,ti,th) reduction(min:rc)
     for (int64_t i = 0; i < (int64_t)n; i++) {
         orc_count c;
-        int e = trace_one(s, &rays[i], &hits[i], &c);
+        int e = trace_one(s, &rays[i], &hits[i], &c, NULL);
         if (e < rc) rc = e;
         if (counts) counts[i] = c;
         tn += c.nodes; tt += c.tris; ti += c.insts; th += hits[i].prim != ORC_INVALID_PRIM;
     }
     if (totals) { totals->rays = n; totals->nodes = tn; totals->tris = tt; totals->insts = ti; totals->hits = th; }
+    return rc;
+}
+
+/* Per-ray step log for scheduling studies (tests/tools): offsets[i]..offsets[i+1] index `ops`, one byte per step in
+ * the ray's own order.  `counts` must come from a previous orc_trace over the same rays. */
+int orc_trace_oplog(const orc_scene* s, const orc_ray* rays, uint64_t n, const orc_count* counts,
+                    uint8_t* ops, const uint64_t* offsets, int nthreads) {
+    int rc = 0;
+    if (nthreads <= 0) nthreads = orc_max_threads();
+#pragma omp parallel for schedule(dynamic, 2048) num_threads(nthreads) reduction(min:rc)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        orc_hit h; orc_count c;
+        int e = trace_one(s, &rays[i], &h, &c, ops + offsets[i]);
+        if (e < rc) rc = e;
+        if (c.nodes + c.tris + c.insts != counts[i].nodes + counts[i].tris + counts[i].insts) rc = -5;
+    }
     return rc;
 }
 
@@ -410,7 +430,7 @@ int orc_render(const orc_scene* s, const orc_view* vw, uint32_t w, uint32_t h, u
         uint32_t px = (uint32_t)(i % w), py = (uint32_t)(i / w);
         orc_ray ray; orc_primary_ray(vw, w, h, px, py, &ray);
         orc_hit hit; orc_count c;
-        int e = trace_one(s, &ray, &hit, &c);
+        int e = trace_one(s, &ray, &hit, &c, NULL);
         if (e < rc) rc = e;
         pn += c.nodes; pt += c.tris; pi += c.insts; ph += hit.prim != ORC_INVALID_PRIM;
         if (primary) primary[i] = hit;
@@ -419,7 +439,7 @@ int orc_render(const orc_scene* s, const orc_view* vw, uint32_t w, uint32_t h, u
         orc_ray aoray; memset(&aoray, 0, sizeof(aoray));
         if ((flags & ORC_RENDER_BOUNCE) && hit.t < F32_MAX) {
             orc_bounce_ray(s, vw, &ray, &hit, px, py, frame_count, &aoray);
-            e = trace_one(s, &aoray, &ao, &c);
+            e = trace_one(s, &aoray, &ao, &c, NULL);
             if (e < rc) rc = e;
             br++; bn += c.nodes; bt += c.tris; bi += c.insts; bh += ao.prim != ORC_INVALID_PRIM;
             col = (ao.t < F32_MAX) ? ao.t / (1.0f + ao.t) : 1.0f;       /* rt_cpu.rs:82-87 */

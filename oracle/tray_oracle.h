@@ -58,6 +58,10 @@ int orc_max_threads(void);
 int orc_trace(const orc_scene* s, const orc_ray* rays, uint64_t n, orc_hit* hits, orc_count* counts,
               orc_totals* totals, int nthreads);
 
+/* per-ray step log ('N' node, 'T' triangle, 'I' instance entry) for warp-scheduling studies in tests/tools */
+int orc_trace_oplog(const orc_scene* s, const orc_ray* rays, uint64_t n, const orc_count* counts,
+                    uint8_t* ops, const uint64_t* offsets, int nthreads);
+
 /* O(rays x tris) reference: same triangle test, same first-wins rule in ascending index order;
  * also reports how many triangles tie with the winning t (for the tie census). */
 int orc_brute_force(const orc_scene* s, const orc_ray* rays, uint64_t n, orc_hit* hits,

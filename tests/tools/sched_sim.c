@@ -1,0 +1,103 @@
+/* sched_sim.c — issue-slot model of the traversal kernel's WARP schedule (test/analysis infrastructure).
+ *
+ * Input: the per-ray step logs of the CPU oracle ('N' node step, 'T' triangle step, 'I' instance entry), in the
+ * order the kernel's cursor hands rays out.  The model replays them through persistent 32-lane warps with ray
+ * replacement and a per-iteration phase vote, for three lane organisations:
+ *   policy 0  K ray slots per LANE: a lane joins the voted phase if any of its K rays wants it (K = 1 is the kernel
+ *             of round 1)
+ *   policy 1  warp-level POOL of 32*K rays: any lane can run any ray (upper bound for in-warp compaction)
+ * Each step costs issue slots (cn, ct, plus csel when K > 1); the result is total slots, per-phase lane occupancy
+ * and the makespan over warps.  Nothing here is on the product path. */
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+typedef struct sim_cfg {
+    int policy, K, n_warps, refill_min, tri_weight;
+    int cn, ct, cr, csel;          /* issue slots: node step, triangle step, refill, per-step selection overhead */
+} sim_cfg;
+
+typedef struct sim_out {
+    double slots, makespan, node_steps, tri_steps, node_lanes, tri_lanes, refills;
+} sim_out;
+
+typedef struct warp {
+    double t;
+    uint64_t* pos;   /* 32*K cursors into ops (end == idle) */
+    uint64_t* end;
+    int exhausted;
+} warp;
+
+static void heap_sift(int* h, int n, int i, const warp* w) {
+    for (;;) {
+        int l = 2 * i + 1, r = l + 1, m = i;
+        if (l < n && w[h[l]].t < w[h[m]].t) m = l;
+        if (r < n && w[h[r]].t < w[h[m]].t) m = r;
+        if (m == i) return;
+        int tmp = h[i]; h[i] = h[m]; h[m] = tmp; i = m;
+    }
+}
+
+int sched_sim(const uint8_t* ops, const uint64_t* offsets, uint64_t n_rays, const sim_cfg* c, sim_out* o) {
+    const int K = c->policy == 1 ? 1 : c->K, S = c->policy == 1 ? c->K : 32 * K;   /* policy 1: K is the pool size */
+    warp* w = (warp*)calloc((size_t)c->n_warps, sizeof(warp));
+    int* heap = (int*)malloc(sizeof(int) * (size_t)c->n_warps);
+    for (int i = 0; i < c->n_warps; i++) {
+        w[i].pos = (uint64_t*)calloc((size_t)S, 8); w[i].end = (uint64_t*)calloc((size_t)S, 8); heap[i] = i;
+    }
+    memset(o, 0, sizeof *o);
+    uint64_t cursor = 0;
+    int live = c->n_warps;
+    while (live > 0) {
+        warp* W = &w[heap[0]];
+        /* census */
+        int idle_slots = 0, lanes_tri = 0, lanes_node = 0, pool_tri = 0, pool_node = 0;
+        for (int l = 0; l < (c->policy == 1 ? S : 32); l++) {
+            int lt = 0, ln = 0;
+            for (int k = 0; k < K; k++) {
+                const int s = l * K + k;
+                if (W->pos[s] == W->end[s]) { idle_slots++; continue; }
+                if (ops[W->pos[s]] == 'N') { ln = 1; pool_node++; } else { lt = 1; pool_tri++; }
+            }
+            lanes_tri += lt; lanes_node += ln;
+        }
+        int n_tri = c->policy == 1 ? (pool_tri < 32 ? pool_tri : 32) : lanes_tri;
+        int n_node = c->policy == 1 ? (pool_node < 32 ? pool_node : 32) : lanes_node;
+        const int busy = S - idle_slots;
+        if (idle_slots > 0 && !W->exhausted && (idle_slots >= c->refill_min * (K > 1 ? 1 : 1) || busy == 0)) {
+            for (int s = 0; s < S; s++)
+                if (W->pos[s] == W->end[s]) {
+                    if (cursor < n_rays) { W->pos[s] = offsets[cursor]; W->end[s] = offsets[cursor + 1]; cursor++; }
+                }
+            if (cursor >= n_rays) W->exhausted = 1;
+            W->t += c->cr; o->slots += c->cr; o->refills += 1;
+        } else if (busy == 0) {
+            /* retire the warp */
+            if (W->t > o->makespan) o->makespan = W->t;
+            heap[0] = heap[--live];
+            if (live > 0) heap_sift(heap, live, 0, w);
+            continue;
+        } else {
+            const int tri_phase = n_node == 0 || n_tri * c->tri_weight >= n_node;
+            const uint8_t want = tri_phase ? 'T' : 'N';
+            int done = 0;
+            if (c->policy == 1) {
+                for (int s = 0; s < S && done < 32; s++)
+                    if (W->pos[s] != W->end[s] && ((ops[W->pos[s]] == 'N') == (want == 'N'))) { W->pos[s]++; done++; }
+            } else {
+                for (int l = 0; l < 32; l++)
+                    for (int k = 0; k < K; k++) {
+                        const int s = l * K + k;
+                        if (W->pos[s] != W->end[s] && ((ops[W->pos[s]] == 'N') == (want == 'N'))) { W->pos[s]++; done++; break; }
+                    }
+            }
+            const int cost = (tri_phase ? c->ct : c->cn) + (c->K > 1 || c->policy == 1 ? c->csel : 0);
+            W->t += cost; o->slots += cost;
+            if (tri_phase) { o->tri_steps += 1; o->tri_lanes += done; } else { o->node_steps += 1; o->node_lanes += done; }
+        }
+        heap_sift(heap, live, 0, w);
+    }
+    for (int i = 0; i < c->n_warps; i++) { free(w[i].pos); free(w[i].end); }
+    free(w); free(heap);
+    return 0;
+}

@@ -68,6 +68,7 @@ struct TraceParams {
     uint32_t* __restrict__ cursor;            // work cursor
     unsigned long long* __restrict__ counters;// rays, nodes, tris, instances, hits (COUNT builds)
     uint32_t* __restrict__ overflow;
+    uint2* __restrict__ spill;                // pooled kernel: global scratch for stack entries past the shared-memory ones
     uint32_t k4b;                             // 0x4B000000, passed at run time (see byte_f32)
     uint32_t force_exact;                     // scene has node scales >= 2^40: always take the unfused node test
     float zero;                               // 0.0f, passed at run time (see child_test_fast)

@@ -10,6 +10,7 @@
 #include <new>
 
 #include "traverse.cuh"
+#include "traverse_pool.cuh"
 
 static_assert(sizeof(tray_cwbvh_node) == 80, "CwBvhNode is 80 bytes (bvh_embree_to_cwbvh.rs:91, rt_gpu/mod.rs:70)");
 static_assert(sizeof(tray_tri48) == 48 && sizeof(tray_tri64) == 64, "triangle record strides");
@@ -59,6 +60,9 @@ struct tray_scene {
     uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
     bool counting = false;
     uint32_t refill_min = 4, tri_weight = 4;
+    bool pool = false;                       // pooled kernel (traverse_pool.cuh) or one-ray-per-lane kernel (traverse.cuh)
+    uint32_t pool_refill_min = 8, pool_tri_weight = 1;
+    uint2* d_spill = nullptr; uint64_t spill_cap = 0;
     int blocks_per_sm = 0;
     // ray-batch staging
     tray_ray* d_rays = nullptr; tray_hit* d_hits = nullptr; uint64_t batch_cap = 0;
@@ -90,6 +94,14 @@ kernel_fn pick_kernel(bool tlas, bool count, uint32_t stride) {
     if (tlas) return count ? pick_stride<true, true>(stride) : pick_stride<true, false>(stride);
     return count ? pick_stride<false, true>(stride) : pick_stride<false, false>(stride);
 }
+template <bool TLAS, bool COUNT>
+kernel_fn pick_pool_stride(uint32_t stride) {
+    return stride == 64 ? (kernel_fn)trace_pool_kernel<TLAS, COUNT, 64> : (kernel_fn)trace_pool_kernel<TLAS, COUNT, 48>;
+}
+kernel_fn pick_pool_kernel(bool tlas, bool count, uint32_t stride) {
+    if (tlas) return count ? pick_pool_stride<true, true>(stride) : pick_pool_stride<true, false>(stride);
+    return count ? pick_pool_stride<false, true>(stride) : pick_pool_stride<false, false>(stride);
+}
 
 uint64_t local_items(uint32_t w, uint32_t h, uint32_t shard, uint32_t shards) {
     const uint64_t tiles = (uint64_t)((w + 31) / 32) * ((h + 7) / 8);
@@ -106,10 +118,12 @@ void base_params(const tray_scene* s, TraceParams& P) {
 
 // one launch: reset the cursor, run the persistent grid (sized to the chip, or to the work if that is smaller)
 int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot) {
-    kernel_fn k = pick_kernel(s->tlas, s->counting, s->tri_stride);
+    kernel_fn k = s->pool ? pick_pool_kernel(s->tlas, s->counting, s->tri_stride) : pick_kernel(s->tlas, s->counting, s->tri_stride);
+    const int threads = s->pool ? POOL_WARPS * 32 : BLOCK_THREADS;
+    const uint64_t rays_per_block = s->pool ? (uint64_t)POOL_WARPS * POOL_SLOTS : (uint64_t)BLOCK_THREADS;
     if (s->blocks_per_sm == 0) {
         int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, BLOCK_THREADS, 0));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, 0));
         s->blocks_per_sm = nb > 0 ? nb : 1;
         int cap = env_int("TRAY_CUDA_BLOCKS_PER_SM", 0);
         if (cap > 0 && cap < s->blocks_per_sm) s->blocks_per_sm = cap;
@@ -117,12 +131,23 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot) {
     P.counters = s->d_cursor + 1 + 5 * counter_slot;
     CU(cudaMemsetAsync(s->d_cursor, 0, sizeof(unsigned long long), st));
     if (s->counting) CU(cudaMemsetAsync(P.counters, 0, 5 * sizeof(unsigned long long), st));
-    const uint64_t warps_needed = ((uint64_t)P.n_work + 31) / 32;
-    const uint64_t blocks_needed = (warps_needed + (BLOCK_THREADS / 32) - 1) / (BLOCK_THREADS / 32);
+    const uint64_t blocks_needed = ((uint64_t)P.n_work + rays_per_block - 1) / rays_per_block;
     uint64_t grid = (uint64_t)s->sm_count * s->blocks_per_sm;
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid == 0) return TRAY_OK;
-    k<<<(unsigned)grid, BLOCK_THREADS, 0, st>>>(P);
+    if (s->pool) {
+        P.refill_min = s->pool_refill_min; P.tri_weight = s->pool_tri_weight;
+        const uint64_t need = grid * POOL_WARPS * POOL_STACK_SPILL * POOL_SLOTS;      // uint2 entries
+        if (need > s->spill_cap) {
+            CU(cudaStreamSynchronize(st));
+            cudaFree(s->d_spill); s->d_spill = nullptr; s->spill_cap = 0;
+            const uint64_t cap = (uint64_t)s->sm_count * s->blocks_per_sm * POOL_WARPS * POOL_STACK_SPILL * POOL_SLOTS;
+            CU(cudaMalloc(&s->d_spill, cap * sizeof(uint2)));
+            s->spill_cap = cap;
+        }
+        P.spill = s->d_spill;
+    }
+    k<<<(unsigned)grid, threads, 0, st>>>(P);
     CU(cudaGetLastError());
     return TRAY_OK;
 }
@@ -207,7 +232,7 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_blas); cudaFree(s->d_cursor); cudaFree(s->d_overflow);
-    cudaFree(s->d_rays); cudaFree(s->d_hits);
+    cudaFree(s->d_rays); cudaFree(s->d_hits); cudaFree(s->d_spill);
     cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba); cudaFree(s->d_untiled);
     cudaFree(s->d_prays); cudaFree(s->d_bitem); cudaFree(s->d_brays_item);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
@@ -240,6 +265,11 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
         if (e[0] >= 167 || e[1] >= 167 || e[2] >= 167) s->force_exact = true;   // scale = 2^(e-127) >= 2^40
     }
     s->tri_weight = (uint32_t)env_int("TRAY_CUDA_TRI_WEIGHT", 4);
+    s->pool = env_int("TRAY_CUDA_POOL", 0) != 0;
+    s->pool_refill_min = (uint32_t)env_int("TRAY_CUDA_POOL_REFILL_MIN", 8);
+    s->pool_tri_weight = (uint32_t)env_int("TRAY_CUDA_POOL_TRI_WEIGHT", 1);
+    if (s->pool_refill_min < 1) s->pool_refill_min = 1;
+    if (s->pool_refill_min > POOL_SLOTS) s->pool_refill_min = POOL_SLOTS;
     int rc = TRAY_OK;
     auto body = [&]() -> int {
         cudaDeviceProp prop;
