@@ -310,7 +310,8 @@ def run_ours(args):
                          "nodes_per_ray": cp["nodes"] / cp["rays"], "tris_per_ray": cp["tris"] / cp["rays"]},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 160 * world, "d2h_bytes_per_step": w * h * 4,
                     "note": "tray_cuda_render + tray_cuda_frame_download(rgba) per rank, pinned host frame, wall clock"},
-            "gpu_launches": args.steps * world * 3,     # per step: 2 traversal kernels per rank + one untile per shard on rank 0
+            # per step and rank: raygen_primary, trace (primary), raygen_bounce, trace (bounce); rank 0 adds one untile per shard
+            "gpu_launches": args.steps * world * 5,
             "clocks": clocks,
         }
         if cpu_base is not None:

@@ -228,3 +228,15 @@ def test_start_slot_runs_the_reference_protocol(cornell):
     from tray_racing_b200.runner import Options, Scene, cwbvh_cuda_runner
     st = cwbvh_cuda_runner(cornell, Options(width=320, height=184, render_time=0.1, tlas=True), Scene(camera=cornell.camera))
     assert st.frames >= 1 and st.traversal_ms > 0
+
+
+@pytest.mark.parametrize("use_tlas,stride", [(False, 48), (True, 64)])
+def test_pooled_kernel_is_bit_identical_too(cornell, monkeypatch, use_tlas, stride):
+    """TRAY_CUDA_POOL=1 selects the pooled kernel (traverse_pool.cuh): another lane assignment, the same per-ray
+    sequence of node and triangle tests — so the same hits AND the same visit counters."""
+    monkeypatch.setenv("TRAY_CUDA_POOL", "1")
+    render_and_compare(cornell, 640, 360, use_tlas, stride)
+    render_and_compare(host.Mesh.generate("hairball", 3, 0.1), 480, 270)
+    monkeypatch.setenv("TRAY_CUDA_POOL_REFILL_MIN", "1")
+    monkeypatch.setenv("TRAY_CUDA_POOL_TRI_WEIGHT", "3")
+    render_and_compare(cornell, 101, 37, use_tlas, stride)

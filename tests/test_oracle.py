@@ -294,3 +294,23 @@ def test_empty_inputs():
     assert len(o.trace(np.zeros(0, dtype=ob.RAY_DTYPE))) == 0
     h = o.trace(random_rays(10, 1))
     assert (h["prim"] == ob.INVALID_PRIM).all() and np.isinf(h["t"]).all()
+
+
+def test_step_log_matches_the_visit_counters(cornell):
+    """orc_trace_oplog (input of tests/tools/sched_sim.py): one byte per step, 'N' per node fetched and 'T' per
+    triangle tested, in the ray's own order; every ray starts with the root node."""
+    import ctypes as C
+    p = host.PackedScene(cornell)
+    orc = ob.Oracle.from_packed(p)
+    rays = random_rays(3000, 11)
+    hits, cnt, tot = orc.trace(rays, counts=True)
+    n_ops = cnt["nodes"].astype(np.uint64) + cnt["tris"] + cnt["insts"]
+    offsets = np.zeros(rays.shape[0] + 1, dtype=np.uint64)
+    np.cumsum(n_ops, out=offsets[1:])
+    ops = np.zeros(int(offsets[-1]) + 1, dtype=np.uint8)
+    L = ob.lib()
+    L.orc_trace_oplog.restype = C.c_int
+    L.orc_trace_oplog.argtypes = [C.POINTER(ob.OrcScene), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    assert L.orc_trace_oplog(C.byref(orc.scene), rays.ctypes.data, rays.shape[0], cnt.ctypes.data, ops.ctypes.data, offsets.ctypes.data, 0) == 0
+    assert (ops[:-1] == ord("N")).sum() == tot["nodes"] and (ops[:-1] == ord("T")).sum() == tot["tris"]
+    assert (ops[offsets[:-1].astype(np.int64)] == ord("N")).all()

@@ -5,7 +5,9 @@
  * replacement and a per-iteration phase vote, for three lane organisations:
  *   policy 0  K ray slots per LANE: a lane joins the voted phase if any of its K rays wants it (K = 1 is the kernel
  *             of round 1)
- *   policy 1  warp-level POOL of 32*K rays: any lane can run any ray (upper bound for in-warp compaction)
+ *   policy 1  warp-level POOL of K rays: any lane can run any ray (upper bound for in-warp compaction)
+ *   policy 2  one ray per lane, but a triangle phase DRAINS every participating lane's triangle group
+ *             (cost = csel + ct per round, rounds = the longest group)
  * Each step costs issue slots (cn, ct, plus csel when K > 1); the result is total slots, per-phase lane occupancy
  * and the makespan over warps.  Nothing here is on the product path. */
 #include <stdint.h>
@@ -39,7 +41,7 @@ static void heap_sift(int* h, int n, int i, const warp* w) {
 }
 
 int sched_sim(const uint8_t* ops, const uint64_t* offsets, uint64_t n_rays, const sim_cfg* c, sim_out* o) {
-    const int K = c->policy == 1 ? 1 : c->K, S = c->policy == 1 ? c->K : 32 * K;   /* policy 1: K is the pool size */
+    const int K = c->policy == 1 ? 1 : (c->policy == 2 ? 1 : c->K), S = c->policy == 1 ? c->K : 32 * K;   /* policy 1: K is the pool size */
     warp* w = (warp*)calloc((size_t)c->n_warps, sizeof(warp));
     int* heap = (int*)malloc(sizeof(int) * (size_t)c->n_warps);
     for (int i = 0; i < c->n_warps; i++) {
@@ -81,6 +83,21 @@ int sched_sim(const uint8_t* ops, const uint64_t* offsets, uint64_t n_rays, cons
             const int tri_phase = n_node == 0 || n_tri * c->tri_weight >= n_node;
             const uint8_t want = tri_phase ? 'T' : 'N';
             int done = 0;
+            if (c->policy == 2 && tri_phase) {
+                /* drain: rounds until no participating lane has a 'T' at its cursor */
+                int rounds = 0;
+                for (;;) {
+                    int any = 0;
+                    for (int s = 0; s < S; s++)
+                        if (W->pos[s] != W->end[s] && ops[W->pos[s]] != 'N') { W->pos[s]++; any++; }
+                    if (!any) break;
+                    rounds++; o->tri_steps += 1; o->tri_lanes += any;
+                }
+                const int cost = c->csel + rounds * c->ct;
+                W->t += cost; o->slots += cost;
+                heap_sift(heap, live, 0, w);
+                continue;
+            }
             if (c->policy == 1) {
                 for (int s = 0; s < S && done < 32; s++)
                     if (W->pos[s] != W->end[s] && ((ops[W->pos[s]] == 'N') == (want == 'N'))) { W->pos[s]++; done++; }
@@ -91,7 +108,7 @@ int sched_sim(const uint8_t* ops, const uint64_t* offsets, uint64_t n_rays, cons
                         if (W->pos[s] != W->end[s] && ((ops[W->pos[s]] == 'N') == (want == 'N'))) { W->pos[s]++; done++; break; }
                     }
             }
-            const int cost = (tri_phase ? c->ct : c->cn) + (c->K > 1 || c->policy == 1 ? c->csel : 0);
+            const int cost = (tri_phase ? c->ct : c->cn) + ((c->K > 1 && c->policy == 0) || c->policy == 1 ? c->csel : 0);
             W->t += cost; o->slots += cost;
             if (tri_phase) { o->tri_steps += 1; o->tri_lanes += done; } else { o->node_steps += 1; o->node_lanes += done; }
         }

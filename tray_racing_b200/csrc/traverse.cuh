@@ -28,6 +28,9 @@
 namespace tray {
 
 constexpr int BLOCK_THREADS = 128;
+#ifndef TRAY_MIN_BLOCKS
+#define TRAY_MIN_BLOCKS 8
+#endif
 constexpr int STACK_SMEM = 12;     // entries per thread in shared memory
 constexpr int STACK_SPILL = 36;    // further entries per thread in local memory (total 48 > obvhs' 32, cwbvh.rs:88)
 constexpr unsigned FULL = 0xffffffffu;
@@ -107,6 +110,13 @@ template <int J> __device__ __forceinline__ uint32_t byte_u32(uint32_t w) {
     asm("prmt.b32 %0, %1, 0, %2;" : "=r"(r) : "r"(w), "n"(0x4440 + J));
     return r;
 }
+
+// L1 prefetch of the record a lane will need on its NEXT step (issued as soon as the step that decides it ends, so the
+// fetch overlaps the warp's vote / refill bookkeeping and the other warps' work)
+#ifndef TRAY_PREFETCH
+#define TRAY_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
 // ---- per-ray constants ---------------------------------------------------------------------------
 struct RayConst {
@@ -469,7 +479,7 @@ __global__ void __launch_bounds__(256) raygen_bounce_kernel(const __grid_constan
 //   IDLE  tri_y == 0, cur_y == 0             no ray; waits for the next refill
 // so one pair of ballots per iteration drives everything (refill, phase vote, exit).
 template <bool TLAS, bool COUNT, int TRI_STRIDE>
-__global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_constant__ TraceParams P) {
+__global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
     uint2 spill[STACK_SPILL];
     const unsigned lane = threadIdx.x & 31u;
@@ -572,6 +582,17 @@ __global__ void __launch_bounds__(BLOCK_THREADS) trace_kernel(const __grid_const
                 cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386
                 tri_y = hitmask & 0x00ffffffu;                                                 // :387
                 if (tri_y == 0u && cur_y < 0x01000000u) pop_or_retire();
+                if (TRAY_PREFETCH) {
+                    if (tri_y != 0u) {
+                        if (!TLAS || tlas_sp != INVALID)
+                            prefetch_l1(P.tris + (size_t)(tri_x + 31u - (uint32_t)__clz((int)tri_y)) * (TRI_STRIDE / 16));
+                    } else if (cur_y >= 0x01000000u) {
+                        const uint32_t o2 = 31u - (uint32_t)__clz((int)cur_y);
+                        const uint32_t s2 = (o2 - 24u) ^ (r.oct_inv4 & 0xffu);
+                        const uint4* q = P.nodes + (size_t)(bvh_off + cur_x + (uint32_t)__popc(cur_y & ~(0xffffffffu << s2))) * 5u;
+                        prefetch_l1(q); prefetch_l1(q + 4);
+                    }
+                }
             }
         } else {
             if (want_tri) {

@@ -21,8 +21,14 @@ namespace tray {
 
 constexpr int POOL_WARPS = 4;
 constexpr int POOL_SLOTS = 64;            // rays per warp
-constexpr int POOL_STACK_SMEM = 8;        // stack entries per ray in shared memory
-constexpr int POOL_STACK_SPILL = 40;      // further entries per ray in global scratch (total 48 > obvhs' 32)
+#ifndef TRAY_POOL_STACK
+#define TRAY_POOL_STACK 8
+#endif
+#ifndef TRAY_POOL_MIN_BLOCKS
+#define TRAY_POOL_MIN_BLOCKS 6
+#endif
+constexpr int POOL_STACK_SMEM = TRAY_POOL_STACK;   // stack entries per ray in shared memory
+constexpr int POOL_STACK_SPILL = 48 - POOL_STACK_SMEM;      // further entries per ray in global scratch (total 48 > obvhs' 32)
 
 struct PoolWarpSmem {
     float4 A[POOL_SLOTS];                 // origin.xyz, best_t (the ray's current tmax)
@@ -35,7 +41,7 @@ struct PoolWarpSmem {
 };
 
 template <bool TLAS, bool COUNT, int TRI_STRIDE>
-__global__ void __launch_bounds__(POOL_WARPS * 32, 6) trace_pool_kernel(const __grid_constant__ TraceParams P) {
+__global__ void __launch_bounds__(POOL_WARPS * 32, TRAY_POOL_MIN_BLOCKS) trace_pool_kernel(const __grid_constant__ TraceParams P) {
     __shared__ PoolWarpSmem s_pool[POOL_WARPS];
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
