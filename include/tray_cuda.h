@@ -204,6 +204,26 @@ int tray_cuda_frame_device_ptrs(tray_scene* scene, void** d_primary, void** d_bo
 int tray_cuda_untile_rgba(tray_scene* scene, const void* d_compact, uint32_t width, uint32_t height,
                           uint32_t shard_index, uint32_t shard_count, void* d_frame);
 
+/* ---- fused framebuffer exchange over peer memory (multi-GPU, SURVEY.md §8e option 1) ---------------------------
+ * The reference has one GPU and one framebuffer (rt_gpu_software.rs:177-180).  With rays sharded over N GPUs the only
+ * exchange is "every shard's pixels reach ONE frame".  Instead of gathering compact shards with a collective and
+ * untiling them, a scene can be given a FRAME TARGET: a row-major width x height RGBA8 frame that may live on
+ * another GPU of the box (a peer mapping opened from a CUDA IPC handle).  The traversal kernels then store each
+ * finished pixel straight into that frame over NVLink while they are still tracing, so the transfer overlaps the
+ * traversal pixel by pixel and no collective or untile launch remains (only a completion barrier).
+ *
+ *   rank 0:  tray_cuda_frame_alloc -> tray_cuda_ipc_export -> (send the 64-byte handle to the other ranks)
+ *   rank k:  tray_cuda_ipc_open -> tray_cuda_scene_set_frame_target(scene, mapped_ptr)
+ *   all:     tray_cuda_render(.. TRAY_RENDER_RGBA ..) per frame; synchronise streams + barrier = frame complete   */
+int tray_cuda_frame_alloc(int device, uint64_t bytes, void** d_ptr);          /* plain cudaMalloc: IPC-exportable   */
+int tray_cuda_frame_free(int device, void* d_ptr);
+int tray_cuda_ipc_export(int device, void* d_ptr, uint8_t handle[64]);        /* cudaIpcGetMemHandle                */
+int tray_cuda_ipc_open(int device, const uint8_t handle[64], void** d_ptr);   /* cudaIpcOpenMemHandle + peer access */
+int tray_cuda_ipc_close(int device, void* d_ptr);
+/* RGBA8 of every later tray_cuda_render goes to `d_frame` (row-major, width*height*4 bytes, on this or a peer
+ * device) instead of the scene's compact buffer; NULL restores the compact buffer.  The pointer is borrowed.        */
+int tray_cuda_scene_set_frame_target(tray_scene* scene, void* d_frame);
+
 /* Run all subsequent work of this scene on `stream` (a cudaStream_t as void*; NULL restores the scene's own
  * stream) — lets a host that already owns a stream (torch, NCCL) order its collectives after the kernels. */
 int tray_cuda_scene_set_stream(tray_scene* scene, void* stream);

@@ -240,3 +240,34 @@ def test_pooled_kernel_is_bit_identical_too(cornell, monkeypatch, use_tlas, stri
     monkeypatch.setenv("TRAY_CUDA_POOL_REFILL_MIN", "1")
     monkeypatch.setenv("TRAY_CUDA_POOL_TRI_WEIGHT", "3")
     render_and_compare(cornell, 101, 37, use_tlas, stride)
+
+
+@pytest.mark.parametrize("w,h,shards", [(640, 360, 1), (101, 37, 1), (333, 130, 3)])
+def test_frame_target_receives_the_same_pixels(cornell, w, h, shards):
+    """Fused framebuffer exchange (include/tray_cuda.h, tray_cuda_scene_set_frame_target): the kernels store RGBA
+    straight into a row-major frame (here on the same GPU; a peer mapping in a multi-GPU run) — same bytes as the
+    compact buffer + untile path, for whole frames and for interleaved tile shards writing into ONE frame."""
+    p = host.PackedScene(cornell)
+    view = host.view_from_camera(cornell.camera, w, h)
+    sc = cuda.TrayCudaScene.from_packed(p)
+    frame = cuda.frame_alloc(w * h * 4)
+    try:
+        sc.render(view, w, h, 0, cuda.RENDER_BOUNCE | cuda.RENDER_RGBA)
+        want = sc.download(rgba=True)["rgba"].copy()
+        sc.set_frame_target(frame)
+        for s in range(shards):
+            sc.render(view, w, h, 0, cuda.RENDER_BOUNCE | cuda.RENDER_RGBA, shard=s, shards=shards)
+        sc.sync()
+        import torch
+        got = torch.as_tensor(cuda.DeviceArray(frame, (h, w, 4), "|u1", sc), device="cuda").cpu().numpy()
+        assert (got.reshape(want.shape) == want).all()
+        with pytest.raises(cuda.TrayCudaError):
+            sc.download(rgba=True)                       # the compact RGBA buffer was not written for this frame
+        sc.set_frame_target(None)
+        sc.render(view, w, h, 0, cuda.RENDER_RGBA)       # primary-only shading goes through the same switch
+        sc.download(rgba=True)
+        # an IPC handle can be exported for the allocation (opening it needs a second process: bench.py --gpus 2)
+        assert len(cuda.ipc_export(frame)) == 64
+    finally:
+        sc.close()
+        cuda.frame_free(frame)

@@ -66,7 +66,8 @@ struct TraceParams {
     uint32_t n_work;
     const uint32_t* __restrict__ n_work_dev;  // optional: ray count produced on the device (overrides n_work)
     tray_hit* __restrict__ hits_out;
-    uchar4* __restrict__ rgba_out;            // optional
+    uchar4* __restrict__ rgba_out;            // optional: compact (item order), or a row-major frame when frame_w != 0
+    uint32_t frame_w, frame_h, frame_tiles_x, frame_shard, frame_shards;   // frame target geometry (item -> pixel)
     uint32_t shade_mode;
     uint32_t* __restrict__ cursor;            // work cursor
     unsigned long long* __restrict__ counters;// rays, nodes, tris, instances, hits (COUNT builds)
@@ -111,10 +112,11 @@ template <int J> __device__ __forceinline__ uint32_t byte_u32(uint32_t w) {
     return r;
 }
 
-// L1 prefetch of the record a lane will need on its NEXT step (issued as soon as the step that decides it ends, so the
-// fetch overlaps the warp's vote / refill bookkeeping and the other warps' work)
+// Optional L1 prefetch of the record a lane will need on its NEXT step, issued as soon as the step that decides it
+// ends.  MEASURED SLOWER on B200 (hairball primary 0.968 vs 0.906 ms, kitchen bounce 0.96 vs 0.60 ms): the extra
+// address arithmetic costs issue slots and the two 128-byte line fills per node evict useful L1 lines.  Off.
 #ifndef TRAY_PREFETCH
-#define TRAY_PREFETCH 1
+#define TRAY_PREFETCH 0
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
@@ -321,6 +323,16 @@ __device__ __forceinline__ bool item_to_pixel(const FrameParams& P, uint32_t j, 
     return px < P.width && py < P.height;
 }
 
+// where the RGBA of work item `item` goes: slot `item` of the compact buffer, or its pixel of a row-major frame target
+// (possibly peer memory: the store then travels over NVLink while the warp keeps tracing); -1 = pixel outside the frame
+__device__ __forceinline__ long long rgba_slot(uint32_t item, uint32_t w, uint32_t h, uint32_t tiles_x, uint32_t shard, uint32_t shards) {
+    if (w == 0u) return (long long)item;
+    FrameParams F; F.width = w; F.height = h; F.tiles_x = tiles_x; F.shard_index = shard; F.shard_count = shards;
+    uint32_t px, py;
+    if (!item_to_pixel(F, item, px, py)) return -1;
+    return (long long)py * w + px;
+}
+
 // glam Mat4 * Vec4 (column-major): ((c0*x + c1*y) + c2*z) + c3*w
 __device__ __forceinline__ void mat4_mul(const float* m, float x, float y, float z, float w, float o[4]) {
 #pragma unroll
@@ -432,7 +444,7 @@ __global__ void __launch_bounds__(256) raygen_bounce_kernel(const __grid_constan
                                                             const tray_hit* __restrict__ primary, tray_ray* __restrict__ rays,
                                                             uint32_t* __restrict__ ray_item, uint32_t* __restrict__ n_rays,
                                                             tray_hit* __restrict__ bounce_out, uchar4* __restrict__ rgba_out,
-                                                            tray_ray* __restrict__ rays_by_item) {
+                                                            tray_ray* __restrict__ rays_by_item, uint32_t rgba_row_major) {
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     uint32_t px = 0, py = 0;
@@ -466,7 +478,10 @@ __global__ void __launch_bounds__(256) raygen_bounce_kernel(const __grid_constan
         if (!shoot) {
             tray_hit miss; miss.t = __int_as_float(0x7f800000); miss.prim = INVALID;
             bounce_out[j] = miss;
-            if (rgba_out) rgba_out[j] = shade(__fdiv_rn(1.0f, ph.t));                   // rt_cpu.rs:59 (1/inf = 0)
+            if (rgba_out) {                                                             // rt_cpu.rs:59 (1/inf = 0)
+                if (!rgba_row_major) rgba_out[j] = shade(__fdiv_rn(1.0f, ph.t));
+                else if (item_to_pixel(F, j, px, py)) rgba_out[(size_t)py * F.width + px] = shade(__fdiv_rn(1.0f, ph.t));
+            }
         }
         if (rays_by_item) { float4* o2 = reinterpret_cast<float4*>(rays_by_item + j); o2[0] = a; o2[1] = b; }
     }
@@ -516,7 +531,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                 float col;
                 if (P.shade_mode == SHADE_PRIMARY) col = __fdiv_rn(1.0f, h.t);                       // rt_cpu.rs:59
                 else col = h.t < F32_MAX_ ? __fdiv_rn(h.t, add(1.0f, h.t)) : 1.0f;                   // rt_cpu.rs:82-87
-                P.rgba_out[item] = shade(col);
+                const long long o = rgba_slot(item, P.frame_w, P.frame_h, P.frame_tiles_x, P.frame_shard, P.frame_shards);
+                if (o >= 0) P.rgba_out[o] = shade(col);
             }
             if (COUNT && best_prim != INVALID) c_hits++;
             cur_x = 0; cur_y = 0;                                                                    // IDLE

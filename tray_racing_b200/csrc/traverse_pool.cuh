@@ -77,7 +77,8 @@ __global__ void __launch_bounds__(POOL_WARPS * 32, TRAY_POOL_MIN_BLOCKS) trace_p
                 float col;
                 if (P.shade_mode == SHADE_PRIMARY) col = __fdiv_rn(1.0f, h.t);                       // rt_cpu.rs:59
                 else col = h.t < F32_MAX_ ? __fdiv_rn(h.t, add(1.0f, h.t)) : 1.0f;                   // rt_cpu.rs:82-87
-                P.rgba_out[item] = shade(col);
+                const long long o = rgba_slot(item, P.frame_w, P.frame_h, P.frame_tiles_x, P.frame_shard, P.frame_shards);
+                if (o >= 0) P.rgba_out[o] = shade(col);
             }
             if (COUNT && best_prim != INVALID) c_hits++;
             cur_x = 0; cur_y = 0; tri_x = 0; tri_y = 0;                                              // slot is idle

@@ -76,6 +76,7 @@ struct tray_scene {
     uint32_t* d_bitem = nullptr;             // local item of compact bounce ray i
     tray_ray* d_brays_item = nullptr;        // optional: bounce rays by local item (TRAY_RENDER_KEEP_RAYS)
     void* d_untiled = nullptr; uint64_t untiled_cap = 0;
+    uchar4* frame_target = nullptr;          // borrowed: row-major RGBA8 frame (this or a peer device), see tray_cuda_scene_set_frame_target
     tray::FrameParams last_frame;
     tray_counters cnt_primary{}, cnt_bounce{};
 };
@@ -354,6 +355,56 @@ int tray_cuda_untile_rgba(tray_scene* s, const void* d_compact, uint32_t w, uint
     return TRAY_OK;
 }
 
+int tray_cuda_frame_alloc(int device, uint64_t bytes, void** d_ptr) {
+    if (!d_ptr || bytes == 0) return fail(TRAY_ERR_ARG, "bad argument");
+    if (tray_cuda_device_count() == 0) return fail(TRAY_ERR_NO_DEVICE, "no CUDA device");
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(d_ptr, bytes));
+    CU(cudaMemset(*d_ptr, 0, bytes));
+    return TRAY_OK;
+}
+
+int tray_cuda_frame_free(int device, void* d_ptr) {
+    if (!d_ptr) return TRAY_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaFree(d_ptr));
+    return TRAY_OK;
+}
+
+int tray_cuda_ipc_export(int device, void* d_ptr, uint8_t handle[64]) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+    if (!d_ptr || !handle) return fail(TRAY_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(handle, &h, 64);
+    return TRAY_OK;
+}
+
+int tray_cuda_ipc_open(int device, const uint8_t handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return fail(TRAY_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TRAY_OK;
+}
+
+int tray_cuda_ipc_close(int device, void* d_ptr) {
+    if (!d_ptr) return TRAY_OK;
+    CU(cudaSetDevice(device));
+    CU(cudaIpcCloseMemHandle(d_ptr));
+    return TRAY_OK;
+}
+
+int tray_cuda_scene_set_frame_target(tray_scene* s, void* d_frame) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    s->frame_target = (uchar4*)d_frame;
+    return TRAY_OK;
+}
+
 int tray_cuda_sync(tray_scene* s) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
     CU(cudaSetDevice(s->device));
@@ -450,7 +501,7 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     }
     FrameParams F; frame_params(F, view, w, h, frame_count, shard, shards);
     s->fw = w; s->fh = h; s->fshard = shard; s->fshards = shards; s->f_items = F.n_items;
-    s->f_has_bounce = bounce; s->f_has_rgba = rgba; s->f_has_rays = keep_rays && bounce;
+    s->f_has_bounce = bounce; s->f_has_rgba = rgba && !s->frame_target; s->f_has_rays = keep_rays && bounce;
     s->last_frame = F;
     if (F.n_items == 0) { if (ms_primary) *ms_primary = 0.f; if (ms_bounce) *ms_bounce = 0.f; return TRAY_OK; }
     const unsigned gen_grid = (F.n_items + 255) / 256;
@@ -463,7 +514,13 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     CU(cudaGetLastError());
     TraceParams P; base_params(s, P);
     P.rays = s->d_prays; P.n_work = F.n_items; P.hits_out = s->d_primary;
-    P.rgba_out = (rgba && !bounce) ? s->d_rgba : nullptr; P.shade_mode = SHADE_PRIMARY;
+    uchar4* const rgba_dst = s->frame_target ? s->frame_target : s->d_rgba;
+    auto set_frame = [&](TraceParams& T) {
+        if (!s->frame_target) return;
+        T.frame_w = w; T.frame_h = h; T.frame_tiles_x = F.tiles_x; T.frame_shard = shard; T.frame_shards = shards;
+    };
+    P.rgba_out = (rgba && !bounce) ? rgba_dst : nullptr; P.shade_mode = SHADE_PRIMARY;
+    if (P.rgba_out) set_frame(P);
     int rc = launch(s, P, s->stream, 0);
     if (rc) return rc;
     if (timed) CU(cudaEventRecord(s->ev[1], s->stream));
@@ -473,14 +530,15 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
         CU(cudaMemsetAsync(d_nbrays, 0, sizeof(uint32_t), s->stream));
         if (s->tri_stride == 64)
             tray::raygen_bounce_kernel<64><<<gen_grid, 256, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays,
-                                                                            s->d_bounce, rgba ? s->d_rgba : nullptr, keep_rays ? s->d_brays_item : nullptr);
+                                                                            s->d_bounce, rgba ? rgba_dst : nullptr, keep_rays ? s->d_brays_item : nullptr, s->frame_target ? 1u : 0u);
         else
             tray::raygen_bounce_kernel<48><<<gen_grid, 256, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays,
-                                                                            s->d_bounce, rgba ? s->d_rgba : nullptr, keep_rays ? s->d_brays_item : nullptr);
+                                                                            s->d_bounce, rgba ? rgba_dst : nullptr, keep_rays ? s->d_brays_item : nullptr, s->frame_target ? 1u : 0u);
         CU(cudaGetLastError());
         TraceParams B; base_params(s, B);
         B.rays = s->d_brays; B.ray_item = s->d_bitem; B.n_work = F.n_items; B.n_work_dev = d_nbrays;   // count stays on the device
-        B.hits_out = s->d_bounce; B.rgba_out = rgba ? s->d_rgba : nullptr; B.shade_mode = SHADE_BOUNCE;
+        B.hits_out = s->d_bounce; B.rgba_out = rgba ? rgba_dst : nullptr; B.shade_mode = SHADE_BOUNCE;
+        if (B.rgba_out) set_frame(B);
         rc = launch(s, B, s->stream, 1);
         if (rc) return rc;
         if (timed) CU(cudaEventRecord(s->ev[2], s->stream));

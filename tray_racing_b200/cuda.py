@@ -22,6 +22,8 @@ EXPORTS = (
     "tray_cuda_shard_pixels", "tray_cuda_frame_download", "tray_cuda_frame_device_ptrs", "tray_cuda_sync",
     "tray_cuda_counters", "tray_cuda_set_counting", "tray_cuda_start", "tray_cuda_last_error",
     "tray_cuda_untile_rgba", "tray_cuda_scene_set_stream", "tray_cuda_bandwidth_probe",
+    "tray_cuda_frame_alloc", "tray_cuda_frame_free", "tray_cuda_ipc_export", "tray_cuda_ipc_open", "tray_cuda_ipc_close",
+    "tray_cuda_scene_set_frame_target",
 )
 
 
@@ -92,6 +94,18 @@ def lib() -> C.CDLL:
         L.tray_cuda_scene_set_stream.argtypes = [vp, vp]
         L.tray_cuda_bandwidth_probe.restype = i32
         L.tray_cuda_bandwidth_probe.argtypes = [i32, u64, i32, f32p]
+        L.tray_cuda_frame_alloc.restype = i32
+        L.tray_cuda_frame_alloc.argtypes = [i32, u64, C.POINTER(vp)]
+        L.tray_cuda_frame_free.restype = i32
+        L.tray_cuda_frame_free.argtypes = [i32, vp]
+        L.tray_cuda_ipc_export.restype = i32
+        L.tray_cuda_ipc_export.argtypes = [i32, vp, C.c_char_p]
+        L.tray_cuda_ipc_open.restype = i32
+        L.tray_cuda_ipc_open.argtypes = [i32, C.c_char_p, C.POINTER(vp)]
+        L.tray_cuda_ipc_close.restype = i32
+        L.tray_cuda_ipc_close.argtypes = [i32, vp]
+        L.tray_cuda_scene_set_frame_target.restype = i32
+        L.tray_cuda_scene_set_frame_target.argtypes = [vp, vp]
         L.tray_cuda_counters.restype = i32
         L.tray_cuda_counters.argtypes = [vp, C.POINTER(Counters), C.POINTER(Counters)]
         L.tray_cuda_set_counting.restype = i32
@@ -117,6 +131,36 @@ def bandwidth_probe(nbytes: int, iters: int = 20, device: int = 0) -> float:
     g = C.c_float()
     _check(lib().tray_cuda_bandwidth_probe(device, int(nbytes), int(iters), C.byref(g)))
     return g.value
+
+
+def frame_alloc(nbytes: int, device: int = 0) -> int:
+    """A zeroed device allocation that can be exported over CUDA IPC (the shared row-major frame of a multi-GPU run)."""
+    p = C.c_void_p()
+    _check(lib().tray_cuda_frame_alloc(device, int(nbytes), C.byref(p)))
+    return p.value
+
+
+def frame_free(ptr: int, device: int = 0):
+    _check(lib().tray_cuda_frame_free(device, C.c_void_p(ptr)))
+
+
+def ipc_export(ptr: int, device: int = 0) -> bytes:
+    h = C.create_string_buffer(64)
+    _check(lib().tray_cuda_ipc_export(device, C.c_void_p(ptr), h))
+    return h.raw
+
+
+def ipc_open(handle: bytes, device: int = 0) -> int:
+    """Map another process's frame_alloc() allocation (same box) into this process; enables peer access."""
+    if len(handle) != 64:
+        raise ValueError("a CUDA IPC handle is 64 bytes")
+    p = C.c_void_p()
+    _check(lib().tray_cuda_ipc_open(device, C.create_string_buffer(handle, 64), C.byref(p)))
+    return p.value
+
+
+def ipc_close(ptr: int, device: int = 0):
+    _check(lib().tray_cuda_ipc_close(device, C.c_void_p(ptr)))
 
 
 def shard_pixels(w: int, h: int, shard: int = 0, shards: int = 1) -> int:
@@ -234,6 +278,11 @@ class TrayCudaScene:
     def set_stream(self, cuda_stream: int):
         """Enqueue this scene's work on a caller-owned cudaStream_t (0 restores the scene's own stream)."""
         _check(lib().tray_cuda_scene_set_stream(self._h, cuda_stream or None))
+
+    def set_frame_target(self, d_frame: int | None):
+        """RGBA of later renders goes straight into the row-major frame at `d_frame` (this GPU or a peer mapping from
+        ipc_open): the fused framebuffer exchange of include/tray_cuda.h.  None restores the compact local buffer."""
+        _check(lib().tray_cuda_scene_set_frame_target(self._h, C.c_void_p(d_frame or 0)))
 
     def untile_rgba(self, d_compact: int, width: int, height: int, shard: int, shards: int, d_frame: int):
         _check(lib().tray_cuda_untile_rgba(self._h, d_compact, width, height, shard, shards, d_frame))
