@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TRAY_CUDA_ABI_VERSION 1u
+#define TRAY_CUDA_ABI_VERSION 2u
 
 /* ---- status codes -------------------------------------------------------------------------- */
 typedef enum tray_status {
@@ -183,6 +183,13 @@ int tray_cuda_trace_device(tray_scene* scene, const tray_ray* d_rays, uint64_t n
 int tray_cuda_render(tray_scene* scene, const tray_view* view, uint32_t width, uint32_t height,
                      uint32_t frame_count, uint32_t flags, uint32_t shard_index, uint32_t shard_count,
                      float* ms_primary, float* ms_bounce);
+
+/* Same frame, timed as a whole: *ms_frame is the CUDA-event time from the first ray-generation launch to the
+ * end of the last traversal kernel — what the reference's timestamp queries bracket
+ * (rt_gpu_software.rs:296-301,337-344).  Synchronises.                                                  */
+int tray_cuda_render_timed(tray_scene* scene, const tray_view* view, uint32_t width, uint32_t height,
+                           uint32_t frame_count, uint32_t flags, uint32_t shard_index, uint32_t shard_count,
+                           float* ms_frame);
 
 /* Number of pixels (= primary rays) shard `shard_index` owns for a width x height frame. */
 uint64_t tray_cuda_shard_pixels(uint32_t width, uint32_t height, uint32_t shard_index, uint32_t shard_count);

@@ -1,0 +1,20 @@
+"""Dev: when do the persistent warps of a traversal launch run dry / exit?
+
+Build the instrumented library (`make -C tray_racing_b200/csrc exitlog`), then on a GPU
+  TRAY_CUDA_LIB=$PWD/tray_racing_b200/libtray_cuda_exitlog.so TRAY_EXIT_LOG_FILE=gpurun_out/exitlog \
+      python scripts/render_frames.py --scene hairball --frames 3
+and read the dumps here:  python scripts/exit_log.py gpurun_out/exitlog.*.bin
+Each dump holds, per warp, the %globaltimer (ns) at which the work cursor was exhausted for it and at which it exited."""
+import sys
+
+import numpy as np
+
+for f in sorted(sys.argv[1:], key=lambda x: int(x.split(".")[-2])):
+    a = np.fromfile(f, dtype=np.uint64).reshape(-1, 2).astype(np.int64)
+    dry, ex = a[:, 0], a[:, 1]
+    ok = ex > 0
+    t_end = ex[ok].max()
+    d = dry[ok & (dry > 0)]
+    q = (t_end - np.percentile(ex[ok], [10, 50, 90, 99])) / 1e3
+    print(f"{f}: {int(ok.sum())} warps | cursor dry {(t_end - np.median(d)) / 1e3:.1f} us before the launch ends (first {(t_end - d.min()) / 1e3:.1f}, last {(t_end - d.max()) / 1e3:.1f})"
+          f" | warps exit p10 {q[0]:.1f} p50 {q[1]:.1f} p90 {q[2]:.1f} p99 {q[3]:.1f} us before the end")

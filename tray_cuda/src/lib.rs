@@ -36,6 +36,8 @@ extern "C" {
         ms_kernel: *mut f32, ms_total: *mut f32) -> c_int;
     pub fn tray_cuda_render(scene: *mut TrayScene, view: *const TrayView, width: u32, height: u32, frame_count: u32,
         flags: u32, shard_index: u32, shard_count: u32, ms_primary: *mut f32, ms_bounce: *mut f32) -> c_int;
+    pub fn tray_cuda_render_timed(scene: *mut TrayScene, view: *const TrayView, width: u32, height: u32, frame_count: u32,
+        flags: u32, shard_index: u32, shard_count: u32, ms_frame: *mut f32) -> c_int;
     pub fn tray_cuda_frame_download(scene: *mut TrayScene, primary: *mut TrayHit, bounce: *mut TrayHit,
         bounce_rays: *mut TrayRay, rgba: *mut u8) -> c_int;
     pub fn tray_cuda_start(bvh: *const c_void, bvh_len: u64, inst: *const c_void, inst_len: u64, tris: *const c_void,

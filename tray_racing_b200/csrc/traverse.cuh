@@ -560,6 +560,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                 uint32_t base = 0;
                 if ((int)lane == leader) base = atomicAdd(P.cursor, n_idle);
                 base = __shfl_sync(FULL, base, leader);
+#ifdef TRAY_EXIT_LOG
+                if (base + n_idle >= n_work && !exhausted && P.spill && lane == 0) {   // ... and when it ran dry
+                    unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                    ((unsigned long long*)P.spill)[2 * (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5))] = t;
+                }
+#endif
                 if (base + n_idle >= n_work) exhausted = true;
                 if ((idle >> lane) & 1u) {
                     ray_idx = base + (uint32_t)__popc(idle & ((1u << lane) - 1u));
@@ -633,6 +639,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
         }
     }
 
+#ifdef TRAY_EXIT_LOG
+    if (P.spill && lane == 0) {       // dev instrumentation (scripts/exit_log.py): when this warp exited (ns)
+        unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+        ((unsigned long long*)P.spill)[2 * (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5)) + 1] = t;
+    }
+#endif
     if (COUNT) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {

@@ -23,7 +23,7 @@ EXPORTS = (
     "tray_cuda_counters", "tray_cuda_set_counting", "tray_cuda_start", "tray_cuda_last_error",
     "tray_cuda_untile_rgba", "tray_cuda_scene_set_stream", "tray_cuda_bandwidth_probe",
     "tray_cuda_frame_alloc", "tray_cuda_frame_free", "tray_cuda_ipc_export", "tray_cuda_ipc_open", "tray_cuda_ipc_close",
-    "tray_cuda_scene_set_frame_target",
+    "tray_cuda_scene_set_frame_target", "tray_cuda_render_timed",
 )
 
 
@@ -80,6 +80,8 @@ def lib() -> C.CDLL:
         L.tray_cuda_trace_device.argtypes = [vp, vp, u64, vp, vp, f32p]
         L.tray_cuda_render.restype = i32
         L.tray_cuda_render.argtypes = [vp, C.POINTER(TrayView), u32, u32, u32, u32, u32, u32, f32p, f32p]
+        L.tray_cuda_render_timed.restype = i32
+        L.tray_cuda_render_timed.argtypes = [vp, C.POINTER(TrayView), u32, u32, u32, u32, u32, u32, f32p]
         L.tray_cuda_shard_pixels.restype = u64
         L.tray_cuda_shard_pixels.argtypes = [u32, u32, u32, u32]
         L.tray_cuda_frame_download.restype = i32
@@ -235,6 +237,15 @@ class TrayCudaScene:
         self.frame_size = (width, height)
         self.frame_shard = (shard, shards)
         return (a.value, b.value) if timed else None
+
+    def render_frame_ms(self, view: TrayView, width: int, height: int, frame_count: int = 0, flags: int = RENDER_BOUNCE | RENDER_RGBA,
+                        shard: int = 0, shards: int = 1) -> float:
+        """Whole-frame CUDA-event time (ray generation + both traversal launches) — tray_cuda_render_timed."""
+        ms = C.c_float()
+        _check(lib().tray_cuda_render_timed(self._h, C.byref(view), width, height, frame_count, flags, shard, shards, C.byref(ms)))
+        self.frame_size = (width, height)
+        self.frame_shard = (shard, shards)
+        return ms.value
 
     def download(self, primary=False, bounce=False, bounce_rays=False, rgba=False, into: dict | None = None,
                  merge: bool = False) -> dict:
