@@ -61,9 +61,12 @@ typedef struct tray_cwbvh_node {
 /* Triangle record, BVH order (tris[primitive_indices[i]], src/rt_cpu/mod.rs:38-43).
  * f32 like the CPU path's obvhs `RtTriangle` {v0, e1 = v0 - v1, e2 = v2 - v0, ng = cross(e1, e2)}
  *  — NOT the f16 `RtCompressedTriangle` of the wgpu path, which cannot meet
- * the 1e-5 parity bar.  Two strides are accepted:
+ * the 1e-5 parity bar.  Two strides are accepted for the parity path:
  *   48: {v0.xyz, pad, e1.xyz, pad, e2.xyz, pad}           (ng recomputed in-register, bit-identical)
- *   64: {v0, e1, e2, ng} each padded to 16 B              (byte image of [RtTriangle])           */
+ *   64: {v0, e1, e2, ng} each padded to 16 B              (byte image of [RtTriangle])
+ * and, as the NON-parity variant of SURVEY.md §8 f4 (half the triangle bytes per test),
+ *   24: the wgpu path's own `RtCompressedTriangle` byte image {v0: f32 x 3, e: u32 x 3},
+ *       e[k] = half(v2 - v0)[k] | half(v1 - v0)[k] << 16  (src/rt_gpu/mod.rs:39-43,86; query.hlsl:75-85) */
 typedef struct tray_tri48 {
     float v0[3], pad0;
     float e1[3], pad1;
@@ -76,6 +79,11 @@ typedef struct tray_tri64 {
     float e2[3], pad2;
     float ng[3], pad3;
 } tray_tri64;
+
+typedef struct tray_tri24 {
+    float    v0[3];
+    uint32_t e[3];               /* e[k] = half(v2 - v0)[k] | half(v1 - v0)[k] << 16 */
+} tray_tri24;
 
 /* Ray = obvhs `Ray::new(origin, direction, tmin, tmax)` (src/rt_cpu/rt_cpu.rs:50-55).  32 bytes. */
 typedef struct tray_ray {
@@ -130,6 +138,8 @@ typedef struct tray_scene_info {
 #define TRAY_RENDER_RGBA       0x2u /* write pow(col,2.2)*255 RGBA8 (rt_cpu.rs:102-107)                       */
 #define TRAY_RENDER_COUNTERS   0x4u /* run the counting build of the kernels (slower; fills tray_counters)    */
 #define TRAY_RENDER_KEEP_RAYS  0x8u /* also store the generated bounce rays (for checkers)                    */
+#define TRAY_RENDER_ANYHIT_AO  0x10u /* bounce rays stop at their FIRST hit (rt_cpu.rs:78-79 "a faster anyhit query"):
+                                      * the bounce buffer holds that hit, RGBA is visibility (0 / 1) — not the reference image */
 
 typedef struct tray_scene tray_scene;
 
@@ -144,7 +154,7 @@ unsigned tray_cuda_abi_version(void);
  * rt_gpu_software.rs:177-180 with the argument meaning of `start()` (rt_gpu_software.rs:24-32):
  *   nodes/n_nodes   bvh_bytes as 80-byte nodes: flat BVH with root at 0, or BLAS0|BLAS1|..|TLAS with
  *                   the TLAS root at index `tlas_start` (src/rt_gpu/mod.rs:62-69,88-91,99)
- *   tris/n_tris     tri_bytes, BVH-ordered, stride 48 or 64 (see above)
+ *   tris/n_tris     tri_bytes, BVH-ordered, stride 48, 64 or 24 (see above)
  *   blas_offsets    instance_bytes as u32: node offset of the BLAS behind TLAS leaf k
  *                   (src/rt_gpu/mod.rs:72-78); NULL / n_instances = 0 selects single-level traversal
  *   tlas_start      node index of the TLAS root; ignored when n_instances == 0                     */
@@ -170,6 +180,15 @@ int tray_cuda_trace(tray_scene* scene, const tray_ray* rays, uint64_t n, tray_hi
  * ms_kernel != NULL.                                                                             */
 int tray_cuda_trace_device(tray_scene* scene, const tray_ray* d_rays, uint64_t n, tray_hit* d_hits,
                            void* stream, float* ms_kernel);
+
+/* Any hit: the same traversal, each ray stopped at the FIRST accepted triangle — the shadow /
+ * occlusion query the reference wishes for at rt_cpu.rs:78-79 (its own intersects_bl_bvh, query.hlsl:440-445, runs
+ * the closest-hit loop).  hits[i] = that triangle and its t, or {+inf, 0xFFFFFFFF}; hits[i].prim != 0xFFFFFFFF
+ * exactly when tray_cuda_trace finds a hit for the same ray.                                              */
+int tray_cuda_trace_any(tray_scene* scene, const tray_ray* rays, uint64_t n, tray_hit* hits,
+                        float* ms_kernel, float* ms_total);
+int tray_cuda_trace_any_device(tray_scene* scene, const tray_ray* d_rays, uint64_t n, tray_hit* d_hits,
+                               void* stream, float* ms_kernel);
 
 /* ---- frame operator: the render loop body (src/rt_cpu/rt_cpu.rs:35-91, rt_gpu_software.hlsl:47-144) */
 

@@ -36,7 +36,7 @@
 
 static uint32_t g_variant = ORC_VARIANT_DEFAULT;
 void orc_set_variant(uint32_t flags) { g_variant = flags; }
-unsigned orc_abi_version(void) { return 1u; }
+unsigned orc_abi_version(void) { return 2u; }
 int orc_max_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
@@ -139,10 +139,40 @@ uint32_t orc_node_intersect(const uint8_t* node80, const orc_ray* ray, float tma
 /* ---- RtTriangle::intersect, twin intersect_ray_tri (query.hlsl:89-129) -----------------------
  * Record = {v0, e1 = v0 - v1, e2 = v2 - v0 [, ng = cross(e1,e2)]}, 16-byte padded vectors.
  * Returns t, or +inf for a miss, with the range test `t >= tmin && t <= tmax` of query.hlsl:120. */
+/* IEEE binary16 -> binary32, exact (f16tof32 of unpack_2x16f_uint, query.hlsl:75-85) */
+static inline float half_to_float(uint32_t h) {
+    uint32_t sign = (h & 0x8000u) << 16, e = (h >> 10) & 0x1fu, m = h & 0x3ffu;
+    if (e == 0) {
+        if (m == 0) return as_float(sign);
+        float f = (float)m * 5.9604644775390625e-8f;                   /* subnormal: m * 2^-24, exact */
+        return (sign ? -f : f);
+    }
+    if (e == 31) return as_float(sign | 0x7f800000u | (m << 13));
+    return as_float(sign | ((e + 112u) << 23) | (m << 13));
+}
+
+float orc_half_to_float(uint16_t h) { return half_to_float(h); }
+
+/* v0, e1 = v0 - v1, e2 = v2 - v0 of one record.  Stride 48/64: the CPU path's f32 RtTriangle.  Stride 24: the wgpu
+ * path's RtCompressedTriangle {v0: [f32;3], e: [u32;3]}, e[k] = half(e2[k]) | half((v1 - v0)[k]) << 16
+ * (src/rt_gpu/mod.rs:39-43, unpack query.hlsl:75-85, e1 negated at query.hlsl:91) — NOT the parity path. */
+static inline void tri_load(const uint8_t* rec, uint32_t stride, float v0[3], float e1[3], float e2[3]) {
+    v0[0] = load_f32(rec + 0); v0[1] = load_f32(rec + 4); v0[2] = load_f32(rec + 8);
+    if (stride == 24) {
+        for (int k = 0; k < 3; k++) {
+            uint32_t e = load_u32(rec + 12 + 4 * k);
+            e2[k] = half_to_float(e & 0xffffu);
+            e1[k] = -half_to_float(e >> 16);
+        }
+    } else {
+        e1[0] = load_f32(rec + 16); e1[1] = load_f32(rec + 20); e1[2] = load_f32(rec + 24);
+        e2[0] = load_f32(rec + 32); e2[1] = load_f32(rec + 36); e2[2] = load_f32(rec + 40);
+    }
+}
+
 static inline float tri_intersect(const uint8_t* rec, uint32_t stride, const prep_ray* r, float tmax) {
-    float v0[3] = { load_f32(rec + 0), load_f32(rec + 4), load_f32(rec + 8) };
-    float e1[3] = { load_f32(rec + 16), load_f32(rec + 20), load_f32(rec + 24) };
-    float e2[3] = { load_f32(rec + 32), load_f32(rec + 36), load_f32(rec + 40) };
+    float v0[3], e1[3], e2[3];
+    tri_load(rec, stride, v0, e1, e2);
     float ng[3];
     if (stride == 64) { ng[0] = load_f32(rec + 48); ng[1] = load_f32(rec + 52); ng[2] = load_f32(rec + 56); }
     else cross3(e1, e2, ng);                                           /* query.hlsl:93 */
@@ -172,7 +202,9 @@ static inline int closer(float t, float tmax) {
 }
 
 /* ---- CwBvh::ray_traverse / ray_traverse_tlas_blas; twins query.hlsl:328-438, query_tlas.hlsl:333-500 */
-static int trace_one(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_count* cnt, uint8_t* oplog) {
+/* `any_hit`: stop at the first accepted triangle (the "faster anyhit query" rt_cpu.rs:78-79 asks for; the reference's
+ * own intersects_bl_bvh, query.hlsl:440-445, runs the full closest-hit loop).  Same order of tests up to that point. */
+static int trace_one_ex(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_count* cnt, uint8_t* oplog, int any_hit) {
     uint32_t n_ops = 0;   /* optional step log: 'N' node fetch+test, 'T' triangle test, 'I' instance entry */
     prep_ray r; prepare_ray(ray, &r);
     uint32_t stack[ORC_STACK][2];
@@ -240,8 +272,10 @@ static int trace_one(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_c
             if (oplog) oplog[n_ops++] = 'T';
             float t = tri_intersect(s->tris + (uint64_t)global * s->tri_stride, s->tri_stride, &r, best_t);
             if (closer(t, best_t)) { best_t = t; best_prim = global; }     /* :410-413 with the CPU tie rule */
+            if (any_hit && best_prim != ORC_INVALID_PRIM) break;
         }
         if (overflow) break;
+        if (any_hit && best_prim != ORC_INVALID_PRIM) break;
 
         if ((cur_y & 0xff000000u) == 0) {                                  /* :417 */
             if (size == 0) break;                                          /* :420-424 */
@@ -257,6 +291,27 @@ static int trace_one(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_c
     else { out->t = INFINITY; out->prim = ORC_INVALID_PRIM; }              /* RayHit::none() */
     if (cnt) { cnt->nodes = n_nodes; cnt->tris = n_tris; cnt->insts = n_insts; }
     return overflow ? -4 : 0;
+}
+
+static int trace_one(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_count* cnt, uint8_t* oplog) {
+    return trace_one_ex(s, ray, out, cnt, oplog, 0);
+}
+
+int orc_trace_any(const orc_scene* s, const orc_ray* rays, uint64_t n, orc_hit* hits, orc_count* counts,
+                  orc_totals* totals, int nthreads) {
+    int rc = 0;
+    uint64_t tn = 0, tt = 0, ti = 0, th = 0;
+    if (nthreads <= 0) nthreads = orc_max_threads();
+#pragma omp parallel for schedule(dynamic, 2048) num_threads(nthreads) reduction(+:tn,tt,ti,th) reduction(min:rc)
+    for (int64_t i = 0; i < (int64_t)n; i++) {
+        orc_count c;
+        int e = trace_one_ex(s, &rays[i], &hits[i], &c, NULL, 1);
+        if (e < rc) rc = e;
+        if (counts) counts[i] = c;
+        tn += c.nodes; tt += c.tris; ti += c.insts; th += hits[i].prim != ORC_INVALID_PRIM;
+    }
+    if (totals) { totals->rays = n; totals->nodes = tn; totals->tris = tt; totals->insts = ti; totals->hits = th; }
+    return rc;
 }
 
 int orc_trace(const orc_scene* s, const orc_ray* rays, uint64_t n, orc_hit* hits, orc_count* counts,
@@ -387,8 +442,8 @@ void orc_bounce_ray(const orc_scene* s, const orc_view* vw, const orc_ray* pr, c
     memset(out, 0, sizeof(*out));
     if (!(hit->t < F32_MAX)) return;                                    /* rt_cpu.rs:61 */
     const uint8_t* rec = s->tris + (uint64_t)hit->prim * s->tri_stride;
-    float e1[3] = { load_f32(rec + 16), load_f32(rec + 20), load_f32(rec + 24) };
-    float e2[3] = { load_f32(rec + 32), load_f32(rec + 36), load_f32(rec + 40) };
+    float v0[3], e1[3], e2[3];
+    tri_load(rec, s->tri_stride, v0, e1, e2);
     float n[3];
     if (s->tri_stride == 64) { n[0] = load_f32(rec + 48); n[1] = load_f32(rec + 52); n[2] = load_f32(rec + 56); }
     else cross3(e1, e2, n);

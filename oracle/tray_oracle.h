@@ -34,7 +34,7 @@ typedef struct orc_view {          /* ViewUniform, src/main.rs:589-617, 160 B */
 
 typedef struct orc_scene {
     const uint8_t* nodes;  uint64_t n_nodes;      /* 80-byte CwBvhNode records */
-    const uint8_t* tris;   uint64_t n_tris;  uint32_t tri_stride;   /* 48 or 64 */
+    const uint8_t* tris;   uint64_t n_tris;  uint32_t tri_stride;   /* 48 or 64 (f32, parity path); 24 = f16 edges (wgpu path) */
     const uint32_t* blas_offsets; uint32_t n_instances; uint32_t tlas_start;
     int use_tlas;
 } orc_scene;
@@ -58,6 +58,11 @@ int orc_max_threads(void);
 int orc_trace(const orc_scene* s, const orc_ray* rays, uint64_t n, orc_hit* hits, orc_count* counts,
               orc_totals* totals, int nthreads);
 
+/* any hit: the same traversal, stopped at the FIRST accepted triangle (hits[i] = that triangle and its t).
+ * hits[i].prim != ORC_INVALID_PRIM  <=>  orc_trace finds a hit for the same ray. */
+int orc_trace_any(const orc_scene* s, const orc_ray* rays, uint64_t n, orc_hit* hits, orc_count* counts,
+                  orc_totals* totals, int nthreads);
+
 /* per-ray step log ('N' node, 'T' triangle, 'I' instance entry) for warp-scheduling studies in tests/tools */
 int orc_trace_oplog(const orc_scene* s, const orc_ray* rays, uint64_t n, const orc_count* counts,
                     uint8_t* ops, const uint64_t* offsets, int nthreads);
@@ -66,6 +71,9 @@ int orc_trace_oplog(const orc_scene* s, const orc_ray* rays, uint64_t n, const o
  * also reports how many triangles tie with the winning t (for the tie census). */
 int orc_brute_force(const orc_scene* s, const orc_ray* rays, uint64_t n, orc_hit* hits,
                     uint32_t* n_ties, int nthreads);
+
+/* IEEE binary16 -> binary32 as the f16 triangle records are decoded (query.hlsl:75-85) */
+float orc_half_to_float(uint16_t h);
 
 /* ray/triangle test on one record; returns t or +inf */
 float orc_intersect_tri(const orc_scene* s, uint32_t prim, const orc_ray* ray);

@@ -58,10 +58,14 @@ def lib() -> C.CDLL:
         L.orc_max_threads.restype = i32
         L.orc_trace.restype = i32
         L.orc_trace.argtypes = [C.POINTER(OrcScene), vp, u64, vp, vp, C.POINTER(OrcTotals), i32]
+        L.orc_trace_any.restype = i32
+        L.orc_trace_any.argtypes = [C.POINTER(OrcScene), vp, u64, vp, vp, C.POINTER(OrcTotals), i32]
         L.orc_brute_force.restype = i32
         L.orc_brute_force.argtypes = [C.POINTER(OrcScene), vp, u64, vp, vp, i32]
         L.orc_intersect_tri.restype = C.c_float
         L.orc_intersect_tri.argtypes = [C.POINTER(OrcScene), u32, vp]
+        L.orc_half_to_float.restype = C.c_float
+        L.orc_half_to_float.argtypes = [C.c_uint16]
         L.orc_primary_rays.argtypes = [C.POINTER(OrcView), u32, u32, vp, i32]
         L.orc_render.restype = i32
         L.orc_render.argtypes = [C.POINTER(OrcScene), C.POINTER(OrcView), u32, u32, u32, u32, vp, vp, vp, vp,
@@ -102,12 +106,14 @@ class Oracle:
     def from_packed(cls, p) -> "Oracle":
         return cls(p.bvh_bytes, p.tri_bytes, p.tri_stride, p.blas_offsets if p.use_tlas else None, p.tlas_start, p.use_tlas)
 
-    def trace(self, rays, counts=False, nthreads=0):
+    def trace(self, rays, counts=False, nthreads=0, any_hit=False):
+        """closest hit per ray; any_hit=True stops each ray at the first accepted triangle (orc_trace_any)"""
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
         cnt = np.empty(rays.shape[0], dtype=COUNT_DTYPE) if counts else None
         tot = OrcTotals()
-        rc = lib().orc_trace(C.byref(self.scene), rays.ctypes.data, rays.shape[0], hits.ctypes.data,
+        fn = lib().orc_trace_any if any_hit else lib().orc_trace
+        rc = fn(C.byref(self.scene), rays.ctypes.data, rays.shape[0], hits.ctypes.data,
                              None if cnt is None else cnt.ctypes.data, C.byref(tot), nthreads)
         if rc != 0:
             raise RuntimeError(f"oracle traversal stack overflow ({rc})")

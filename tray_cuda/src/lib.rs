@@ -34,6 +34,8 @@ extern "C" {
     pub fn tray_cuda_scene_destroy(scene: *mut TrayScene);
     pub fn tray_cuda_trace(scene: *mut TrayScene, rays: *const TrayRay, n: u64, hits: *mut TrayHit,
         ms_kernel: *mut f32, ms_total: *mut f32) -> c_int;
+    pub fn tray_cuda_trace_any(scene: *mut TrayScene, rays: *const TrayRay, n: u64, hits: *mut TrayHit,
+        ms_kernel: *mut f32, ms_total: *mut f32) -> c_int;
     pub fn tray_cuda_render(scene: *mut TrayScene, view: *const TrayView, width: u32, height: u32, frame_count: u32,
         flags: u32, shard_index: u32, shard_count: u32, ms_primary: *mut f32, ms_bounce: *mut f32) -> c_int;
     pub fn tray_cuda_render_timed(scene: *mut TrayScene, view: *const TrayView, width: u32, height: u32, frame_count: u32,

@@ -24,6 +24,29 @@ struct tray_mesh {
 
 namespace {
 
+// binary32 -> binary16, round to nearest even (what the `half` crate's f16::from_f32 does)
+uint16_t float_to_half(float f) {
+    uint32_t x; std::memcpy(&x, &f, 4);
+    const uint32_t sign = (x >> 16) & 0x8000u;
+    x &= 0x7fffffffu;
+    if (x >= 0x7f800000u) return (uint16_t)(sign | 0x7c00u | (x > 0x7f800000u ? 0x200u : 0u));   // inf / nan
+    if (x >= 0x477ff000u) return (uint16_t)(sign | 0x7c00u);                                      // rounds to >= 65520: inf
+    if (x < 0x33000001u) return (uint16_t)sign;                                                   // <= 2^-25: zero
+    if (x < 0x38800000u) {                                                                        // subnormal half
+        const uint32_t e = x >> 23, m = (x & 0x7fffffu) | 0x800000u;
+        const uint32_t shift = 126u - e;                        // 14..24: the half subnormal keeps the top 24 - shift bits of m
+        uint32_t h = m >> shift;
+        const uint32_t rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1u);
+        if (rem > half || (rem == half && (h & 1u))) h++;
+        return (uint16_t)(sign | h);
+    }
+    uint32_t h = ((x >> 23) - 112u) << 10 | ((x >> 13) & 0x3ffu);
+    const uint32_t rem = x & 0x1fffu;
+    if (rem > 0x1000u || (rem == 0x1000u && (h & 1u))) h++;      // may carry into the exponent: still the right value
+    return (uint16_t)(sign | h);
+}
+
+
 struct V3 { double x, y, z; };
 inline V3 operator+(V3 a, V3 b) { return { a.x + b.x, a.y + b.y, a.z + b.z }; }
 inline V3 operator-(V3 a, V3 b) { return { a.x - b.x, a.y - b.y, a.z - b.z }; }
@@ -374,7 +397,7 @@ extern "C" {
 
 int tray_host_pack(const tray_mesh* mesh, int use_tlas, uint32_t tri_stride, uint32_t max_prims_per_leaf,
                    int nthreads, tray_packed** out) {
-    if (!mesh || !out || (tri_stride != 48 && tri_stride != 64)) return -1;
+    if (!mesh || !out || (tri_stride != 48 && tri_stride != 64 && tri_stride != 24)) return -1;
 #ifdef _OPENMP
     if (nthreads <= 0) nthreads = omp_get_max_threads();
 #else
@@ -434,6 +457,17 @@ int tray_host_pack(const tray_mesh* mesh, int use_tlas, uint32_t tri_stride, uin
             // RtTriangle::from(&Triangle): v0, e1 = v0 - v1, e2 = v2 - v0, ng = cross(e1, e2)  
             float v0[3] = { t[0], t[1], t[2] }, e1[3], e2[3];
             for (int a = 0; a < 3; a++) { e1[a] = t[a] - t[3 + a]; e2[a] = t[6 + a] - t[a]; }
+            if (tri_stride == 24) {
+                // RtCompressedTriangle::from(&Triangle): v0 as f32, e[k] = half(v2 - v0)[k] | half(v1 - v0)[k] << 16
+                // (src/rt_gpu/mod.rs:39-43; unpacked at rt_gpu_software_query.hlsl:75-85)
+                uint32_t* e = (uint32_t*)(rec + 3);
+                for (int a = 0; a < 3; a++) {
+                    rec[a] = v0[a];
+                    e[a] = (uint32_t)float_to_half(e2[a]) | ((uint32_t)float_to_half(t[3 + a] - t[a]) << 16);
+                }
+                p->prim_to_mesh_tri[tri_off + i] = (uint32_t)mesh_tri;
+                continue;
+            }
             for (int a = 0; a < 3; a++) { rec[a] = v0[a]; rec[4 + a] = e1[a]; rec[8 + a] = e2[a]; }
             if (tri_stride == 64) {
                 volatile float m0 = e1[1] * e2[2], m1 = e1[2] * e2[1], m2 = e1[2] * e2[0], m3 = e1[0] * e2[2], m4 = e1[0] * e2[1], m5 = e1[1] * e2[0];

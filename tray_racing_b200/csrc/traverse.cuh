@@ -20,6 +20,7 @@
 //   * all parity-relevant float math uses round-to-nearest intrinsics without FMA contraction, because the
 //     reference CPU path (Rust/glam) never fuses (SURVEY.md §7 "bit-level float parity").
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -54,7 +55,7 @@ struct FrameParams {
     uint32_t n_items;                             // padded local pixel count of this shard (multiple of 256)
 };
 
-enum ShadeMode { SHADE_NONE = 0, SHADE_PRIMARY = 1, SHADE_BOUNCE = 2 };
+enum ShadeMode { SHADE_NONE = 0, SHADE_PRIMARY = 1, SHADE_BOUNCE = 2, SHADE_OCCLUSION = 3 };
 
 struct TraceParams {
     const uint4* __restrict__ nodes;          // 5 x uint4 per node
@@ -281,17 +282,40 @@ __device__ __forceinline__ uint32_t node_test_fast(const RayConst& r, float tmax
     return mask;
 }
 
+// ---- triangle records ---------------------------------------------------------------------------
+// stride 48 / 64: the CPU path's f32 RtTriangle {v0, e1 = v0 - v1, e2 = v2 - v0 [, ng]} as 3 / 4 x 16-byte loads.
+// stride 24: the wgpu path's RtCompressedTriangle {v0: f32 x 3, e[k] = half(v2 - v0)[k] | half(v1 - v0)[k] << 16}
+//            (src/rt_gpu/mod.rs:39-43; unpack query.hlsl:75-85, e1 negated at :91) as 3 x 8-byte loads — half the
+//            triangle bytes per test, NOT the parity path against rt_cpu (checked against the oracle on the same records).
+__device__ __forceinline__ float half_lo(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w & 0xffffu))); }
+__device__ __forceinline__ float half_hi(uint32_t w) { return __half2float(__ushort_as_half((unsigned short)(w >> 16))); }
+
+template <int TRI_STRIDE>
+__device__ __forceinline__ void tri_load(const uint4* __restrict__ tris, uint32_t prim, float& v0x, float& v0y, float& v0z,
+                                         float& e1x, float& e1y, float& e1z, float& e2x, float& e2y, float& e2z) {
+    if (TRI_STRIDE == 24) {
+        const uint2* rec = reinterpret_cast<const uint2*>(tris) + (size_t)prim * 3u;
+        const uint2 a = __ldg(rec), b = __ldg(rec + 1), c = __ldg(rec + 2);
+        v0x = __uint_as_float(a.x); v0y = __uint_as_float(a.y); v0z = __uint_as_float(b.x);
+        e2x = half_lo(b.y); e2y = half_lo(c.x); e2z = half_lo(c.y);
+        e1x = -half_hi(b.y); e1y = -half_hi(c.x); e1z = -half_hi(c.y);
+    } else {
+        const uint4* rec = tris + (size_t)prim * (TRI_STRIDE / 16);
+        const uint4 a = __ldg(rec), b = __ldg(rec + 1), c4 = __ldg(rec + 2);
+        v0x = __uint_as_float(a.x); v0y = __uint_as_float(a.y); v0z = __uint_as_float(a.z);
+        e1x = __uint_as_float(b.x); e1y = __uint_as_float(b.y); e1z = __uint_as_float(b.z);
+        e2x = __uint_as_float(c4.x); e2y = __uint_as_float(c4.y); e2z = __uint_as_float(c4.z);
+    }
+}
+
 // ---- triangle test: RtTriangle::intersect, twin query.hlsl:89-129; returns t or +inf -------------
 template <int TRI_STRIDE>
 __device__ __forceinline__ float tri_test(const RayConst& r, float tmax, const uint4* __restrict__ tris, uint32_t prim) {
-    const uint4* rec = tris + (size_t)prim * (TRI_STRIDE / 16);
-    const uint4 a = __ldg(rec), b = __ldg(rec + 1), c4 = __ldg(rec + 2);
-    const float v0x = __uint_as_float(a.x), v0y = __uint_as_float(a.y), v0z = __uint_as_float(a.z);
-    const float e1x = __uint_as_float(b.x), e1y = __uint_as_float(b.y), e1z = __uint_as_float(b.z);
-    const float e2x = __uint_as_float(c4.x), e2y = __uint_as_float(c4.y), e2z = __uint_as_float(c4.z);
+    float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
+    tri_load<TRI_STRIDE>(tris, prim, v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z);
     float ngx, ngy, ngz;
     if (TRI_STRIDE == 64) {
-        const uint4 g = __ldg(rec + 3);
+        const uint4 g = __ldg(tris + (size_t)prim * 4u + 3);
         ngx = __uint_as_float(g.x); ngy = __uint_as_float(g.y); ngz = __uint_as_float(g.z);
     } else {
         cross3(e1x, e1y, e1z, e2x, e2y, e2z, ngx, ngy, ngz);                       // :93
@@ -384,15 +408,14 @@ template <int TRI_STRIDE>
 __device__ __forceinline__ void bounce_ray(const FrameParams& P, const uint4* __restrict__ tris, uint32_t px, uint32_t py,
                                            float pdx, float pdy, float pdz, float t, uint32_t prim,
                                            float& ox, float& oy, float& oz, float& dx, float& dy, float& dz) {
-    const uint4* rec = tris + (size_t)prim * (TRI_STRIDE / 16);
     float nx, ny, nz;
     if (TRI_STRIDE == 64) {
-        const uint4 g = __ldg(rec + 3);
+        const uint4 g = __ldg(tris + (size_t)prim * 4u + 3);
         nx = __uint_as_float(g.x); ny = __uint_as_float(g.y); nz = __uint_as_float(g.z);
     } else {
-        const uint4 b = __ldg(rec + 1), c = __ldg(rec + 2);
-        cross3(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z),
-               __uint_as_float(c.x), __uint_as_float(c.y), __uint_as_float(c.z), nx, ny, nz);
+        float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
+        tri_load<TRI_STRIDE>(tris, prim, v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z);
+        cross3(e1x, e1y, e1z, e2x, e2y, e2z, nx, ny, nz);
     }
     normalize3(nx, ny, nz);                                                    // RtTriangle::compute_normal
     const float sgn = copysignf(1.0f, dot3(nx, ny, nz, -pdx, -pdy, -pdz));     // f32::signum (rt_cpu.rs:65)
@@ -493,7 +516,9 @@ __global__ void __launch_bounds__(256) raygen_bounce_kernel(const __grid_constan
 //   NODE  tri_y == 0, cur_y has node bits    next action: fetch + test one node
 //   IDLE  tri_y == 0, cur_y == 0             no ray; waits for the next refill
 // so one pair of ballots per iteration drives everything (refill, phase vote, exit).
-template <bool TLAS, bool COUNT, int TRI_STRIDE>
+// ANYHIT: a ray retires at its FIRST accepted triangle (the "faster anyhit query" rt_cpu.rs:78-79 asks for AO rays);
+// the sequence of tests up to that point is the closest-hit one, so "found a hit" is the same predicate.
+template <bool TLAS, bool COUNT, int TRI_STRIDE, bool ANYHIT = false>
 __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
     uint2 spill[STACK_SPILL];
@@ -530,6 +555,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
             if (P.rgba_out) {
                 float col;
                 if (P.shade_mode == SHADE_PRIMARY) col = __fdiv_rn(1.0f, h.t);                       // rt_cpu.rs:59
+                else if (P.shade_mode == SHADE_OCCLUSION) col = h.t < F32_MAX_ ? 0.0f : 1.0f;        // any-hit AO: visibility only
                 else col = h.t < F32_MAX_ ? __fdiv_rn(h.t, add(1.0f, h.t)) : 1.0f;                   // rt_cpu.rs:82-87
                 const long long o = rgba_slot(item, P.frame_w, P.frame_h, P.frame_tiles_x, P.frame_shard, P.frame_shards);
                 if (o >= 0) P.rgba_out[o] = shade(col);
@@ -633,6 +659,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                     if (COUNT) c_tris++;
                     const float t = tri_test<TRI_STRIDE>(r, best_t, P.tris, g);
                     if (t < best_t) { best_t = t; best_prim = g; }          // CPU tie rule: first of equal t wins (§8a a11)
+                    if (ANYHIT && best_prim != INVALID) { sp = 0; tri_y = 0u; cur_y = 0u; }   // drop the rest of the traversal
                     if (tri_y == 0u && cur_y < 0x01000000u) pop_or_retire();
                 }
             }

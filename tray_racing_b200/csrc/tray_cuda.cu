@@ -14,7 +14,7 @@
 #include "traverse_pool.cuh"
 
 static_assert(sizeof(tray_cwbvh_node) == 80, "CwBvhNode is 80 bytes (bvh_embree_to_cwbvh.rs:91, rt_gpu/mod.rs:70)");
-static_assert(sizeof(tray_tri48) == 48 && sizeof(tray_tri64) == 64, "triangle record strides");
+static_assert(sizeof(tray_tri48) == 48 && sizeof(tray_tri64) == 64 && sizeof(tray_tri24) == 24, "triangle record strides");
 static_assert(sizeof(tray_ray) == 32 && sizeof(tray_hit) == 8, "ray / hit records");
 static_assert(sizeof(tray_view) == 160, "ViewUniform is padded to 160 bytes (main.rs:589-597)");
 
@@ -66,7 +66,7 @@ struct tray_scene {
     bool pool = false;                       // pooled kernel (traverse_pool.cuh) or one-ray-per-lane kernel (traverse.cuh)
     uint32_t pool_refill_min = 8, pool_tri_weight = 1;
     uint2* d_spill = nullptr; uint64_t spill_cap = 0;
-    int blocks_per_sm = 0;
+    int blocks_per_sm[2] = { 0, 0 };         // resident CTAs per SM of the lane kernel [0] and the pooled kernel [1]
     // ray-batch staging
     tray_ray* d_rays = nullptr; tray_hit* d_hits = nullptr; uint64_t batch_cap = 0;
     // frame state (compact local order)
@@ -90,13 +90,18 @@ using namespace tray;
 
 typedef void (*kernel_fn)(const TraceParams);
 
-template <bool TLAS, bool COUNT>
+template <bool TLAS, bool COUNT, bool ANYHIT>
 kernel_fn pick_stride(uint32_t stride) {
-    return stride == 64 ? (kernel_fn)trace_kernel<TLAS, COUNT, 64> : (kernel_fn)trace_kernel<TLAS, COUNT, 48>;
+    return stride == 64 ? (kernel_fn)trace_kernel<TLAS, COUNT, 64, ANYHIT>
+         : stride == 24 ? (kernel_fn)trace_kernel<TLAS, COUNT, 24, ANYHIT> : (kernel_fn)trace_kernel<TLAS, COUNT, 48, ANYHIT>;
 }
-kernel_fn pick_kernel(bool tlas, bool count, uint32_t stride) {
-    if (tlas) return count ? pick_stride<true, true>(stride) : pick_stride<true, false>(stride);
-    return count ? pick_stride<false, true>(stride) : pick_stride<false, false>(stride);
+kernel_fn pick_kernel(bool tlas, bool count, uint32_t stride, bool anyhit) {
+    if (anyhit) {
+        if (tlas) return count ? pick_stride<true, true, true>(stride) : pick_stride<true, false, true>(stride);
+        return count ? pick_stride<false, true, true>(stride) : pick_stride<false, false, true>(stride);
+    }
+    if (tlas) return count ? pick_stride<true, true, false>(stride) : pick_stride<true, false, false>(stride);
+    return count ? pick_stride<false, true, false>(stride) : pick_stride<false, false, false>(stride);
 }
 template <bool TLAS, bool COUNT>
 kernel_fn pick_pool_stride(uint32_t stride) {
@@ -121,31 +126,33 @@ void base_params(const tray_scene* s, TraceParams& P) {
 }
 
 // one launch: reset the cursor, run the persistent grid (sized to the chip, or to the work if that is smaller)
-int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot) {
-    kernel_fn k = s->pool ? pick_pool_kernel(s->tlas, s->counting, s->tri_stride) : pick_kernel(s->tlas, s->counting, s->tri_stride);
-    const int threads = s->pool ? POOL_WARPS * 32 : BLOCK_THREADS;
-    const uint64_t rays_per_block = s->pool ? (uint64_t)POOL_WARPS * POOL_SLOTS : (uint64_t)BLOCK_THREADS;
-    if (s->blocks_per_sm == 0) {
+int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, bool anyhit = false) {
+    const bool pool = s->pool && !anyhit && s->tri_stride != 24;      // the pooled kernel covers closest hit on f32 records
+    kernel_fn k = pool ? pick_pool_kernel(s->tlas, s->counting, s->tri_stride) : pick_kernel(s->tlas, s->counting, s->tri_stride, anyhit);
+    const int threads = pool ? POOL_WARPS * 32 : BLOCK_THREADS;
+    const uint64_t rays_per_block = pool ? (uint64_t)POOL_WARPS * POOL_SLOTS : (uint64_t)BLOCK_THREADS;
+    int& bps = s->blocks_per_sm[pool ? 1 : 0];
+    if (bps == 0) {
         int nb = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, 0));
-        s->blocks_per_sm = nb > 0 ? nb : 1;
+        bps = nb > 0 ? nb : 1;
         int cap = env_int("TRAY_CUDA_BLOCKS_PER_SM", 0);
-        if (cap > 0 && cap < s->blocks_per_sm) s->blocks_per_sm = cap;
+        if (cap > 0 && cap < bps) bps = cap;
     }
     P.counters = s->d_cursor + 1 + 5 * counter_slot;
     CU(cudaMemsetAsync(s->d_cursor, 0, sizeof(unsigned long long), st));
     if (s->counting) CU(cudaMemsetAsync(P.counters, 0, 5 * sizeof(unsigned long long), st));
     const uint64_t blocks_needed = ((uint64_t)P.n_work + rays_per_block - 1) / rays_per_block;
-    uint64_t grid = (uint64_t)s->sm_count * s->blocks_per_sm;
+    uint64_t grid = (uint64_t)s->sm_count * bps;
     if (blocks_needed < grid) grid = blocks_needed;
     if (grid == 0) return TRAY_OK;
-    if (s->pool) {
+    if (pool) {
         P.refill_min = s->pool_refill_min; P.tri_weight = s->pool_tri_weight;
         const uint64_t need = grid * POOL_WARPS * POOL_STACK_SPILL * POOL_SLOTS;      // uint2 entries
         if (need > s->spill_cap) {
             CU(cudaStreamSynchronize(st));
             cudaFree(s->d_spill); s->d_spill = nullptr; s->spill_cap = 0;
-            const uint64_t cap = (uint64_t)s->sm_count * s->blocks_per_sm * POOL_WARPS * POOL_STACK_SPILL * POOL_SLOTS;
+            const uint64_t cap = (uint64_t)s->sm_count * bps * POOL_WARPS * POOL_STACK_SPILL * POOL_SLOTS;
             CU(cudaMalloc(&s->d_spill, cap * sizeof(uint2)));
             s->spill_cap = cap;
         }
@@ -163,7 +170,7 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot) {
 #ifdef TRAY_EXIT_LOG
     static unsigned long long* d_log = nullptr;
     const size_t log_n = 2 * grid * (threads / 32);
-    if (!s->pool) {
+    if (!pool) {
         if (!d_log) CU(cudaMalloc(&d_log, 1 << 24));
         CU(cudaMemsetAsync(d_log, 0, log_n * 8, st));
         P.spill = (uint2*)d_log;
@@ -172,7 +179,7 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot) {
     void* args[1] = { (void*)&P };
     CU(cudaLaunchKernelExC(&cfg, (const void*)k, args));
 #ifdef TRAY_EXIT_LOG
-    if (!s->pool && getenv("TRAY_EXIT_LOG_FILE")) {
+    if (!pool && getenv("TRAY_EXIT_LOG_FILE")) {
         std::vector<unsigned long long> h(log_n);
         CU(cudaStreamSynchronize(st));
         CU(cudaMemcpy(h.data(), d_log, log_n * 8, cudaMemcpyDeviceToHost));
@@ -278,7 +285,7 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
     if (!out) return fail(TRAY_ERR_ARG, "out_scene is NULL");
     *out = nullptr;
     if ((n_nodes && !nodes) || (n_tris && !tris)) return fail(TRAY_ERR_ARG, "NULL node / triangle buffer");
-    if (tri_stride != 48 && tri_stride != 64) return fail(TRAY_ERR_ARG, "tri_stride must be 48 or 64 (got %u)", tri_stride);
+    if (tri_stride != 48 && tri_stride != 64 && tri_stride != 24) return fail(TRAY_ERR_ARG, "tri_stride must be 48, 64 or 24 (got %u)", tri_stride);
     if (n_instances && !blas_offsets) return fail(TRAY_ERR_ARG, "n_instances > 0 but blas_offsets is NULL");
     if (n_instances && tlas_start >= n_nodes) return fail(TRAY_ERR_ARG, "tlas_start %u outside %llu nodes", tlas_start, (unsigned long long)n_nodes);
     if (n_nodes >= 0xffffffffull || n_tris >= 0xffffffffull) return fail(TRAY_ERR_ARG, "node / triangle indices are 32-bit");
@@ -361,7 +368,7 @@ int tray_cuda_scene_info(const tray_scene* s, tray_scene_info* o) {
 
 int tray_cuda_set_counting(tray_scene* s, int enabled) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
-    if (s->counting != (enabled != 0)) { s->counting = enabled != 0; s->blocks_per_sm = 0; }
+    if (s->counting != (enabled != 0)) { s->counting = enabled != 0; s->blocks_per_sm[0] = s->blocks_per_sm[1] = 0; }
     return TRAY_OK;
 }
 
@@ -442,7 +449,10 @@ int tray_cuda_sync(tray_scene* s) {
     return check_overflow(s);
 }
 
-int tray_cuda_trace_device(tray_scene* s, const tray_ray* d_rays, uint64_t n, tray_hit* d_hits, void* stream, float* ms_kernel) {
+}  // extern "C"
+
+namespace {
+int trace_device_impl(tray_scene* s, const tray_ray* d_rays, uint64_t n, tray_hit* d_hits, void* stream, float* ms_kernel, bool anyhit) {
     if (!s || (n && (!d_rays || !d_hits))) return fail(TRAY_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(s->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
@@ -451,7 +461,7 @@ int tray_cuda_trace_device(tray_scene* s, const tray_ray* d_rays, uint64_t n, tr
     for (uint64_t off = 0; off < n; off += chunk) {
         TraceParams P; base_params(s, P);
         P.rays = d_rays + off; P.n_work = (uint32_t)(n - off < chunk ? n - off : chunk); P.hits_out = d_hits + off;
-        int rc = launch(s, P, st, 0);
+        int rc = launch(s, P, st, 0, anyhit);
         if (rc) return rc;
     }
     if (ms_kernel) {
@@ -462,7 +472,7 @@ int tray_cuda_trace_device(tray_scene* s, const tray_ray* d_rays, uint64_t n, tr
     return TRAY_OK;
 }
 
-int tray_cuda_trace(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, float* ms_kernel, float* ms_total) {
+int trace_impl(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, float* ms_kernel, float* ms_total, bool anyhit) {
     if (!s || (n && (!rays || !hits))) return fail(TRAY_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(s->device));
     const auto t0 = std::chrono::steady_clock::now();
@@ -474,7 +484,7 @@ int tray_cuda_trace(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* h
     }
     if (n) CU(cudaMemcpyAsync(s->d_rays, rays, n * sizeof(tray_ray), cudaMemcpyHostToDevice, s->stream));
     float k = 0.f;
-    int rc = tray_cuda_trace_device(s, s->d_rays, n, s->d_hits, s->stream, &k);
+    int rc = trace_device_impl(s, s->d_rays, n, s->d_hits, s->stream, &k, anyhit);
     if (rc) return rc;
     if (n) CU(cudaMemcpyAsync(hits, s->d_hits, n * sizeof(tray_hit), cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
@@ -484,6 +494,22 @@ int tray_cuda_trace(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* h
     if (ms_kernel) *ms_kernel = k;
     if (ms_total) *ms_total = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     return TRAY_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int tray_cuda_trace_device(tray_scene* s, const tray_ray* d_rays, uint64_t n, tray_hit* d_hits, void* stream, float* ms_kernel) {
+    return trace_device_impl(s, d_rays, n, d_hits, stream, ms_kernel, false);
+}
+int tray_cuda_trace(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, float* ms_kernel, float* ms_total) {
+    return trace_impl(s, rays, n, hits, ms_kernel, ms_total, false);
+}
+int tray_cuda_trace_any_device(tray_scene* s, const tray_ray* d_rays, uint64_t n, tray_hit* d_hits, void* stream, float* ms_kernel) {
+    return trace_device_impl(s, d_rays, n, d_hits, stream, ms_kernel, true);
+}
+int tray_cuda_trace_any(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, float* ms_kernel, float* ms_total) {
+    return trace_impl(s, rays, n, hits, ms_kernel, ms_total, true);
 }
 
 uint64_t tray_cuda_shard_pixels(uint32_t w, uint32_t h, uint32_t shard, uint32_t shards) {
@@ -510,6 +536,7 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     const uint64_t items_cap = local_items(w, h, 0, shards);   // every shard's buffers have the size of the largest (gather)
     const bool bounce = (flags & TRAY_RENDER_BOUNCE) != 0, rgba = (flags & TRAY_RENDER_RGBA) != 0;
     const bool keep_rays = (flags & TRAY_RENDER_KEEP_RAYS) != 0;
+    const bool any_ao = (flags & TRAY_RENDER_ANYHIT_AO) != 0;
     if (items_cap > s->f_cap || (keep_rays && !s->d_brays_item)) {
         const uint64_t cap = items_cap > s->f_cap ? items_cap : s->f_cap;
         cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba);
@@ -558,18 +585,15 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     // ---- bounce: generate + compact rays of hit pixels, trace ----
     if (bounce) {
         CU(cudaMemsetAsync(d_nbrays, 0, sizeof(uint32_t), s->stream));
-        if (s->tri_stride == 64)
-            tray::raygen_bounce_kernel<64><<<gen_grid, 256, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays,
-                                                                            s->d_bounce, rgba ? rgba_dst : nullptr, keep_rays ? s->d_brays_item : nullptr, s->frame_target ? 1u : 0u);
-        else
-            tray::raygen_bounce_kernel<48><<<gen_grid, 256, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays,
-                                                                            s->d_bounce, rgba ? rgba_dst : nullptr, keep_rays ? s->d_brays_item : nullptr, s->frame_target ? 1u : 0u);
+        auto gen = s->tri_stride == 64 ? tray::raygen_bounce_kernel<64> : s->tri_stride == 24 ? tray::raygen_bounce_kernel<24> : tray::raygen_bounce_kernel<48>;
+        gen<<<gen_grid, 256, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays, s->d_bounce,
+                                             rgba ? rgba_dst : nullptr, keep_rays ? s->d_brays_item : nullptr, s->frame_target ? 1u : 0u);
         CU(cudaGetLastError());
         TraceParams B; base_params(s, B);
         B.rays = s->d_brays; B.ray_item = s->d_bitem; B.n_work = F.n_items; B.n_work_dev = d_nbrays;   // count stays on the device
-        B.hits_out = s->d_bounce; B.rgba_out = rgba ? rgba_dst : nullptr; B.shade_mode = SHADE_BOUNCE;
+        B.hits_out = s->d_bounce; B.rgba_out = rgba ? rgba_dst : nullptr; B.shade_mode = any_ao ? SHADE_OCCLUSION : SHADE_BOUNCE;
         if (B.rgba_out) set_frame(B);
-        rc = launch(s, B, s->stream, 1);
+        rc = launch(s, B, s->stream, 1, any_ao);
         if (rc) return rc;
         if (timed) CU(cudaEventRecord(s->ev[2], s->stream));
     }

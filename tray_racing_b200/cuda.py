@@ -14,7 +14,7 @@ from .host import HIT_DTYPE, RAY_DTYPE, TrayView
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRAY_CUDA_LIB") or os.path.join(_HERE, "libtray_cuda.so")   # override: A/B builds only
 
-RENDER_BOUNCE, RENDER_RGBA, RENDER_COUNTERS, RENDER_KEEP_RAYS = 1, 2, 4, 8
+RENDER_BOUNCE, RENDER_RGBA, RENDER_COUNTERS, RENDER_KEEP_RAYS, RENDER_ANYHIT_AO = 1, 2, 4, 8, 16
 
 EXPORTS = (
     "tray_cuda_device_count", "tray_cuda_abi_version", "tray_cuda_scene_create", "tray_cuda_scene_destroy",
@@ -23,7 +23,7 @@ EXPORTS = (
     "tray_cuda_counters", "tray_cuda_set_counting", "tray_cuda_start", "tray_cuda_last_error",
     "tray_cuda_untile_rgba", "tray_cuda_scene_set_stream", "tray_cuda_bandwidth_probe",
     "tray_cuda_frame_alloc", "tray_cuda_frame_free", "tray_cuda_ipc_export", "tray_cuda_ipc_open", "tray_cuda_ipc_close",
-    "tray_cuda_scene_set_frame_target", "tray_cuda_render_timed",
+    "tray_cuda_scene_set_frame_target", "tray_cuda_render_timed", "tray_cuda_trace_any", "tray_cuda_trace_any_device",
 )
 
 
@@ -78,6 +78,10 @@ def lib() -> C.CDLL:
         L.tray_cuda_trace.argtypes = [vp, vp, u64, vp, f32p, f32p]
         L.tray_cuda_trace_device.restype = i32
         L.tray_cuda_trace_device.argtypes = [vp, vp, u64, vp, vp, f32p]
+        L.tray_cuda_trace_any.restype = i32
+        L.tray_cuda_trace_any.argtypes = [vp, vp, u64, vp, f32p, f32p]
+        L.tray_cuda_trace_any_device.restype = i32
+        L.tray_cuda_trace_any_device.argtypes = [vp, vp, u64, vp, vp, f32p]
         L.tray_cuda_render.restype = i32
         L.tray_cuda_render.argtypes = [vp, C.POINTER(TrayView), u32, u32, u32, u32, u32, u32, f32p, f32p]
         L.tray_cuda_render_timed.restype = i32
@@ -206,18 +210,22 @@ class TrayCudaScene:
         return i.as_dict()
 
     # ---- Traversable::traverse at batch grain -----------------------------------------------
-    def traverse(self, rays: np.ndarray, timings: dict | None = None) -> np.ndarray:
+    def traverse(self, rays: np.ndarray, timings: dict | None = None, any_hit: bool = False) -> np.ndarray:
+        """Closest hit per ray (`Traversable::traverse` at batch grain); any_hit=True stops each ray at its first
+        accepted triangle (tray_cuda_trace_any)."""
         rays = np.ascontiguousarray(rays, dtype=RAY_DTYPE)
         hits = np.empty(rays.shape[0], dtype=HIT_DTYPE)
         k, t = C.c_float(), C.c_float()
-        _check(lib().tray_cuda_trace(self._h, rays.ctypes.data, rays.shape[0], hits.ctypes.data, C.byref(k), C.byref(t)))
+        fn = lib().tray_cuda_trace_any if any_hit else lib().tray_cuda_trace
+        _check(fn(self._h, rays.ctypes.data, rays.shape[0], hits.ctypes.data, C.byref(k), C.byref(t)))
         if timings is not None:
             timings["ms_kernel"], timings["ms_total"] = k.value, t.value
         return hits
 
-    def traverse_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, stream: int = 0, timed: bool = False):
+    def traverse_device(self, d_rays_ptr: int, n: int, d_hits_ptr: int, stream: int = 0, timed: bool = False, any_hit: bool = False):
         k = C.c_float()
-        _check(lib().tray_cuda_trace_device(self._h, d_rays_ptr, n, d_hits_ptr, stream or None, C.byref(k) if timed else None))
+        fn = lib().tray_cuda_trace_any_device if any_hit else lib().tray_cuda_trace_device
+        _check(fn(self._h, d_rays_ptr, n, d_hits_ptr, stream or None, C.byref(k) if timed else None))
         return k.value if timed else None
 
     def set_counting(self, on: bool):

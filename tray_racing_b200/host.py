@@ -251,8 +251,18 @@ def view_from_camera(cam: Camera, width: int, height: int, tlas_start: int = 0) 
 
 
 def tri_records(tris: np.ndarray, stride: int = 48) -> np.ndarray:
-    """`RtTriangle::from(&Triangle)`: {v0, e1 = v0 - v1, e2 = v2 - v0 [, ng]} as padded f32 records."""
+    """`RtTriangle::from(&Triangle)`: {v0, e1 = v0 - v1, e2 = v2 - v0 [, ng]} as padded f32 records; stride 24 is the wgpu
+    path's `RtCompressedTriangle` {v0: f32 x 3, e[k] = half(v2 - v0)[k] | half(v1 - v0)[k] << 16}
+    (reference src/rt_gpu/mod.rs:39-43)."""
     t = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 3, 3)
+    if stride == 24:
+        rec = np.zeros((t.shape[0], 6), dtype=np.uint32)
+        rec[:, 0:3] = t[:, 0].view(np.uint32)
+        with np.errstate(over="ignore"):
+            lo = (t[:, 2] - t[:, 0]).astype(np.float16).view(np.uint16).astype(np.uint32)
+            hi = (t[:, 1] - t[:, 0]).astype(np.float16).view(np.uint16).astype(np.uint32)
+        rec[:, 3:6] = lo | (hi << 16)
+        return rec.view(np.uint8).reshape(-1)
     rec = np.zeros((t.shape[0], stride // 4), dtype=np.float32)
     rec[:, 0:3] = t[:, 0]
     rec[:, 4:7] = t[:, 0] - t[:, 1]
