@@ -70,7 +70,7 @@ def test_argument_validation_without_touching_a_device():
         cuda.TrayCudaScene(nodes, np.zeros(47, np.uint8))                 # reference asserts tri stride, mod.rs:86,107
     L = cuda.lib()
     h = C.c_void_p()
-    assert L.tray_cuda_scene_create(nodes.ctypes.data, 1, tris.ctypes.data, 1, 24, None, 0, 0, 0, C.byref(h)) == -1
+    assert L.tray_cuda_scene_create(nodes.ctypes.data, 1, tris.ctypes.data, 1, 32, None, 0, 0, 0, C.byref(h)) == -1   # strides: 48, 64 (f32) or 24 (f16)
     assert b"tri_stride" in L.tray_cuda_last_error()
     assert L.tray_cuda_scene_create(None, 1, tris.ctypes.data, 1, 48, None, 0, 0, 0, C.byref(h)) == -1
     assert L.tray_cuda_scene_create(nodes.ctypes.data, 1, tris.ctypes.data, 1, 48, None, 3, 0, 0, C.byref(h)) == -1
