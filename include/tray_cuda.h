@@ -165,6 +165,30 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes,
 
 void tray_cuda_scene_destroy(tray_scene* scene);
 
+/* ---- device-side builder ----------------------------------------------------------------
+ * The step before the path: the reference builds its CwBvh on the CPU (`cwbvh_from_tris`, src/cwbvh.rs:24-105,
+ * 0.95-2.9 s for its large scenes) and uploads it.  This builds the same FORMAT on the GPU — Morton sort, PLOC
+ * clustering (search radius = obvhs' `search_distance`, default 14, src/main.rs:563-587), collapse to 8-wide,
+ * octant slot order and quantisation as embree/src/bvh_embree_to_cwbvh.rs:85-186 — straight into the scene's device
+ * buffers; only the triangle soup crosses PCIe.  Single-level scenes only (no TLAS).  Deterministic: the same
+ * triangles give the same bytes on every device, so per-rank replicas agree on every primitive id.
+ *   tris9                n_tris x 9 floats (v0, v1, v2), HOST memory, borrowed for the call
+ *   max_prims_per_leaf   1..3 (reference default 3, src/main.rs:575)
+ *   search_radius        PLOC neighbourhood, 1..64; 0 = 14                                                  */
+typedef struct tray_build_stats {
+    uint64_t n_tris, n_nodes;
+    uint32_t ploc_iterations, levels;
+    float    ms_upload, ms_sort, ms_ploc, ms_collapse, ms_total;   /* host wall clock around synchronised phases */
+} tray_build_stats;
+
+int tray_cuda_scene_build(const float* tris9, uint64_t n_tris, uint32_t tri_stride, uint32_t max_prims_per_leaf,
+                          uint32_t search_radius, int device, tray_scene** out_scene, tray_build_stats* out_stats);
+
+/* Copy a scene's BVH back to HOST memory (any pointer may be NULL): nodes n_nodes x 80 B, tris n_tris x tri_stride,
+ * prim_indices n_tris x u32 (BVH slot -> input triangle; only scenes made by tray_cuda_scene_build have them —
+ * others return TRAY_ERR_ARG when prim_indices != NULL).  For checkers and for the dump format of INTEGRATION.md. */
+int tray_cuda_scene_download(tray_scene* scene, void* nodes, void* tris, uint32_t* prim_indices);
+
 int tray_cuda_scene_info(const tray_scene* scene, tray_scene_info* out_info);
 
 /* ---- ray-batch operator: Traversable::traverse at batch grain (traversable/src/lib.rs:20) ----- */

@@ -1,0 +1,476 @@
+// build_gpu.cu — device-side CWBVH builder: triangles in, the 80-byte CwBvhNode array + BVH-ordered
+// triangle records out, all resident in HBM, so that a scene can be traced without the host ever holding a BVH.
+//
+// The reference builds on the CPU with obvhs' `ploc_cwbvh` (src/cwbvh.rs:24-105: PLOC BVH2 -> collapse -> CWBVH; 0.95-2.9 s
+// multi-threaded for its large scenes).  obvhs is an un-vendored dependency, so nothing here is derived from
+// its code; the pipeline below is the published algorithm family laid out for a GPU:
+//   1. per-triangle boxes + scene bounds                              (one pass, atomics on ordered ints)
+//   2. 63-bit Morton codes of the box centres, radix sort              (cub::DeviceRadixSort — library code, like the
+//                                                                        prefix sums; the builder is not the hot path)
+//   3. PLOC (Meister & Bittner 2018): every cluster looks `radius` neighbours left and right in Morton order for the
+//      partner with the smallest merged surface area; mutual pairs merge; compaction by prefix sum; repeat until one
+//      cluster is left.  radius defaults to 14 = obvhs' `search_distance` default (src/main.rs:563-587).
+//   4. collapse to 8-wide, level by level: a wide node starts from a BVH2 node's two children and keeps opening the
+//      largest-area subtree that must stay inner (> max_prims_per_leaf) until it has 8 children, then spends free
+//      slots on splitting small subtrees into tighter leaves; children are placed in slots by octant
+//      (embree/src/bvh_embree.rs:284-349) and encoded exactly as the in-tree encoder does
+//      (embree/src/bvh_embree_to_cwbvh.rs:85-186: p / exponent / floor-ceil quantisation / child_meta).
+//      Node and primitive indices come from prefix sums, not atomics: the same triangles give the same bytes on every
+//      GPU, so N ranks that each build their replica agree on every primitive id.
+// Same collapse rule, slot assignment and encoder as the host producer in host/cwbvh_build.cpp; only the BVH2 differs
+// (PLOC here, binned SAH there).
+#include <cub/cub.cuh>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cstdio>
+#include <cstring>
+
+#include "build_gpu.h"
+
+namespace tray_build {
+
+namespace {
+
+#define BCU(call)                                                                                                  \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) {                                                                                   \
+            snprintf(err, errlen, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);     \
+            return -2;                                                                                             \
+        }                                                                                                          \
+    } while (0)
+
+constexpr int TPB = 256;
+inline unsigned blocks(uint64_t n) { return (unsigned)((n + TPB - 1) / TPB); }
+
+// ---- ordered-int float atomics ------------------------------------------------------------------------------
+__device__ __forceinline__ int f2o(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __forceinline__ float o2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+// BVH2 node: lo = (min.xyz, left), hi = (max.xyz, right).  Leaf i (< n_prims): left = -1, right = primitive index.
+struct Bvh2 {
+    float4* lo; float4* hi; uint32_t* count;
+};
+__device__ __forceinline__ int node_left(const float4& lo) { return __float_as_int(lo.w); }
+__device__ __forceinline__ int node_right(const float4& hi) { return __float_as_int(hi.w); }
+__device__ __forceinline__ float half_area(const float4& lo, const float4& hi) {
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// ---- 1. boxes and scene bounds -----------------------------------------------------------------------------------
+__global__ void prim_bounds_kernel(const float* __restrict__ tris9, uint32_t n, float4* __restrict__ plo, float4* __restrict__ phi, int* __restrict__ scene) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    float mn[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, mx[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
+    if (i < n) {
+        const float* t = tris9 + 9ull * i;
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            mn[a] = fminf(t[a], fminf(t[3 + a], t[6 + a]));
+            mx[a] = fmaxf(t[a], fmaxf(t[3 + a], t[6 + a]));
+        }
+        plo[i] = make_float4(mn[0], mn[1], mn[2], 0.f);
+        phi[i] = make_float4(mx[0], mx[1], mx[2], 0.f);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        float lo = mn[a], hi = mx[a];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, o)); hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, o)); }
+        if ((threadIdx.x & 31) == 0) { atomicMin(scene + a, f2o(lo)); atomicMax(scene + 3 + a, f2o(hi)); }
+    }
+}
+
+__device__ __forceinline__ unsigned long long spread21(unsigned long long v) {
+    v &= 0x1fffffull;
+    v = (v | (v << 32)) & 0x1f00000000ffffull;
+    v = (v | (v << 16)) & 0x1f0000ff0000ffull;
+    v = (v | (v << 8)) & 0x100f00f00f00f00full;
+    v = (v | (v << 4)) & 0x10c30c30c30c30c3ull;
+    v = (v | (v << 2)) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void morton_kernel(const float4* __restrict__ plo, const float4* __restrict__ phi, uint32_t n, const int* __restrict__ scene,
+                              unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 lo = plo[i], hi = phi[i];
+    const float c[3] = { 0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z) };
+    unsigned long long q[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        const float s0 = o2f(scene[a]), s1 = o2f(scene[3 + a]);
+        const float ext = s1 - s0;
+        float u = ext > 0.f ? (c[a] - s0) / ext : 0.f;
+        u = fminf(fmaxf(u, 0.f), 1.f);
+        q[a] = (unsigned long long)fminf(u * 2097152.f, 2097151.f);
+    }
+    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    vals[i] = i;
+}
+
+__global__ void leaf_init_kernel(const float4* __restrict__ plo, const float4* __restrict__ phi, const uint32_t* __restrict__ sorted_prim, uint32_t n,
+                                 Bvh2 b, int* __restrict__ cluster) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t p = sorted_prim[i];
+    float4 lo = plo[p], hi = phi[p];
+    lo.w = __int_as_float(-1); hi.w = __int_as_float((int)p);
+    b.lo[i] = lo; b.hi[i] = hi; b.count[i] = 1u;
+    cluster[i] = (int)i;
+}
+
+// ---- 3. PLOC ----------------------------------------------------------------------------------------------------
+// nearest neighbour of cluster i among positions [i - r, i + r]: smallest half-area of the merged box, ties to the
+// lower position (so that "mutual" is well defined and the build is deterministic)
+__global__ void __launch_bounds__(TPB) ploc_nn_kernel(const int* __restrict__ cluster, uint32_t m, int r, Bvh2 b, int* __restrict__ nn) {
+    extern __shared__ float4 s_box[];                 // [(TPB + 2r) x 2]
+    const int base = (int)(blockIdx.x * TPB) - r;
+    const int span = TPB + 2 * r;
+    for (int k = threadIdx.x; k < span; k += TPB) {
+        const int pos = base + k;
+        if (pos >= 0 && pos < (int)m) { const int c = cluster[pos]; s_box[2 * k] = b.lo[c]; s_box[2 * k + 1] = b.hi[c]; }
+    }
+    __syncthreads();
+    const int i = (int)(blockIdx.x * TPB + threadIdx.x);
+    if (i >= (int)m) return;
+    const float4 lo = s_box[2 * (threadIdx.x + r)], hi = s_box[2 * (threadIdx.x + r) + 1];
+    float best = 3.4e38f; int best_j = -1;
+    const int j0 = max(0, i - r), j1 = min((int)m - 1, i + r);
+    for (int j = j0; j <= j1; j++) {
+        if (j == i) continue;
+        const float4 l2 = s_box[2 * (j - base)], h2 = s_box[2 * (j - base) + 1];
+        const float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
+        const float a = dx * dy + dy * dz + dz * dx;
+        if (a < best) { best = a; best_j = j; }
+    }
+    nn[i] = best_j;
+}
+
+__global__ void ploc_flag_kernel(const int* __restrict__ nn, uint32_t m, uint32_t* __restrict__ keep, uint32_t* __restrict__ lead) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    const int j = nn[i];
+    const bool mutual = j >= 0 && nn[j] == (int)i;
+    keep[i] = (mutual && (int)i > j) ? 0u : 1u;       // the higher position of a merged pair disappears
+    lead[i] = (mutual && (int)i < j) ? 1u : 0u;       // the lower one creates the parent
+}
+
+__global__ void ploc_merge_kernel(const int* __restrict__ cluster, const int* __restrict__ nn, uint32_t m, const uint32_t* __restrict__ keep,
+                                  const uint32_t* __restrict__ keep_pos, const uint32_t* __restrict__ lead, const uint32_t* __restrict__ lead_pos,
+                                  uint32_t next_node, Bvh2 b, int* __restrict__ cluster_out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m || !keep[i]) return;
+    int c = cluster[i];
+    if (lead[i]) {
+        const int l = c, rgt = cluster[nn[i]];
+        const float4 a0 = b.lo[l], a1 = b.hi[l], b0 = b.lo[rgt], b1 = b.hi[rgt];
+        const int id = (int)(next_node + lead_pos[i]);
+        b.lo[id] = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), __int_as_float(l));
+        b.hi[id] = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), __int_as_float(rgt));
+        b.count[id] = b.count[l] + b.count[rgt];
+        c = id;
+    }
+    cluster_out[keep_pos[i]] = c;
+}
+
+// ---- 4. collapse to 8-wide ------------------------------------------------------------------------------------------
+struct Kids { int id[8]; int n; };
+
+// children of the wide node that replaces BVH2 subtree `root` (same rule as Collapser::run in host/cwbvh_build.cpp)
+__device__ void gather_kids(const Bvh2& b, int root, uint32_t max_leaf, Kids& k) {
+    const float4 rlo = b.lo[root], rhi = b.hi[root];
+    k.n = 0;
+    if (b.count[root] <= max_leaf || node_left(rlo) < 0) { k.id[k.n++] = root; }
+    else { k.id[k.n++] = node_left(rlo); k.id[k.n++] = node_right(rhi); }
+    for (int phase = 0; phase < 2; phase++) {
+        while (k.n < 8) {
+            int best = -1; float best_a = -1.f;
+            for (int i = 0; i < k.n; i++) {
+                const int c = k.id[i];
+                const float4 lo = b.lo[c];
+                if (node_left(lo) < 0) continue;                      // a single primitive cannot be opened
+                const uint32_t cnt = b.count[c];
+                const bool big = cnt > max_leaf;
+                if ((phase == 0) != big) continue;
+                const float a = half_area(lo, b.hi[c]) * (phase == 0 ? 1.f : (float)cnt);
+                if (a > best_a) { best_a = a; best = i; }
+            }
+            if (best < 0) break;
+            const int c = k.id[best];
+            k.id[best] = node_left(b.lo[c]); k.id[k.n++] = node_right(b.hi[c]);
+        }
+    }
+}
+
+__global__ void collapse_count_kernel(const int* __restrict__ items, uint32_t n_items, Bvh2 b, uint32_t max_leaf,
+                                      uint32_t* __restrict__ n_inner, uint32_t* __restrict__ n_tris) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    Kids k; gather_kids(b, items[i], max_leaf, k);
+    uint32_t ni = 0, nt = 0;
+    for (int c = 0; c < k.n; c++) {
+        const uint32_t cnt = b.count[k.id[c]];
+        if (cnt > max_leaf) ni++; else nt += cnt;
+    }
+    n_inner[i] = ni; n_tris[i] = nt;
+}
+
+// smallest power of two 2^k with 255 * 2^k >= extent (bvh_embree_to_cwbvh.rs:97-110)
+__device__ int quant_exponent(float extent) {
+    extent = fmaxf(extent, 1e-20f);
+    int k = (int)ceil(log2((double)extent / 255.0));
+    while (ldexp(255.0, k) < (double)extent) k++;
+    while (ldexp(255.0, k - 1) >= (double)extent) k--;
+    return k;
+}
+
+template <int STRIDE>
+__device__ void write_tri_record(const float* __restrict__ tris9, uint32_t prim, uint8_t* __restrict__ out, uint64_t slot) {
+    const float* t = tris9 + 9ull * prim;
+    float v0[3] = { t[0], t[1], t[2] }, e1[3], e2[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { e1[a] = __fsub_rn(t[a], t[3 + a]); e2[a] = __fsub_rn(t[6 + a], t[a]); }
+    if (STRIDE == 24) {
+        // RtCompressedTriangle (src/rt_gpu/mod.rs:39-43): v0 f32 x 3, e[k] = half(v2 - v0) | half(v1 - v0) << 16
+        uint32_t* rec = reinterpret_cast<uint32_t*>(out + slot * 24ull);
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            rec[a] = __float_as_uint(v0[a]);
+            rec[3 + a] = (uint32_t)__half_as_ushort(__float2half_rn(e2[a])) | ((uint32_t)__half_as_ushort(__float2half_rn(__fsub_rn(t[3 + a], t[a]))) << 16);
+        }
+    } else {
+        float4* rec = reinterpret_cast<float4*>(out + slot * (uint64_t)STRIDE);
+        rec[0] = make_float4(v0[0], v0[1], v0[2], 0.f);
+        rec[1] = make_float4(e1[0], e1[1], e1[2], 0.f);
+        rec[2] = make_float4(e2[0], e2[1], e2[2], 0.f);
+        if (STRIDE == 64)     // ng = cross(e1, e2): mul, mul, sub, each rounded
+            rec[3] = make_float4(__fsub_rn(__fmul_rn(e1[1], e2[2]), __fmul_rn(e1[2], e2[1])), __fsub_rn(__fmul_rn(e1[2], e2[0]), __fmul_rn(e1[0], e2[2])),
+                                 __fsub_rn(__fmul_rn(e1[0], e2[1]), __fmul_rn(e1[1], e2[0])), 0.f);
+    }
+}
+
+template <int STRIDE>
+__global__ void collapse_emit_kernel(const int* __restrict__ items, uint32_t n_items, Bvh2 b, uint32_t max_leaf,
+                                     const uint32_t* __restrict__ inner_off, const uint32_t* __restrict__ tri_off,
+                                     uint32_t level_base, uint32_t next_base, uint32_t prim_base,
+                                     const float* __restrict__ tris9, uint8_t* __restrict__ nodes, uint8_t* __restrict__ tri_out,
+                                     uint32_t* __restrict__ prim_indices, int* __restrict__ items_next, uint32_t* __restrict__ flags) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_items) return;
+    const int root = items[i];
+    Kids k; gather_kids(b, root, max_leaf, k);
+    const float4 nlo = b.lo[root], nhi = b.hi[root];
+    const float nmn[3] = { nlo.x, nlo.y, nlo.z }, nmx[3] = { nhi.x, nhi.y, nhi.z };
+    // slot assignment by octant (bvh_embree.rs:284-349): greedy min-cost matching of (child centre - node centre) . (+-1,+-1,+-1)
+    float cost[8][8];
+    for (int c = 0; c < k.n; c++) {
+        const float4 lo = b.lo[k.id[c]], hi = b.hi[k.id[c]];
+        const float d0 = 0.5f * (lo.x + hi.x) - 0.5f * (nmn[0] + nmx[0]), d1 = 0.5f * (lo.y + hi.y) - 0.5f * (nmn[1] + nmx[1]),
+                    d2 = 0.5f * (lo.z + hi.z) - 0.5f * (nmn[2] + nmx[2]);
+        for (int s = 0; s < 8; s++)
+            cost[c][s] = d0 * ((s & 4) ? -1.f : 1.f) + d1 * ((s & 2) ? -1.f : 1.f) + d2 * ((s & 1) ? -1.f : 1.f);
+    }
+    int slot_child[8]; unsigned child_done = 0, slot_used = 0;
+    for (int s = 0; s < 8; s++) slot_child[s] = -1;
+    for (int r = 0; r < k.n; r++) {
+        float bc = 3.4e38f; int bi = -1, bs = -1;
+        for (int c = 0; c < k.n; c++) if (!((child_done >> c) & 1u))
+            for (int s = 0; s < 8; s++) if (!((slot_used >> s) & 1u) && cost[c][s] < bc) { bc = cost[c][s]; bi = c; bs = s; }
+        child_done |= 1u << bi; slot_used |= 1u << bs; slot_child[bs] = bi;
+    }
+    // encode (bvh_embree_to_cwbvh.rs:85-186)
+    uint32_t w[20];
+#pragma unroll
+    for (int q = 0; q < 20; q++) w[q] = 0u;
+    uint8_t* nb = reinterpret_cast<uint8_t*>(w);
+    double scale[3];
+    for (int a = 0; a < 3; a++) {
+        w[a] = __float_as_uint(nmn[a]);
+        const int ke = quant_exponent(nmx[a] - nmn[a]);
+        nb[12 + a] = (uint8_t)(ke + 127);
+        if (ke + 127 >= 167) atomicOr(flags, 1u);          // scale >= 2^40: the traversal must use its unfused node test
+        scale[a] = ldexp(1.0, ke);
+    }
+    w[4] = next_base + inner_off[i];                        // child_base_idx
+    w[5] = prim_base + tri_off[i];                          // primitive_base_idx
+    uint32_t tri_local = 0, n_in = 0, imask = 0;
+    for (int s = 0; s < 8; s++) {
+        if (slot_child[s] < 0) continue;
+        const int c = k.id[slot_child[s]];
+        const float4 lo = b.lo[c], hi = b.hi[c];
+        const float cmn[3] = { lo.x, lo.y, lo.z }, cmx[3] = { hi.x, hi.y, hi.z };
+        for (int a = 0; a < 3; a++) {
+            double ql = floor(((double)cmn[a] - (double)nmn[a]) / scale[a]);
+            double qh = ceil(((double)cmx[a] - (double)nmn[a]) / scale[a]);
+            ql = fmin(255.0, fmax(0.0, ql)); qh = fmin(255.0, fmax(0.0, qh));
+            nb[32 + 16 * a + s] = (uint8_t)ql; nb[40 + 16 * a + s] = (uint8_t)qh;
+        }
+        const uint32_t cnt = b.count[c];
+        if (cnt > max_leaf) {
+            imask |= 1u << s;
+            nb[24 + s] = (uint8_t)((24 + s) | 0x20);
+            items_next[inner_off[i] + n_in] = c; n_in++;
+        } else {
+            const uint8_t unary = cnt == 1 ? 0x20 : cnt == 2 ? 0x60 : 0xE0;
+            nb[24 + s] = (uint8_t)(unary | tri_local);
+            // primitives of the small subtree, left to right
+            int stack[4]; int sp = 0; stack[sp++] = c;
+            while (sp) {
+                const int x = stack[--sp];
+                const float4 xl = b.lo[x];
+                if (node_left(xl) < 0) {
+                    const uint32_t prim = (uint32_t)node_right(b.hi[x]);
+                    const uint64_t slot = (uint64_t)prim_base + tri_off[i] + tri_local;
+                    prim_indices[slot] = prim;
+                    write_tri_record<STRIDE>(tris9, prim, tri_out, slot);
+                    tri_local++;
+                } else { stack[sp++] = node_right(b.hi[x]); stack[sp++] = node_left(xl); }
+            }
+        }
+    }
+    nb[15] = (uint8_t)imask;
+    uint4* dst = reinterpret_cast<uint4*>(nodes + (uint64_t)(level_base + i) * 80ull);
+#pragma unroll
+    for (int q = 0; q < 5; q++) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+struct Scratch {   // frees everything it owns on scope exit
+    void* p[48]; int n = 0;
+    template <typename T> cudaError_t alloc(T** out, size_t bytes) {
+        void* q = nullptr; cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+        if (e == cudaSuccess) { p[n++] = q; *out = (T*)q; }
+        return e;
+    }
+    ~Scratch() { for (int i = 0; i < n; i++) cudaFree(p[i]); }
+};
+
+double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+}  // namespace
+
+int build(const float* tris9_host, uint64_t n_tris, uint32_t tri_stride, uint32_t max_leaf, uint32_t radius, cudaStream_t st,
+          Result* out, char* err, size_t errlen) {
+    memset(out, 0, sizeof *out);
+    if (n_tris == 0) return 0;
+    if (n_tris >= 0x7fffffffull) { snprintf(err, errlen, "too many triangles"); return -1; }
+    const uint32_t n = (uint32_t)n_tris;
+    const double t_begin = now_ms();
+    Scratch sc;
+    float* d_tris9; float4 *plo, *phi; int* d_scene; unsigned long long *keys, *keys2; uint32_t *vals, *vals2;
+    Bvh2 b; int *cl_a, *cl_b, *nn; uint32_t *keep, *keep_pos, *lead, *lead_pos;
+    BCU(sc.alloc(&d_tris9, (size_t)n * 36));
+    BCU(sc.alloc(&plo, (size_t)n * 16)); BCU(sc.alloc(&phi, (size_t)n * 16));
+    BCU(sc.alloc(&d_scene, 6 * 4));
+    BCU(sc.alloc(&keys, (size_t)n * 8)); BCU(sc.alloc(&keys2, (size_t)n * 8));
+    BCU(sc.alloc(&vals, (size_t)n * 4)); BCU(sc.alloc(&vals2, (size_t)n * 4));
+    BCU(sc.alloc(&b.lo, (size_t)2 * n * 16)); BCU(sc.alloc(&b.hi, (size_t)2 * n * 16)); BCU(sc.alloc(&b.count, (size_t)2 * n * 4));
+    BCU(sc.alloc(&cl_a, (size_t)n * 4)); BCU(sc.alloc(&cl_b, (size_t)n * 4)); BCU(sc.alloc(&nn, (size_t)n * 4));
+    BCU(sc.alloc(&keep, (size_t)(n + 1) * 4)); BCU(sc.alloc(&keep_pos, (size_t)(n + 1) * 4));
+    BCU(sc.alloc(&lead, (size_t)(n + 1) * 4)); BCU(sc.alloc(&lead_pos, (size_t)(n + 1) * 4));
+    BCU(cudaMemcpyAsync(d_tris9, tris9_host, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+    const int scene_init[6] = { 0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000 };   // +max x3, -max x3 (ordered)
+    BCU(cudaMemcpyAsync(d_scene, scene_init, sizeof scene_init, cudaMemcpyHostToDevice, st));
+    BCU(cudaStreamSynchronize(st));
+    const double t_upload = now_ms();
+
+    prim_bounds_kernel<<<blocks(n), TPB, 0, st>>>(d_tris9, n, plo, phi, d_scene);
+    morton_kernel<<<blocks(n), TPB, 0, st>>>(plo, phi, n, d_scene, keys, vals);
+    size_t tmp_bytes = 0, tmp2 = 0;
+    BCU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 63, st));
+    BCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, keep, keep_pos, (int)n + 1, st));
+    if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
+    void* d_tmp; BCU(sc.alloc(&d_tmp, tmp_bytes));
+    BCU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 63, st));
+    leaf_init_kernel<<<blocks(n), TPB, 0, st>>>(plo, phi, vals2, n, b, cl_a);
+    BCU(cudaGetLastError());
+    BCU(cudaStreamSynchronize(st));
+    const double t_sort = now_ms();
+
+    // ---- PLOC ----
+    uint32_t m = n, next_node = n, iters = 0;
+    int* cl_in = cl_a; int* cl_out = cl_b;
+    const int r = (int)(radius < 1 ? 1 : (radius > 64 ? 64 : radius));
+    while (m > 1) {
+        ploc_nn_kernel<<<blocks(m), TPB, (size_t)(TPB + 2 * r) * 32, st>>>(cl_in, m, r, b, nn);
+        ploc_flag_kernel<<<blocks(m), TPB, 0, st>>>(nn, m, keep, lead);
+        // scans run over m + 1 entries so that entry m holds the total (the extra input element is never a keeper)
+        BCU(cudaMemsetAsync(keep + m, 0, 4, st)); BCU(cudaMemsetAsync(lead + m, 0, 4, st));
+        BCU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, keep, keep_pos, (int)m + 1, st));
+        BCU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, lead, lead_pos, (int)m + 1, st));
+        ploc_merge_kernel<<<blocks(m), TPB, 0, st>>>(cl_in, nn, m, keep, keep_pos, lead, lead_pos, next_node, b, cl_out);
+        uint32_t tot[2];
+        BCU(cudaMemcpyAsync(&tot[0], keep_pos + m, 4, cudaMemcpyDeviceToHost, st));
+        BCU(cudaMemcpyAsync(&tot[1], lead_pos + m, 4, cudaMemcpyDeviceToHost, st));
+        BCU(cudaStreamSynchronize(st));
+        if (tot[1] == 0 || tot[0] >= m) { snprintf(err, errlen, "PLOC made no progress at %u clusters", m); return -3; }
+        next_node += tot[1]; m = tot[0]; iters++;
+        int* t = cl_in; cl_in = cl_out; cl_out = t;
+    }
+    int root = 0;
+    BCU(cudaMemcpyAsync(&root, cl_in, 4, cudaMemcpyDeviceToHost, st));
+    BCU(cudaStreamSynchronize(st));
+    const double t_ploc = now_ms();
+
+    // ---- collapse, level by level ----
+    // node count is bounded by the number of BVH2 inner nodes + 1; allocate that, shrink-copy is not worth it (80 B each)
+    const uint64_t node_cap = (uint64_t)n + 1;
+    uint8_t *d_nodes = nullptr, *d_tri_out = nullptr; uint32_t* d_prim_idx = nullptr; uint32_t* d_flags;
+    int *items_a, *items_b; uint32_t *n_inner, *n_tri, *inner_off, *tri_off;
+    BCU(sc.alloc(&items_a, (size_t)n * 4)); BCU(sc.alloc(&items_b, (size_t)n * 4));
+    BCU(sc.alloc(&n_inner, (size_t)(n + 1) * 4)); BCU(sc.alloc(&n_tri, (size_t)(n + 1) * 4));
+    BCU(sc.alloc(&inner_off, (size_t)(n + 1) * 4)); BCU(sc.alloc(&tri_off, (size_t)(n + 1) * 4));
+    BCU(sc.alloc(&d_flags, 4));
+    BCU(cudaMemsetAsync(d_flags, 0, 4, st));
+    if (cudaMalloc(&d_nodes, node_cap * 80) != cudaSuccess || cudaMalloc(&d_tri_out, (size_t)n * tri_stride) != cudaSuccess ||
+        cudaMalloc(&d_prim_idx, (size_t)n * 4) != cudaSuccess) {
+        cudaFree(d_nodes); cudaFree(d_tri_out); cudaFree(d_prim_idx);
+        snprintf(err, errlen, "out of device memory for the BVH"); cudaGetLastError(); return -2;
+    }
+    auto bail = [&]() { cudaFree(d_nodes); cudaFree(d_tri_out); cudaFree(d_prim_idx); };
+#define BCU2(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { bail(); snprintf(err, errlen, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e2_), __FILE__, __LINE__); return -2; } } while (0)
+    BCU2(cudaMemcpyAsync(items_a, &root, 4, cudaMemcpyHostToDevice, st));
+    uint32_t n_items = 1, level_base = 0, prim_base = 0, levels = 0;
+    int* it_in = items_a; int* it_out = items_b;
+    while (n_items) {
+        collapse_count_kernel<<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, b, max_leaf, n_inner, n_tri);
+        BCU2(cudaMemsetAsync(n_inner + n_items, 0, 4, st)); BCU2(cudaMemsetAsync(n_tri + n_items, 0, 4, st));
+        BCU2(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, n_inner, inner_off, (int)n_items + 1, st));
+        BCU2(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, n_tri, tri_off, (int)n_items + 1, st));
+        const uint32_t next_base = level_base + n_items;
+        if (tri_stride == 64)
+            collapse_emit_kernel<64><<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, b, max_leaf, inner_off, tri_off, level_base, next_base, prim_base,
+                                                                     d_tris9, d_nodes, d_tri_out, d_prim_idx, it_out, d_flags);
+        else if (tri_stride == 24)
+            collapse_emit_kernel<24><<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, b, max_leaf, inner_off, tri_off, level_base, next_base, prim_base,
+                                                                     d_tris9, d_nodes, d_tri_out, d_prim_idx, it_out, d_flags);
+        else
+            collapse_emit_kernel<48><<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, b, max_leaf, inner_off, tri_off, level_base, next_base, prim_base,
+                                                                     d_tris9, d_nodes, d_tri_out, d_prim_idx, it_out, d_flags);
+        uint32_t tot[2];
+        BCU2(cudaMemcpyAsync(&tot[0], inner_off + n_items, 4, cudaMemcpyDeviceToHost, st));
+        BCU2(cudaMemcpyAsync(&tot[1], tri_off + n_items, 4, cudaMemcpyDeviceToHost, st));
+        BCU2(cudaStreamSynchronize(st));
+        BCU2(cudaGetLastError());
+        level_base = next_base; prim_base += tot[1]; n_items = tot[0]; levels++;
+        if ((uint64_t)level_base + n_items > node_cap) { bail(); snprintf(err, errlen, "node count exceeds its bound"); return -3; }
+        int* t = it_in; it_in = it_out; it_out = t;
+    }
+    if (prim_base != n) { bail(); snprintf(err, errlen, "collapse placed %u of %u primitives", prim_base, n); return -3; }
+    uint32_t flags = 0;
+    BCU2(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, st));
+    BCU2(cudaStreamSynchronize(st));
+#undef BCU2
+    const double t_end = now_ms();
+    out->d_nodes = d_nodes; out->n_nodes = level_base; out->d_tris = d_tri_out; out->d_prim_indices = d_prim_idx;
+    out->force_exact = (flags & 1u) != 0;
+    out->stats.n_tris = n; out->stats.n_nodes = level_base; out->stats.ploc_iterations = iters; out->stats.levels = levels;
+    out->stats.ms_upload = (float)(t_upload - t_begin); out->stats.ms_sort = (float)(t_sort - t_upload);
+    out->stats.ms_ploc = (float)(t_ploc - t_sort); out->stats.ms_collapse = (float)(t_end - t_ploc); out->stats.ms_total = (float)(t_end - t_begin);
+    return 0;
+}
+
+}  // namespace tray_build

@@ -10,6 +10,7 @@
 #include <new>
 #include <vector>
 
+#include "build_gpu.h"
 #include "traverse.cuh"
 #include "traverse_pool.cuh"
 
@@ -53,6 +54,7 @@ struct tray_scene {
     uint4* d_nodes = nullptr;
     uint4* d_tris = nullptr;
     uint32_t* d_blas = nullptr;
+    uint32_t* d_prim_indices = nullptr;      // BVH slot -> input triangle (scenes made by tray_cuda_scene_build)
     unsigned long long* d_cursor = nullptr;     // [0] cursor (u32), [1..10] 2 x 5 counters, [11] bounce-ray count (u32)
     uint32_t* d_overflow = nullptr;
     cudaStream_t stream = nullptr;          // the stream work is enqueued on
@@ -270,7 +272,7 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
-    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_blas); cudaFree(s->d_cursor); cudaFree(s->d_overflow);
+    cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_blas); cudaFree(s->d_prim_indices); cudaFree(s->d_cursor); cudaFree(s->d_overflow);
     cudaFree(s->d_rays); cudaFree(s->d_hits); cudaFree(s->d_spill);
     cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba); cudaFree(s->d_untiled);
     cudaFree(s->d_prays); cudaFree(s->d_bitem); cudaFree(s->d_brays_item);
@@ -279,12 +281,16 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     delete s;
 }
 
-int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris, uint64_t n_tris, uint32_t tri_stride,
-                           const uint32_t* blas_offsets, uint32_t n_instances, uint32_t tlas_start,
-                           int device, tray_scene** out) {
+}  // extern "C"
+
+namespace {
+// `built` != NULL: adopt the device buffers of the device-side builder instead of uploading host arrays
+int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uint64_t n_tris, uint32_t tri_stride,
+                      const uint32_t* blas_offsets, uint32_t n_instances, uint32_t tlas_start,
+                      int device, const tray_build::Result* built, tray_scene** out) {
     if (!out) return fail(TRAY_ERR_ARG, "out_scene is NULL");
     *out = nullptr;
-    if ((n_nodes && !nodes) || (n_tris && !tris)) return fail(TRAY_ERR_ARG, "NULL node / triangle buffer");
+    if (!built && ((n_nodes && !nodes) || (n_tris && !tris))) return fail(TRAY_ERR_ARG, "NULL node / triangle buffer");
     if (tri_stride != 48 && tri_stride != 64 && tri_stride != 24) return fail(TRAY_ERR_ARG, "tri_stride must be 48, 64 or 24 (got %u)", tri_stride);
     if (n_instances && !blas_offsets) return fail(TRAY_ERR_ARG, "n_instances > 0 but blas_offsets is NULL");
     if (n_instances && tlas_start >= n_nodes) return fail(TRAY_ERR_ARG, "tlas_start %u outside %llu nodes", tlas_start, (unsigned long long)n_nodes);
@@ -298,8 +304,8 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
     s->device = device; s->n_nodes = n_nodes; s->n_tris = n_tris; s->tri_stride = tri_stride;
     s->n_instances = n_instances; s->tlas_start = tlas_start; s->tlas = n_instances > 0;
     s->refill_min = (uint32_t)env_int("TRAY_CUDA_REFILL_MIN", 4);
-    s->force_exact = env_int("TRAY_CUDA_FORCE_EXACT", 0) != 0;
-    for (uint64_t i = 0; i < n_nodes && !s->force_exact; i++) {
+    s->force_exact = env_int("TRAY_CUDA_FORCE_EXACT", 0) != 0 || (built && built->force_exact);
+    for (uint64_t i = 0; !built && i < n_nodes && !s->force_exact; i++) {
         const uint8_t* e = (const uint8_t*)nodes + i * 80 + 12;
         if (e[0] >= 167 || e[1] >= 167 || e[2] >= 167) s->force_exact = true;   // scale = 2^(e-127) >= 2^40
     }
@@ -319,17 +325,22 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
         s->stream = s->own_stream;
         for (auto& e : s->ev) CU(cudaEventCreate(&e));
         const size_t nb = (size_t)(n_nodes ? n_nodes : 1) * 80, tb = (size_t)(n_tris ? n_tris : 1) * tri_stride;
-        CU(cudaMalloc(&s->d_nodes, nb));
-        CU(cudaMalloc(&s->d_tris, tb));
+        if (built && built->d_nodes) {
+            s->d_nodes = (uint4*)built->d_nodes; s->d_tris = (uint4*)built->d_tris; s->d_prim_indices = built->d_prim_indices;
+        } else {
+            CU(cudaMalloc(&s->d_nodes, nb));
+            CU(cudaMalloc(&s->d_tris, tb));
+        }
         CU(cudaMalloc(&s->d_blas, (size_t)(n_instances ? n_instances : 1) * 4));
         CU(cudaMalloc(&s->d_cursor, 16 * sizeof(unsigned long long)));
         CU(cudaMalloc(&s->d_overflow, 4));
         CU(cudaMemsetAsync(s->d_cursor, 0, 16 * sizeof(unsigned long long), s->stream));
         CU(cudaMemsetAsync(s->d_overflow, 0, 4, s->stream));
         s->device_bytes = nb + tb + (size_t)n_instances * 4;
-        if (n_nodes) CU(cudaMemcpyAsync(s->d_nodes, nodes, (size_t)n_nodes * 80, cudaMemcpyHostToDevice, s->stream));
+        if (built && built->d_nodes) {}
+        else if (n_nodes) CU(cudaMemcpyAsync(s->d_nodes, nodes, (size_t)n_nodes * 80, cudaMemcpyHostToDevice, s->stream));
         else CU(cudaMemsetAsync(s->d_nodes, 0, 80, s->stream));   // empty scene: a root with no children, every ray misses
-        if (n_tris) CU(cudaMemcpyAsync(s->d_tris, tris, (size_t)n_tris * tri_stride, cudaMemcpyHostToDevice, s->stream));
+        if (!(built && built->d_nodes) && n_tris) CU(cudaMemcpyAsync(s->d_tris, tris, (size_t)n_tris * tri_stride, cudaMemcpyHostToDevice, s->stream));
         if (n_instances) CU(cudaMemcpyAsync(s->d_blas, blas_offsets, (size_t)n_instances * 4, cudaMemcpyHostToDevice, s->stream));
         // keep the node array hot in the 126 MB L2: persisting access-policy window, attached to every traversal launch
         if (env_int("TRAY_CUDA_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0 && n_nodes) {
@@ -354,6 +365,48 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
     rc = body();
     if (rc != TRAY_OK) { tray_cuda_scene_destroy(s); return rc; }
     *out = s;
+    return TRAY_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris, uint64_t n_tris, uint32_t tri_stride,
+                           const uint32_t* blas_offsets, uint32_t n_instances, uint32_t tlas_start,
+                           int device, tray_scene** out) {
+    return scene_create_impl(nodes, n_nodes, tris, n_tris, tri_stride, blas_offsets, n_instances, tlas_start, device, nullptr, out);
+}
+
+int tray_cuda_scene_build(const float* tris9, uint64_t n_tris, uint32_t tri_stride, uint32_t max_prims_per_leaf,
+                          uint32_t search_radius, int device, tray_scene** out, tray_build_stats* out_stats) {
+    if (!out) return fail(TRAY_ERR_ARG, "out_scene is NULL");
+    *out = nullptr;
+    if (n_tris && !tris9) return fail(TRAY_ERR_ARG, "NULL triangle buffer");
+    if (tri_stride != 48 && tri_stride != 64 && tri_stride != 24) return fail(TRAY_ERR_ARG, "tri_stride must be 48, 64 or 24 (got %u)", tri_stride);
+    if (max_prims_per_leaf < 1 || max_prims_per_leaf > 3) return fail(TRAY_ERR_ARG, "max_prims_per_leaf must be 1..3");
+    if (search_radius > 64) return fail(TRAY_ERR_ARG, "search_radius must be 0 (default 14) or 1..64");
+    const int ndev = tray_cuda_device_count();
+    if (ndev == 0) return fail(TRAY_ERR_NO_DEVICE, "no CUDA device (tray_cuda has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TRAY_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
+    CU(cudaSetDevice(device));
+    tray_build::Result r;
+    char msg[400] = "";
+    const int brc = tray_build::build(tris9, n_tris, tri_stride, max_prims_per_leaf, search_radius ? search_radius : 14u, nullptr, &r, msg, sizeof msg);
+    if (brc) return fail(brc == -1 ? TRAY_ERR_ARG : TRAY_ERR_CUDA, "device build failed: %s", msg);
+    const int rc = scene_create_impl(nullptr, r.n_nodes, nullptr, n_tris, tri_stride, nullptr, 0, 0, device, &r, out);
+    if (rc) { if (!*out) { cudaFree(r.d_nodes); cudaFree(r.d_tris); cudaFree(r.d_prim_indices); } return rc; }
+    if (out_stats) *out_stats = r.stats;
+    return TRAY_OK;
+}
+
+int tray_cuda_scene_download(tray_scene* s, void* nodes, void* tris, uint32_t* prim_indices) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    if (prim_indices && !s->d_prim_indices && s->n_tris) return fail(TRAY_ERR_ARG, "this scene was not built on the device: it has no primitive index array");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    if (nodes && s->n_nodes) CU(cudaMemcpy(nodes, s->d_nodes, (size_t)s->n_nodes * 80, cudaMemcpyDeviceToHost));
+    if (tris && s->n_tris) CU(cudaMemcpy(tris, s->d_tris, (size_t)s->n_tris * s->tri_stride, cudaMemcpyDeviceToHost));
+    if (prim_indices && s->n_tris) CU(cudaMemcpy(prim_indices, s->d_prim_indices, (size_t)s->n_tris * 4, cudaMemcpyDeviceToHost));
     return TRAY_OK;
 }
 

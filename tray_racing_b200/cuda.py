@@ -38,6 +38,14 @@ class Counters(C.Structure):
         return {n: getattr(self, n) for n, _ in self._fields_}
 
 
+class BuildStats(C.Structure):
+    _fields_ = [("n_tris", C.c_uint64), ("n_nodes", C.c_uint64), ("ploc_iterations", C.c_uint32), ("levels", C.c_uint32),
+                ("ms_upload", C.c_float), ("ms_sort", C.c_float), ("ms_ploc", C.c_float), ("ms_collapse", C.c_float), ("ms_total", C.c_float)]
+
+    def as_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
 class SceneInfo(C.Structure):
     _fields_ = [("n_nodes", C.c_uint64), ("n_tris", C.c_uint64), ("tri_stride", C.c_uint32), ("n_instances", C.c_uint32),
                 ("tlas_start", C.c_uint32), ("is_tlas", C.c_uint32), ("device", C.c_int32), ("sm_count", C.c_uint32),
@@ -78,6 +86,10 @@ def lib() -> C.CDLL:
         L.tray_cuda_trace.argtypes = [vp, vp, u64, vp, f32p, f32p]
         L.tray_cuda_trace_device.restype = i32
         L.tray_cuda_trace_device.argtypes = [vp, vp, u64, vp, vp, f32p]
+        L.tray_cuda_scene_build.restype = i32
+        L.tray_cuda_scene_build.argtypes = [vp, u64, u32, u32, u32, i32, C.POINTER(vp), C.POINTER(BuildStats)]
+        L.tray_cuda_scene_download.restype = i32
+        L.tray_cuda_scene_download.argtypes = [vp, vp, vp, vp]
         L.tray_cuda_trace_any.restype = i32
         L.tray_cuda_trace_any.argtypes = [vp, vp, u64, vp, f32p, f32p]
         L.tray_cuda_trace_any_device.restype = i32
@@ -192,6 +204,30 @@ class TrayCudaScene:
         self._h = h
         self.tri_stride = tri_stride
         self.frame_size = None
+
+    @classmethod
+    def build(cls, tris, tri_stride=48, max_prims_per_leaf=3, search_radius=0, device=0) -> "TrayCudaScene":
+        """Build the CWBVH ON THE GPU from a triangle soup (n x 3 x 3 floats) — tray_cuda_scene_build; the reference's
+        `cwbvh_from_tris` (src/cwbvh.rs:24-105) runs on the CPU.  `build_stats` holds the phase times."""
+        t = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
+        self = cls.__new__(cls)
+        h, st = C.c_void_p(), BuildStats()
+        _check(lib().tray_cuda_scene_build(t.ctypes.data, t.shape[0], tri_stride, max_prims_per_leaf, search_radius, device,
+                                           C.byref(h), C.byref(st)))
+        self._h = h
+        self.tri_stride = tri_stride
+        self.frame_size = None
+        self.build_stats = st.as_dict()
+        return self
+
+    def download_bvh(self, prim_indices: bool = True):
+        """(bvh_bytes, tri_bytes, prim_indices) of the scene, copied back to the host (tray_cuda_scene_download)."""
+        i = self.info()
+        nodes = np.zeros(i["n_nodes"] * 80, dtype=np.uint8)
+        tris = np.zeros(i["n_tris"] * i["tri_stride"], dtype=np.uint8)
+        pi = np.zeros(i["n_tris"], dtype=np.uint32) if prim_indices else None
+        _check(lib().tray_cuda_scene_download(self._h, nodes.ctypes.data, tris.ctypes.data, None if pi is None else pi.ctypes.data))
+        return nodes, tris, pi
 
     @classmethod
     def from_packed(cls, p, device=0) -> "TrayCudaScene":
