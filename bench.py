@@ -341,6 +341,29 @@ def run_ours(args):
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_val = rays_all * e2e_steps / float(e2e_s.item()) / 1e6
 
+    # ---- beside the headline (N = 1 only, outside every timed region above): the rows SURVEY.md §8 marks "next" ----
+    extras = None
+    if rank == 0 and world == 1:
+        extras = {}
+        # f4: AO rays as an any-hit query (rt_cpu.rs:78-79) — same rays, each stopped at its first hit
+        ka = [scene.render(view, w, h, 0, flags | cuda.RENDER_ANYHIT_AO, rank, world, timed=True) for _ in range(6)][1:]
+        kb_any = min(b for _, b in ka)
+        extras["anyhit_ao"] = {"bounce_kernel_ms": kb_any, "bounce_kernel_mrays_s": cb["rays"] / kb_any / 1e3,
+                               "closest_hit_bounce_kernel_ms": kb_ms, "note": "TRAY_RENDER_ANYHIT_AO: visibility only, not the reference image"}
+        # f3: the same triangles built into a CWBVH on the device (PLOC) instead of by the host producer
+        tris = mesh.tris()
+        cuda.TrayCudaScene.build(tris[:4096], device=local_rank).close()              # module / allocator warm-up
+        t0 = time.perf_counter()
+        g = cuda.TrayCudaScene.build(tris, tri_stride=TRI_STRIDE, device=local_rank)
+        wall = (time.perf_counter() - t0) * 1e3
+        kg = [g.render(view, w, h, 0, flags) for _ in range(6)][1:]
+        extras["device_builder"] = {"wall_ms": wall, **{k: v for k, v in g.build_stats.items()},
+                                    "host_producer_ms": packed.build_seconds * 1e3,
+                                    "primary_kernel_ms_on_device_built_bvh": min(a for a, _ in kg),
+                                    "bounce_kernel_ms_on_device_built_bvh": min(b for _, b in kg),
+                                    "note": "PLOC radius 14 on the GPU vs binned SAH on the host cores; same collapse + encoder"}
+        g.close()
+
     if rank == 0:
         cpu_base, _ = cpu_oracle_run(packed, mesh, seconds_budget=10.0, frames_min=3) if world == 1 else (None, None)
         line = {
@@ -373,6 +396,8 @@ def run_ours(args):
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
+        if extras:
+            line["next_rows"] = extras
         print(json.dumps(line), flush=True)
     scene.close()
     if peer_ptr is not None and rank != 0:
