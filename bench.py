@@ -326,19 +326,40 @@ def run_ours(args):
     ach = (bytes_p / kp_ms if dominant == "primary" else bytes_b / kb_ms) / 1e6      # GB/s
 
     # ---- end to end through the public API with HOST buffers (per rank: view in, its RGBA shard out) ----
-    host_rgba = torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy()
-    into = {"rgba": host_rgba}
-    e2e_steps = max(3, min(args.steps, 10))
-    scene.render(view, w, h, 0, flags, rank, world, timed=False); scene.download(rgba=True, into=into)
+    # Every step: tray_cuda_render (view + frame parameters go in by value, 160 B) and the readback of that frame's RGBA8
+    # into pinned host memory (tray_cuda_frame_readback_begin / _wait: untile on the scene stream, D2H on the copy stream,
+    # double-buffered, so the copy of frame k overlaps the kernels of frame k + 1).  Frame k is waited for — i.e. is in
+    # host memory — before frame k + 2 is issued, and the last frames are waited for inside the timed region.
+    host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
+    e2e_steps = max(3, min(args.steps, 20))
+    scene.render(view, w, h, 0, flags, rank, world, timed=False)
+    scene.readback_begin(host_frames[0], 0); scene.readback_wait(0)
     sync_all()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        scene.render(view, w, h, 0, flags, rank, world, timed=False)      # view (160 B) + frame params go in by value
-        scene.download(rgba=True, into=into)                              # untile + D2H of this rank's pixels, synchronous
+    for i in range(e2e_steps):
+        slot = i & 1
+        scene.render(view, w, h, 0, flags, rank, world, timed=False)
+        scene.readback_begin(host_frames[slot], slot)
+        if i > 0:
+            scene.readback_wait(slot ^ 1)
+    scene.readback_wait((e2e_steps - 1) & 1)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    # the same, fully synchronous (render, then download, then the next frame): what a caller without the readback pair gets
+    into = {"rgba": host_frames[0]}
+    scene.render(view, w, h, 0, flags, rank, world, timed=False); scene.download(rgba=True, into=into)     # allocates its staging
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        scene.render(view, w, h, 0, flags, rank, world, timed=False)
+        scene.download(rgba=True, into=into)
+    torch.cuda.synchronize()
+    e2e_sync_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_sync_s, op=dist.ReduceOp.MAX)
+    e2e_sync_val = rays_all * e2e_steps / float(e2e_sync_s.item()) / 1e6
     e2e_val = rays_all * e2e_steps / float(e2e_s.item()) / 1e6
 
     # ---- beside the headline (N = 1 only, outside every timed region above): the rows SURVEY.md §8 marks "next" ----
@@ -388,7 +409,10 @@ def run_ours(args):
                          "ms_per_launch": kp_ms if dominant == "primary" else kb_ms,
                          "nodes_per_ray": cp["nodes"] / cp["rays"], "tris_per_ray": cp["tris"] / cp["rays"]},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 160 * world, "d2h_bytes_per_step": w * h * 4,
-                    "note": "tray_cuda_render + tray_cuda_frame_download(rgba) per rank, pinned host frame, wall clock"},
+                    "synchronous_value": e2e_sync_val,
+                    "note": "per step and rank: tray_cuda_render + RGBA8 frame to pinned host memory (readback_begin/_wait, double-buffered: "
+                            "the D2H of frame k overlaps the kernels of frame k+1; every frame is waited for inside the timed region), wall clock; "
+                            "synchronous_value = render then tray_cuda_frame_download, no overlap"},
             # per step and rank: raygen_primary, trace (primary), raygen_bounce, trace (bounce); the NCCL path adds one
             # untile per shard on rank 0
             "gpu_launches": args.steps * world * (4 if exchange == "peer" else 5),

@@ -244,6 +244,13 @@ uint64_t tray_cuda_shard_pixels(uint32_t width, uint32_t height, uint32_t shard_
 int tray_cuda_frame_download(tray_scene* scene, tray_hit* primary, tray_hit* bounce,
                              tray_ray* bounce_rays, uint8_t* rgba);
 
+/* Asynchronous readback of the last frame's RGBA8 (row-major, width*height*4 bytes) into HOST memory — pinned memory
+ * if the copy is to overlap anything.  `begin` enqueues the untile on the scene stream and the copy on the scene's own
+ * copy stream and returns; the next tray_cuda_render overlaps the copy.  Two staging buffers (slot 0 / 1): alternate
+ * them, and `wait` for a slot before reading its host frame (begin on a slot still in flight waits for it first).   */
+int tray_cuda_frame_readback_begin(tray_scene* scene, uint8_t* rgba_host, uint32_t slot);
+int tray_cuda_frame_readback_wait(tray_scene* scene, uint32_t slot);
+
 /* Device pointers of the last frame's buffers, for a caller that gathers them itself (NCCL / peer
  * copy).  Layout: row-major full-frame arrays, see tray_cuda_frame_download.                        */
 int tray_cuda_frame_device_ptrs(tray_scene* scene, void** d_primary, void** d_bounce, void** d_rgba);

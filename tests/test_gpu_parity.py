@@ -271,3 +271,34 @@ def test_frame_target_receives_the_same_pixels(cornell, w, h, shards):
     finally:
         sc.close()
         cuda.frame_free(frame)
+
+
+def test_async_readback_matches_synchronous_download(cornell):
+    """tray_cuda_frame_readback_begin / _wait (double-buffered, copy stream) deliver the same bytes as
+    tray_cuda_frame_download for a run of different frames, whatever the interleaving with the next render."""
+    import torch
+    w, h = 333, 187
+    p = host.PackedScene(cornell)
+    view = host.view_from_camera(cornell.camera, w, h)
+    sc = cuda.TrayCudaScene.from_packed(p)
+    try:
+        want = []
+        for f in range(5):
+            sc.render(view, w, h, f, cuda.RENDER_BOUNCE | cuda.RENDER_RGBA)
+            want.append(sc.download(rgba=True)["rgba"].copy())
+        assert any((want[0] != want[k]).any() for k in range(1, 5))        # the frames really differ (bounce directions)
+        bufs = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
+        got = []
+        for f in range(5):
+            slot = f & 1
+            sc.render(view, w, h, f, cuda.RENDER_BOUNCE | cuda.RENDER_RGBA, timed=False)
+            sc.readback_begin(bufs[slot], slot)
+            if f > 0:
+                sc.readback_wait(slot ^ 1)
+                got.append(bufs[slot ^ 1].copy())
+        sc.readback_wait(0)
+        got.append(bufs[0].copy())
+        for f in range(5):
+            assert np.array_equal(got[f], want[f]), f"frame {f}"
+    finally:
+        sc.close()

@@ -81,6 +81,10 @@ struct tray_scene {
     uint32_t* d_bitem = nullptr;             // local item of compact bounce ray i
     tray_ray* d_brays_item = nullptr;        // optional: bounce rays by local item (TRAY_RENDER_KEEP_RAYS)
     void* d_untiled = nullptr; uint64_t untiled_cap = 0;
+    // asynchronous RGBA readback: double-buffered row-major staging, copies on their own stream
+    cudaStream_t copy_stream = nullptr;
+    uchar4* d_stage[2] = { nullptr, nullptr }; uint64_t stage_cap[2] = { 0, 0 }; bool stage_busy[2] = { false, false };
+    cudaEvent_t ev_untiled[2] = { nullptr, nullptr }, ev_copied[2] = { nullptr, nullptr };
     uchar4* frame_target = nullptr;          // borrowed: row-major RGBA8 frame (this or a peer device), see tray_cuda_scene_set_frame_target
     tray::FrameParams last_frame;
     tray_counters cnt_primary{}, cnt_bounce{};
@@ -277,6 +281,13 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba); cudaFree(s->d_untiled);
     cudaFree(s->d_prays); cudaFree(s->d_bitem); cudaFree(s->d_brays_item);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
+    for (int i = 0; i < 2; i++) {
+        if (s->stage_busy[i]) cudaEventSynchronize(s->ev_copied[i]);
+        cudaFree(s->d_stage[i]);
+        if (s->ev_untiled[i]) cudaEventDestroy(s->ev_untiled[i]);
+        if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
+    }
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     delete s;
 }
@@ -324,6 +335,11 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         CU(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
         s->stream = s->own_stream;
         for (auto& e : s->ev) CU(cudaEventCreate(&e));
+        CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&s->ev_untiled[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
+        }
         const size_t nb = (size_t)(n_nodes ? n_nodes : 1) * 80, tb = (size_t)(n_tris ? n_tris : 1) * tri_stride;
         if (built && built->d_nodes) {
             s->d_nodes = (uint4*)built->d_nodes; s->d_tris = (uint4*)built->d_tris; s->d_prim_indices = built->d_prim_indices;
@@ -741,6 +757,43 @@ int tray_cuda_frame_download(tray_scene* s, tray_hit* primary, tray_hit* bounce,
         rc = download<uchar4>(s, s->d_rgba, (uchar4*)rgba); if (rc) return rc;
     }
     return check_overflow(s);
+}
+
+int tray_cuda_frame_readback_begin(tray_scene* s, uint8_t* rgba, uint32_t slot) {
+    if (!s || !rgba || slot > 1) return fail(TRAY_ERR_ARG, "bad argument");
+    if (s->fw == 0 || !s->f_has_rgba) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA (or into a frame target)");
+    CU(cudaSetDevice(s->device));
+    const uint64_t bytes = (uint64_t)s->fw * s->fh * sizeof(uchar4);
+    if (s->stage_busy[slot]) {                       // the previous copy out of this staging buffer must have landed
+        CU(cudaEventSynchronize(s->ev_copied[slot]));
+        s->stage_busy[slot] = false;
+    }
+    if (bytes > s->stage_cap[slot]) {
+        cudaFree(s->d_stage[slot]); s->d_stage[slot] = nullptr; s->stage_cap[slot] = 0;
+        CU(cudaMalloc(&s->d_stage[slot], bytes));
+        s->stage_cap[slot] = bytes;
+    }
+    if (s->fshards > 1) CU(cudaMemsetAsync(s->d_stage[slot], 0, bytes, s->stream));
+    if (s->f_items) {
+        const unsigned grid = (unsigned)((s->f_items + 255) / 256);
+        tray::untile_kernel<uchar4><<<grid, 256, 0, s->stream>>>(s->last_frame, s->d_rgba, s->d_stage[slot]);
+        CU(cudaGetLastError());
+    }
+    CU(cudaEventRecord(s->ev_untiled[slot], s->stream));
+    CU(cudaStreamWaitEvent(s->copy_stream, s->ev_untiled[slot], 0));
+    CU(cudaMemcpyAsync(rgba, s->d_stage[slot], bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    CU(cudaEventRecord(s->ev_copied[slot], s->copy_stream));
+    s->stage_busy[slot] = true;
+    return TRAY_OK;
+}
+
+int tray_cuda_frame_readback_wait(tray_scene* s, uint32_t slot) {
+    if (!s || slot > 1) return fail(TRAY_ERR_ARG, "bad argument");
+    if (!s->stage_busy[slot]) return TRAY_OK;
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventSynchronize(s->ev_copied[slot]));
+    s->stage_busy[slot] = false;
+    return TRAY_OK;
 }
 
 int tray_cuda_start(const void* bvh_bytes, uint64_t bvh_len, const void* instance_bytes, uint64_t instance_len,

@@ -24,7 +24,7 @@ EXPORTS = (
     "tray_cuda_untile_rgba", "tray_cuda_scene_set_stream", "tray_cuda_bandwidth_probe",
     "tray_cuda_frame_alloc", "tray_cuda_frame_free", "tray_cuda_ipc_export", "tray_cuda_ipc_open", "tray_cuda_ipc_close",
     "tray_cuda_scene_set_frame_target", "tray_cuda_render_timed", "tray_cuda_trace_any", "tray_cuda_trace_any_device",
-    "tray_cuda_scene_build", "tray_cuda_scene_download",
+    "tray_cuda_scene_build", "tray_cuda_scene_download", "tray_cuda_frame_readback_begin", "tray_cuda_frame_readback_wait",
 )
 
 
@@ -91,6 +91,10 @@ def lib() -> C.CDLL:
         L.tray_cuda_scene_build.argtypes = [vp, u64, u32, u32, u32, i32, C.POINTER(vp), C.POINTER(BuildStats)]
         L.tray_cuda_scene_download.restype = i32
         L.tray_cuda_scene_download.argtypes = [vp, vp, vp, vp]
+        L.tray_cuda_frame_readback_begin.restype = i32
+        L.tray_cuda_frame_readback_begin.argtypes = [vp, vp, u32]
+        L.tray_cuda_frame_readback_wait.restype = i32
+        L.tray_cuda_frame_readback_wait.argtypes = [vp, u32]
         L.tray_cuda_trace_any.restype = i32
         L.tray_cuda_trace_any.argtypes = [vp, vp, u64, vp, f32p, f32p]
         L.tray_cuda_trace_any_device.restype = i32
@@ -291,6 +295,15 @@ class TrayCudaScene:
         self.frame_size = (width, height)
         self.frame_shard = (shard, shards)
         return ms.value
+
+    def readback_begin(self, rgba: np.ndarray, slot: int):
+        """Start the asynchronous copy of the last frame's RGBA8 into `rgba` ((h, w, 4) uint8, pinned for overlap)."""
+        w, h = self.frame_size
+        assert rgba.dtype == np.uint8 and rgba.size == w * h * 4 and rgba.flags["C_CONTIGUOUS"]
+        _check(lib().tray_cuda_frame_readback_begin(self._h, rgba.ctypes.data, slot))
+
+    def readback_wait(self, slot: int):
+        _check(lib().tray_cuda_frame_readback_wait(self._h, slot))
 
     def download(self, primary=False, bounce=False, bounce_rays=False, rgba=False, into: dict | None = None,
                  merge: bool = False) -> dict:
