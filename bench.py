@@ -35,6 +35,27 @@ METRIC, UNIT = "Mrays/s primary+diffuse", "Mrays/s"
 TRI_STRIDE = 48
 
 
+_RESULT_FD = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries print there too (NCCL's version banner, torchrun notes), so
+    stdout is pointed at stderr for the whole run and the result line alone goes to the real stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def frame_size(n_gpus: int):
     s = n_gpus ** 0.5
     return int(round(BASE_W * s / 8)) * 8, int(round(BASE_H * s / 8)) * 8
@@ -163,7 +184,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -216,18 +237,22 @@ def run_ours(args):
     #         pixels straight into it over NVLink while tracing; a 4-byte all-reduce is the completion barrier
     #   nccl: gather the compact RGBA shards to rank 0, one untile launch per shard
     exchange, peer_frame, peer_ptr, done = args.exchange, None, None, None
+    peer_frame2, peer_ptr2 = None, None                   # second frame: the e2e loop alternates targets (readback overlap)
     if exchange == "auto" and world == 1:
         exchange = "nccl"           # one GPU: nothing to exchange; compact buffer + one untile launch measured 1.8 % faster
     if exchange in ("auto", "peer"):
         try:
             if rank == 0:
                 peer_frame = cuda.frame_alloc(w * h * 4, local_rank)
-                box = [cuda.ipc_export(peer_frame, local_rank)]
+                peer_frame2 = cuda.frame_alloc(w * h * 4, local_rank) if world > 1 else None
+                box = [cuda.ipc_export(peer_frame, local_rank), cuda.ipc_export(peer_frame2, local_rank) if world > 1 else None]
             else:
-                box = [None]
+                box = [None, None]
             if world > 1:
                 dist.broadcast_object_list(box, src=0)
             peer_ptr = peer_frame if rank == 0 else cuda.ipc_open(box[0], local_rank)
+            if world > 1:
+                peer_ptr2 = peer_frame2 if rank == 0 else cuda.ipc_open(box[1], local_rank)
             ok = torch.ones(1, device="cuda")
         except cuda.TrayCudaError as e:
             if exchange == "peer":
@@ -325,30 +350,54 @@ def run_ours(args):
     dominant = "primary" if kp_ms >= kb_ms else "bounce"
     ach = (bytes_p / kp_ms if dominant == "primary" else bytes_b / kb_ms) / 1e6      # GB/s
 
-    # ---- end to end through the public API with HOST buffers (per rank: view in, its RGBA shard out) ----
-    # Every step: tray_cuda_render (view + frame parameters go in by value, 160 B) and the readback of that frame's RGBA8
-    # into pinned host memory (tray_cuda_frame_readback_begin / _wait: untile on the scene stream, D2H on the copy stream,
-    # double-buffered, so the copy of frame k overlaps the kernels of frame k + 1).  Frame k is waited for — i.e. is in
-    # host memory — before frame k + 2 is issued, and the last frames are waited for inside the timed region.
-    host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
+    # ---- end to end through the public API with HOST buffers ----
+    # Every step: tray_cuda_render on every rank (view + frame parameters go in by value, 160 B per rank), the exchange
+    # step, and the readback of that frame's RGBA8 into pinned host memory (tray_cuda_frame_readback_begin / _wait: staging
+    # on the scene stream, D2H on the copy stream, double-buffered, so the copy of frame k overlaps the kernels of frame
+    # k + 1).  N = 1: the rank's own frame.  N > 1: the frame assembled on rank 0 (peer exchange: two frame targets used
+    # alternately, rank 0 snapshots the complete frame after the barrier; NCCL exchange: rank 0 copies the gathered frame).
+    # Frame k is waited for — i.e. is in host memory — before frame k + 2 is issued, and the last frames are waited for
+    # inside the timed region.
+    host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)] if (rank == 0 or world == 1) else None
+    host_t = [torch.from_numpy(a) for a in host_frames] if (host_frames is not None and world > 1 and exchange != "peer") else None
     e2e_steps = max(3, min(args.steps, 20))
-    scene.render(view, w, h, 0, flags, rank, world, timed=False)
-    scene.readback_begin(host_frames[0], 0); scene.readback_wait(0)
+    targets = [peer_ptr, peer_ptr2] if (world > 1 and exchange == "peer") else None
+
+    def e2e_step(i, wait_prev=True):
+        slot = i & 1
+        if targets:
+            scene.set_frame_target(targets[slot])
+            scene.render(view, w, h, 0, flags, rank, world, timed=False)
+            dist.all_reduce(done)                       # frame i complete in targets[slot] on rank 0
+            if rank == 0:
+                scene.readback_begin(host_frames[slot], slot)
+        elif world > 1:
+            step_nccl()                                 # gather + untile into `frame` on rank 0
+            if rank == 0:
+                host_t[slot].view(-1).view(torch.int32).copy_(frame, non_blocking=False)
+        else:
+            scene.render(view, w, h, 0, flags, rank, world, timed=False)
+            scene.readback_begin(host_frames[slot], slot)
+        if wait_prev and i > 0 and (rank == 0 or world == 1) and (targets or world == 1):
+            scene.readback_wait(slot ^ 1)
+
+    e2e_step(0, wait_prev=False)
+    if rank == 0 or world == 1:
+        scene.readback_wait(0)
     sync_all()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        slot = i & 1
-        scene.render(view, w, h, 0, flags, rank, world, timed=False)
-        scene.readback_begin(host_frames[slot], slot)
-        if i > 0:
-            scene.readback_wait(slot ^ 1)
-    scene.readback_wait((e2e_steps - 1) & 1)
+        e2e_step(i)
+    if rank == 0 or world == 1:
+        scene.readback_wait((e2e_steps - 1) & 1)
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    if targets:
+        scene.set_frame_target(None)
     # the same, fully synchronous (render, then download, then the next frame): what a caller without the readback pair gets
-    into = {"rgba": host_frames[0]}
+    into = {"rgba": host_frames[0] if host_frames is not None else np.zeros((h, w, 4), dtype=np.uint8)}
     scene.render(view, w, h, 0, flags, rank, world, timed=False); scene.download(rgba=True, into=into)     # allocates its staging
     sync_all()
     t0 = time.perf_counter()
@@ -409,6 +458,7 @@ def run_ours(args):
                          "ms_per_launch": kp_ms if dominant == "primary" else kb_ms,
                          "nodes_per_ray": cp["nodes"] / cp["rays"], "tris_per_ray": cp["tris"] / cp["rays"]},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 160 * world, "d2h_bytes_per_step": w * h * 4,
+                    "synchronous_note": "per rank: render, then tray_cuda_frame_download of a full-size frame (other shards zero), no exchange, no overlap",
                     "synchronous_value": e2e_sync_val,
                     "note": "per step and rank: tray_cuda_render + RGBA8 frame to pinned host memory (readback_begin/_wait, double-buffered: "
                             "the D2H of frame k overlaps the kernels of frame k+1; every frame is waited for inside the timed region), wall clock; "
@@ -422,14 +472,18 @@ def run_ours(args):
             line["cpu_baseline"] = cpu_base
         if extras:
             line["next_rows"] = extras
-        print(json.dumps(line), flush=True)
+        emit(line)
     scene.close()
     if peer_ptr is not None and rank != 0:
         cuda.ipc_close(peer_ptr, local_rank)
+        if peer_ptr2 is not None:
+            cuda.ipc_close(peer_ptr2, local_rank)
     if world > 1:
         dist.barrier()
     if peer_frame is not None:
         cuda.frame_free(peer_frame, local_rank)
+    if peer_frame2 is not None:
+        cuda.frame_free(peer_frame2, local_rank)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -444,6 +498,7 @@ def main():
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="how shards reach rank 0's frame: peer-mapped frame written by the kernels, or NCCL gather + untile")
     args = ap.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)

@@ -75,6 +75,7 @@ struct tray_scene {
     uint32_t fw = 0, fh = 0, fshard = 0, fshards = 1;
     uint64_t f_items = 0, f_cap = 0;
     bool f_has_bounce = false, f_has_rgba = false, f_has_rays = false;
+    uchar4* f_target = nullptr;              // the frame target the last frame was rendered into (NULL: compact d_rgba)
     tray_hit* d_primary = nullptr; tray_hit* d_bounce = nullptr; uchar4* d_rgba = nullptr;
     tray_ray* d_prays = nullptr;             // generated primary rays, local order
     tray_ray* d_brays = nullptr;             // generated bounce rays, COMPACT (hit pixels only)
@@ -505,8 +506,7 @@ int tray_cuda_ipc_close(int device, void* d_ptr) {
 
 int tray_cuda_scene_set_frame_target(tray_scene* s, void* d_frame) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
-    CU(cudaSetDevice(s->device));
-    CU(cudaStreamSynchronize(s->stream));
+    // launches already enqueued carry the old target in their parameters: no synchronisation needed to switch
     s->frame_target = (uchar4*)d_frame;
     return TRAY_OK;
 }
@@ -628,6 +628,7 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     FrameParams F; frame_params(F, view, w, h, frame_count, shard, shards);
     s->fw = w; s->fh = h; s->fshard = shard; s->fshards = shards; s->f_items = F.n_items;
     s->f_has_bounce = bounce; s->f_has_rgba = rgba && !s->frame_target; s->f_has_rays = keep_rays && bounce;
+    s->f_target = rgba ? s->frame_target : nullptr;
     s->last_frame = F;
     if (F.n_items == 0) { if (ms_primary) *ms_primary = 0.f; if (ms_bounce) *ms_bounce = 0.f; return TRAY_OK; }
     const unsigned gen_grid = (F.n_items + 255) / 256;
@@ -761,7 +762,7 @@ int tray_cuda_frame_download(tray_scene* s, tray_hit* primary, tray_hit* bounce,
 
 int tray_cuda_frame_readback_begin(tray_scene* s, uint8_t* rgba, uint32_t slot) {
     if (!s || !rgba || slot > 1) return fail(TRAY_ERR_ARG, "bad argument");
-    if (s->fw == 0 || !s->f_has_rgba) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA (or into a frame target)");
+    if (s->fw == 0 || (!s->f_has_rgba && !s->f_target)) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA");
     CU(cudaSetDevice(s->device));
     const uint64_t bytes = (uint64_t)s->fw * s->fh * sizeof(uchar4);
     if (s->stage_busy[slot]) {                       // the previous copy out of this staging buffer must have landed
@@ -773,11 +774,17 @@ int tray_cuda_frame_readback_begin(tray_scene* s, uint8_t* rgba, uint32_t slot) 
         CU(cudaMalloc(&s->d_stage[slot], bytes));
         s->stage_cap[slot] = bytes;
     }
-    if (s->fshards > 1) CU(cudaMemsetAsync(s->d_stage[slot], 0, bytes, s->stream));
-    if (s->f_items) {
-        const unsigned grid = (unsigned)((s->f_items + 255) / 256);
-        tray::untile_kernel<uchar4><<<grid, 256, 0, s->stream>>>(s->last_frame, s->d_rgba, s->d_stage[slot]);
-        CU(cudaGetLastError());
+    if (s->f_target) {
+        // the frame was rendered into a row-major frame target (all shards' pixels, once the caller's barrier has passed):
+        // snapshot it, so that the next frame may overwrite the target while this one travels to the host
+        CU(cudaMemcpyAsync(s->d_stage[slot], s->f_target, bytes, cudaMemcpyDeviceToDevice, s->stream));
+    } else {
+        if (s->fshards > 1) CU(cudaMemsetAsync(s->d_stage[slot], 0, bytes, s->stream));
+        if (s->f_items) {
+            const unsigned grid = (unsigned)((s->f_items + 255) / 256);
+            tray::untile_kernel<uchar4><<<grid, 256, 0, s->stream>>>(s->last_frame, s->d_rgba, s->d_stage[slot]);
+            CU(cudaGetLastError());
+        }
     }
     CU(cudaEventRecord(s->ev_untiled[slot], s->stream));
     CU(cudaStreamWaitEvent(s->copy_stream, s->ev_untiled[slot], 0));
