@@ -148,6 +148,7 @@ def cpu_oracle_run(packed, mesh, seconds_budget: float, frames_min: int, w=960, 
             break
     mean = sum(times) / len(times)
     return {"value": rays / mean / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
+            "simd": "AVX2 node test (8 children per vector), scalar triangle test" if ob.simd() else "scalar",
             "sample": f"{len(times)} frames of the same scene+camera at {w}x{h} ({rays} rays/frame, primary+bounce), mean frame time",
             "ms_per_frame": mean * 1e3, "rays_per_frame": rays}, times
 

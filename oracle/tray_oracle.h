@@ -8,6 +8,10 @@
  * dependency `obvhs` (Cargo.toml:26-29) and the reference holds no tests or golden vectors
  * (SURVEY.md §4, §8c), and no Rust toolchain exists here to run it.  This is a restatement of the
  * in-tree spec — see tray_oracle.c for the file:line each function follows.
+ *
+ * It is also the timed CPU baseline (bench.py cpu_baseline / --impl reference), so it is written to be a fair one: -O3,
+ * OpenMP over rays like the reference's rayon loop, and the 8-child node test on AVX2 vectors where the CPU has them
+ * (bit-identical to the scalar statement, tests/test_oracle.py).
  */
 #ifndef TRAY_ORACLE_H
 #define TRAY_ORACLE_H
@@ -52,6 +56,9 @@ typedef struct orc_totals { uint64_t rays, nodes, tris, insts, hits; } orc_total
 void orc_set_variant(uint32_t flags);
 
 unsigned orc_abi_version(void);
+/* the node test runs 8 children per AVX2 vector when the CPU has it (bit-identical to the scalar code); 0 forces scalar */
+void orc_set_simd(int on);
+int orc_simd(void);
 int orc_max_threads(void);
 
 /* closest hit for n rays; returns 0, or -4 if any ray overflowed the 32-entry stack (cwbvh.rs:88) */

@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
         vp, u64, u32, i32 = C.c_void_p, C.c_uint64, C.c_uint32, C.c_int
         L.orc_set_variant.argtypes = [u32]
         L.orc_max_threads.restype = i32
+        L.orc_set_simd.argtypes = [i32]
+        L.orc_simd.restype = i32
         L.orc_trace.restype = i32
         L.orc_trace.argtypes = [C.POINTER(OrcScene), vp, u64, vp, vp, C.POINTER(OrcTotals), i32]
         L.orc_trace_any.restype = i32
@@ -157,6 +159,15 @@ def node_intersect(node80, ray, tmax) -> int:
     n = np.ascontiguousarray(node80, dtype=np.uint8).reshape(80)
     r = np.ascontiguousarray(ray, dtype=RAY_DTYPE).reshape(1)
     return lib().orc_node_intersect(n.ctypes.data, r.ctypes.data, float(tmax))
+
+
+def set_simd(on: bool):
+    """node test on AVX2 vectors (default when the CPU has them) or scalar; results are bit-identical"""
+    lib().orc_set_simd(int(on))
+
+
+def simd() -> bool:
+    return bool(lib().orc_simd())
 
 
 def set_variant(flags: int):

@@ -314,3 +314,45 @@ def test_step_log_matches_the_visit_counters(cornell):
     assert L.orc_trace_oplog(C.byref(orc.scene), rays.ctypes.data, rays.shape[0], cnt.ctypes.data, ops.ctypes.data, offsets.ctypes.data, 0) == 0
     assert (ops[:-1] == ord("N")).sum() == tot["nodes"] and (ops[:-1] == ord("T")).sum() == tot["tris"]
     assert (ops[offsets[:-1].astype(np.int64)] == ord("N")).all()
+
+
+def test_simd_node_test_is_bit_identical_to_scalar(cornell):
+    """The oracle's AVX2 node test (8 children per vector) against its scalar statement of query.hlsl:213-303: same hit
+    masks on random nodes x rays, same hits AND same node / triangle counts on whole traversals — including rays with
+    denormal direction components, whose non-finite per-node constants take the scalar fallback."""
+    if not ob.lib().orc_simd():
+        ob.set_simd(True)
+        if not ob.simd():
+            pytest.skip("no AVX2 on this CPU: the oracle is scalar only")
+    try:
+        p = host.PackedScene(cornell)
+        nodes = p.bvh_bytes.reshape(-1, 80)
+        rays = random_rays(4000, seed=21)
+        rays["d"][:40, 0] = np.float32(1e-42)                       # denormal: 1/d overflows to inf
+        rays["d"][40:80, 1] = np.float32(-3e-45)
+        rng = np.random.default_rng(2)
+        pick = rng.integers(0, nodes.shape[0], size=4000)
+        tmax = rng.uniform(0.0, 5.0, size=4000).astype(np.float32)
+        # aim most probe rays at the middle of the node they are tested against, so that children are really hit
+        aimed = rays.copy()
+        org = nodes[pick, 0:12].copy().view(np.float32)
+        ext = np.ldexp(np.float32(128.0), nodes[pick, 12:15].astype(np.int32) - 127).astype(np.float32)
+        d = (org + ext) - aimed["o"]
+        d /= np.linalg.norm(d, axis=1, keepdims=True)
+        aimed["d"][80:] = d[80:].astype(np.float32)
+        masks = {}
+        for simd in (False, True):
+            ob.set_simd(simd)
+            masks[simd] = np.array([ob.node_intersect(nodes[pick[i]], aimed[i], tmax[i]) for i in range(4000)], dtype=np.uint32)
+        assert np.array_equal(masks[False], masks[True]) and (masks[True] != 0).sum() > 500
+        out = {}
+        for use_tlas in (False, True):
+            q = host.PackedScene(cornell, use_tlas=use_tlas)
+            orc = ob.Oracle.from_packed(q)
+            for simd in (False, True):
+                ob.set_simd(simd)
+                out[simd] = orc.trace(rays, counts=True)
+            assert np.array_equal(out[False][0].view(np.uint8), out[True][0].view(np.uint8))
+            assert np.array_equal(out[False][1].view(np.uint8), out[True][1].view(np.uint8))
+    finally:
+        ob.set_simd(True)
