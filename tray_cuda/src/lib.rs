@@ -26,6 +26,14 @@ pub struct TrayTri48 { pub v0: [f32; 3], pub p0: f32, pub e1: [f32; 3], pub p1: 
 
 #[repr(C)] pub struct TrayScene { _private: [u8; 0] }
 
+/// `tray_build_stats` of include/tray_cuda.h
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct TrayBuildStats {
+    pub n_tris: u64, pub n_nodes: u64, pub ploc_iterations: u32, pub levels: u32,
+    pub ms_upload: f32, pub ms_sort: f32, pub ms_ploc: f32, pub ms_collapse: f32, pub ms_total: f32,
+}
+
 extern "C" {
     pub fn tray_cuda_device_count() -> c_int;
     pub fn tray_cuda_last_error() -> *const c_char;
@@ -40,6 +48,11 @@ extern "C" {
         flags: u32, shard_index: u32, shard_count: u32, ms_primary: *mut f32, ms_bounce: *mut f32) -> c_int;
     pub fn tray_cuda_render_timed(scene: *mut TrayScene, view: *const TrayView, width: u32, height: u32, frame_count: u32,
         flags: u32, shard_index: u32, shard_count: u32, ms_frame: *mut f32) -> c_int;
+    pub fn tray_cuda_frame_readback_begin(scene: *mut TrayScene, rgba_host: *mut u8, slot: u32) -> c_int;
+    pub fn tray_cuda_frame_readback_wait(scene: *mut TrayScene, slot: u32) -> c_int;
+    pub fn tray_cuda_scene_build(tris9: *const f32, n_tris: u64, tri_stride: u32, max_prims_per_leaf: u32, search_radius: u32,
+        device: c_int, out: *mut *mut TrayScene, stats: *mut TrayBuildStats) -> c_int;
+    pub fn tray_cuda_scene_download(scene: *mut TrayScene, nodes: *mut c_void, tris: *mut c_void, prim_indices: *mut u32) -> c_int;
     pub fn tray_cuda_frame_download(scene: *mut TrayScene, primary: *mut TrayHit, bounce: *mut TrayHit,
         bounce_rays: *mut TrayRay, rgba: *mut u8) -> c_int;
     pub fn tray_cuda_start(bvh: *const c_void, bvh_len: u64, inst: *const c_void, inst_len: u64, tris: *const c_void,
