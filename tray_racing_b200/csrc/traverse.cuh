@@ -462,12 +462,14 @@ __global__ void __launch_bounds__(256) raygen_primary_kernel(const __grid_consta
 
 // One thread per pixel of the shard.  Hit pixels append their bounce ray to a compact list (warp-aggregated
 // atomicAdd; `ray_item` remembers the pixel); missed pixels get their final results here.
+constexpr int BOUNCE_BLOCK = 1024;    // pixels per block of raygen_bounce_kernel = the group its rays are sorted in
 template <int TRI_STRIDE>
-__global__ void __launch_bounds__(256) raygen_bounce_kernel(const __grid_constant__ FrameParams F, const uint4* __restrict__ tris,
+__global__ void __launch_bounds__(BOUNCE_BLOCK) raygen_bounce_kernel(const __grid_constant__ FrameParams F, const uint4* __restrict__ tris,
                                                             const tray_hit* __restrict__ primary, tray_ray* __restrict__ rays,
                                                             uint32_t* __restrict__ ray_item, uint32_t* __restrict__ n_rays,
                                                             tray_hit* __restrict__ bounce_out, uchar4* __restrict__ rgba_out,
-                                                            tray_ray* __restrict__ rays_by_item, uint32_t rgba_row_major) {
+                                                            tray_ray* __restrict__ rays_by_item, uint32_t rgba_row_major, uint32_t sort_octant) {
+    __shared__ uint32_t s_cnt[24], s_base[24];
     const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
     const unsigned lane = threadIdx.x & 31u;
     uint32_t px = 0, py = 0;
@@ -484,6 +486,34 @@ __global__ void __launch_bounds__(256) raygen_bounce_kernel(const __grid_constan
         bounce_ray<TRI_STRIDE>(F, tris, px, py, pdx, pdy, pdz, ph.t, ph.prim, ox, oy, oz, dx, dy, dz);
         a = make_float4(ox, oy, oz, 0.0f); b = make_float4(dx, dy, dz, F32_MAX_);
     }
+    if (sort_octant) {
+        // The rays of the block's 1024 pixels (4 tiles: close origins) are appended grouped by direction octant, so that the
+        // 32 rays a traversal warp fetches together share the order in which they visit a node's children.
+        const uint32_t nb = sort_octant >= 2u ? 24u : 8u;
+        if (threadIdx.x < 24) s_cnt[threadIdx.x] = 0u;
+        __syncthreads();
+        uint32_t oct = (b.x < 0.f ? 4u : 0u) | (b.y < 0.f ? 2u : 0u) | (b.z < 0.f ? 1u : 0u);
+        if (sort_octant >= 2u) {        // ... and by dominant axis inside the octant
+            const float ax = fabsf(b.x), ay = fabsf(b.y), az = fabsf(b.z);
+            oct = oct * 3u + (ax >= ay ? (ax >= az ? 0u : 2u) : (ay >= az ? 1u : 2u));
+        }
+        uint32_t pos = 0;
+        if (shoot) pos = atomicAdd(&s_cnt[oct], 1u);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t acc = 0;
+            for (uint32_t o = 0; o < nb; o++) { const uint32_t c = s_cnt[o]; s_base[o] = acc; acc += c; }
+            const uint32_t g = acc ? atomicAdd(n_rays, acc) : 0u;
+            for (uint32_t o = 0; o < nb; o++) s_base[o] += g;
+        }
+        __syncthreads();
+        if (shoot) {
+            const uint32_t slot = s_base[oct] + pos;
+            float4* out = reinterpret_cast<float4*>(rays + slot);
+            out[0] = a; out[1] = b;
+            ray_item[slot] = j;
+        }
+    } else {
     const unsigned m = __ballot_sync(FULL, shoot);
     if (m) {
         const int leader = __ffs(m) - 1;
@@ -496,6 +526,7 @@ __global__ void __launch_bounds__(256) raygen_bounce_kernel(const __grid_constan
             out[0] = a; out[1] = b;
             ray_item[slot] = j;
         }
+    }
     }
     if (j < F.n_items) {
         if (!shoot) {

@@ -656,8 +656,9 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     if (bounce) {
         CU(cudaMemsetAsync(d_nbrays, 0, sizeof(uint32_t), s->stream));
         auto gen = s->tri_stride == 64 ? tray::raygen_bounce_kernel<64> : s->tri_stride == 24 ? tray::raygen_bounce_kernel<24> : tray::raygen_bounce_kernel<48>;
-        gen<<<gen_grid, 256, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays, s->d_bounce,
-                                             rgba ? rgba_dst : nullptr, keep_rays ? s->d_brays_item : nullptr, s->frame_target ? 1u : 0u);
+        gen<<<(F.n_items + BOUNCE_BLOCK - 1) / BOUNCE_BLOCK, BOUNCE_BLOCK, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays, s->d_bounce,
+                                             rgba ? rgba_dst : nullptr, keep_rays ? s->d_brays_item : nullptr, s->frame_target ? 1u : 0u,
+                                             (uint32_t)env_int("TRAY_CUDA_BOUNCE_SORT", 1));
         CU(cudaGetLastError());
         TraceParams B; base_params(s, B);
         B.rays = s->d_brays; B.ray_item = s->d_bitem; B.n_work = F.n_items; B.n_work_dev = d_nbrays;   // count stays on the device
