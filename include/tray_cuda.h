@@ -170,7 +170,7 @@ void tray_cuda_scene_destroy(tray_scene* scene);
  * 0.95-2.9 s for its large scenes) and uploads it.  This builds the same FORMAT on the GPU — Morton sort, PLOC
  * clustering (search radius = obvhs' `search_distance`, default 14, src/main.rs:563-587), collapse to 8-wide,
  * octant slot order and quantisation as embree/src/bvh_embree_to_cwbvh.rs:85-186 — straight into the scene's device
- * buffers; only the triangle soup crosses PCIe.  Single-level scenes only (no TLAS).  Deterministic: the same
+ * buffers; only the triangle soup crosses PCIe.  (Two-level scenes: tray_cuda_scene_build_tlas.)  Deterministic: the same
  * triangles give the same bytes on every device, so per-rank replicas agree on every primitive id.
  *   tris9                n_tris x 9 floats (v0, v1, v2), HOST memory, borrowed for the call
  *   max_prims_per_leaf   1..3 (reference default 3, src/main.rs:575)
@@ -183,6 +183,18 @@ typedef struct tray_build_stats {
 
 int tray_cuda_scene_build(const float* tris9, uint64_t n_tris, uint32_t tri_stride, uint32_t max_prims_per_leaf,
                           uint32_t search_radius, int device, tray_scene** out_scene, tray_build_stats* out_stats);
+
+/* Two-level build: object k = triangles [object_offsets[k], object_offsets[k+1]) (n_objects + 1 offsets, every object
+ * non-empty).  One BLAS per object — all of them built together by a PLOC run that never merges across objects — and a
+ * TLAS over the BLAS boxes, laid out exactly as `cwbvh_gpu_runner` lays out its `--tlas` buffers
+ * (src/rt_gpu/mod.rs:53-100): BLAS nodes | TLAS nodes, TLAS root at tlas_start, blas_offsets in TLAS-leaf order, triangle
+ * indices global.  tray_cuda_scene_info reports n_instances and tlas_start.                                       */
+int tray_cuda_scene_build_tlas(const float* tris9, uint64_t n_tris, const uint64_t* object_offsets, uint32_t n_objects,
+                               uint32_t tri_stride, uint32_t max_prims_per_leaf, uint32_t search_radius, int device,
+                               tray_scene** out_scene, tray_build_stats* out_stats);
+
+/* blas_offsets (n_instances x u32) of a two-level scene, to HOST memory */
+int tray_cuda_scene_download_instances(tray_scene* scene, uint32_t* blas_offsets);
 
 /* Copy a scene's BVH back to HOST memory (any pointer may be NULL): nodes n_nodes x 80 B, tris n_tris x tri_stride,
  * prim_indices n_tris x u32 (BVH slot -> input triangle; only scenes made by tray_cuda_scene_build have them —

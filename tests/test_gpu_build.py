@@ -130,3 +130,69 @@ def test_build_is_deterministic_and_comparable_to_the_host_producer():
         assert ca["nodes"] < 1.5 * cc["nodes"], (ca, cc)
     finally:
         a.close(); b.close()
+
+
+def two_level_check(mesh, w, h, stride=48, max_leaf=3):
+    """device-built BLAS forest + TLAS: layout invariants, oracle parity in two-level mode, and the same picture as a flat
+    device build of the same triangles"""
+    tris, offs = mesh.tris(), mesh.object_offsets()
+    n_obj = offs.size - 1
+    sc = cuda.TrayCudaScene.build(tris, tri_stride=stride, max_prims_per_leaf=max_leaf, object_offsets=offs)
+    try:
+        info = sc.info()
+        assert info["is_tlas"] and info["n_instances"] == n_obj and info["tlas_start"] > 0
+        nodes, tri_bytes, pi = sc.download_bvh()
+        blas = sc.download_instances()
+        assert np.array_equal(np.sort(pi), np.arange(tris.shape[0], dtype=np.uint32))
+        assert np.array_equal(tri_bytes, host.tri_records(tris[pi], stride))
+        assert np.array_equal(np.sort(blas), np.arange(n_obj, dtype=np.uint32))      # BLAS k starts at node k; TLAS-leaf order permutes them
+        assert info["tlas_start"] + 1 <= nodes.size // 80
+        # every triangle slot belongs to the object whose BLAS holds it: slots of one object are exactly its triangles
+        obj_of_tri = np.searchsorted(offs, pi, side="right") - 1
+        assert (np.bincount(obj_of_tri, minlength=n_obj) == np.diff(offs).astype(np.int64)).all()
+        orc = ob.Oracle(nodes, tri_bytes, stride, blas_offsets=blas, tlas_start=info["tlas_start"], use_tlas=True)
+        rays = random_rays(30000, seed=n_obj)
+        got, want = sc.traverse(rays), orc.trace(rays)
+        assert np.array_equal(got["prim"], want["prim"]) and np.array_equal(bits(got["t"]), bits(want["t"]))
+        view = host.view_from_camera(mesh.camera, w, h, info["tlas_start"])
+        sc.render(view, w, h, 0, cuda.RENDER_BOUNCE | cuda.RENDER_COUNTERS)
+        out = sc.download(primary=True, bounce=True)
+        cp, _ = sc.counters()
+        ref = orc.render(view, w, h, 0)
+        for k in ("primary", "bounce"):
+            assert np.array_equal(out[k]["prim"], ref[k]["prim"]) and np.array_equal(bits(out[k]["t"]), bits(ref[k]["t"]))
+        assert cp["instances"] == ref["primary_totals"]["insts"] and cp["instances"] > 0
+    finally:
+        sc.close()
+    flat = cuda.TrayCudaScene.build(tris, tri_stride=stride, max_prims_per_leaf=max_leaf)
+    try:
+        _, _, pf = flat.download_bvh()
+        flat.render(host.view_from_camera(mesh.camera, w, h), w, h, 0, 0)
+        f = flat.download(primary=True)["primary"]
+    finally:
+        flat.close()
+    a = out["primary"]
+    hit = f["prim"] != ob.INVALID_PRIM
+    assert np.array_equal(a["prim"] != ob.INVALID_PRIM, hit)
+    assert (np.abs(a["t"][hit] - f["t"][hit]) <= 1e-5 * f["t"][hit]).mean() > 0.9999
+    assert (pi[a["prim"][hit]] == pf[f["prim"][hit]]).mean() > 0.999
+
+
+def test_two_level_build_cornell_box(cornell):
+    two_level_check(cornell, 320, 184)
+    two_level_check(cornell, 160, 92, stride=64, max_leaf=1)
+
+
+def test_two_level_build_many_objects_and_tiny_blas(box):
+    two_level_check(box, 200, 120)                                          # BLASes of a handful of triangles
+    two_level_check(host.Mesh.generate("caldera", 5, 0.02), 320, 180)       # ~80 objects of 1k-20k triangles
+
+
+def test_two_level_build_argument_errors(cornell):
+    tris, offs = cornell.tris(), cornell.object_offsets().copy()
+    bad = offs.copy(); bad[1] = bad[0]                                      # an empty object
+    with pytest.raises(cuda.TrayCudaError):
+        cuda.TrayCudaScene.build(tris, object_offsets=bad)
+    bad = offs.copy(); bad[-1] -= 1                                         # offsets do not cover the triangles
+    with pytest.raises(cuda.TrayCudaError):
+        cuda.TrayCudaScene.build(tris, object_offsets=bad)

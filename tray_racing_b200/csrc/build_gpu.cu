@@ -61,18 +61,26 @@ __device__ __forceinline__ float half_area(const float4& lo, const float4& hi) {
 }
 
 // ---- 1. boxes and scene bounds -----------------------------------------------------------------------------------
-__global__ void prim_bounds_kernel(const float* __restrict__ tris9, uint32_t n, float4* __restrict__ plo, float4* __restrict__ phi, int* __restrict__ scene) {
+__global__ void tri_boxes_kernel(const float* __restrict__ tris9, uint32_t n, float4* __restrict__ plo, float4* __restrict__ phi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* t = tris9 + 9ull * i;
+    float mn[3], mx[3];
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+        mn[a] = fminf(t[a], fminf(t[3 + a], t[6 + a]));
+        mx[a] = fmaxf(t[a], fmaxf(t[3 + a], t[6 + a]));
+    }
+    plo[i] = make_float4(mn[0], mn[1], mn[2], 0.f);
+    phi[i] = make_float4(mx[0], mx[1], mx[2], 0.f);
+}
+
+__global__ void box_bounds_kernel(const float4* __restrict__ plo, const float4* __restrict__ phi, uint32_t n, int* __restrict__ scene) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     float mn[3] = { 3.4e38f, 3.4e38f, 3.4e38f }, mx[3] = { -3.4e38f, -3.4e38f, -3.4e38f };
     if (i < n) {
-        const float* t = tris9 + 9ull * i;
-#pragma unroll
-        for (int a = 0; a < 3; a++) {
-            mn[a] = fminf(t[a], fminf(t[3 + a], t[6 + a]));
-            mx[a] = fmaxf(t[a], fmaxf(t[3 + a], t[6 + a]));
-        }
-        plo[i] = make_float4(mn[0], mn[1], mn[2], 0.f);
-        phi[i] = make_float4(mx[0], mx[1], mx[2], 0.f);
+        const float4 lo = plo[i], hi = phi[i];
+        mn[0] = lo.x; mn[1] = lo.y; mn[2] = lo.z; mx[0] = hi.x; mx[1] = hi.y; mx[2] = hi.z;
     }
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -93,8 +101,10 @@ __device__ __forceinline__ unsigned long long spread21(unsigned long long v) {
     return v;
 }
 
+// `prim_seg` (optional): segment (object) of every primitive; it becomes the top 21 bits of the key (42-bit Morton code
+// below it), so that a sort groups every object's primitives and PLOC can be kept from merging across objects
 __global__ void morton_kernel(const float4* __restrict__ plo, const float4* __restrict__ phi, uint32_t n, const int* __restrict__ scene,
-                              unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
+                              const uint32_t* __restrict__ prim_seg, unsigned long long* __restrict__ keys, uint32_t* __restrict__ vals) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 lo = plo[i], hi = phi[i];
@@ -108,40 +118,49 @@ __global__ void morton_kernel(const float4* __restrict__ plo, const float4* __re
         u = fminf(fmaxf(u, 0.f), 1.f);
         q[a] = (unsigned long long)fminf(u * 2097152.f, 2097151.f);
     }
-    keys[i] = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    unsigned long long key = (spread21(q[0]) << 2) | (spread21(q[1]) << 1) | spread21(q[2]);
+    if (prim_seg) key = ((unsigned long long)prim_seg[i] << 42) | (key >> 21);
+    keys[i] = key;
     vals[i] = i;
 }
 
 __global__ void leaf_init_kernel(const float4* __restrict__ plo, const float4* __restrict__ phi, const uint32_t* __restrict__ sorted_prim, uint32_t n,
-                                 Bvh2 b, int* __restrict__ cluster) {
+                                 const uint32_t* __restrict__ prim_seg, uint32_t* __restrict__ node_seg, Bvh2 b, int* __restrict__ cluster) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t p = sorted_prim[i];
     float4 lo = plo[p], hi = phi[p];
     lo.w = __int_as_float(-1); hi.w = __int_as_float((int)p);
     b.lo[i] = lo; b.hi[i] = hi; b.count[i] = 1u;
+    if (node_seg) node_seg[i] = prim_seg[p];
     cluster[i] = (int)i;
 }
 
 // ---- 3. PLOC ----------------------------------------------------------------------------------------------------
 // nearest neighbour of cluster i among positions [i - r, i + r]: smallest half-area of the merged box, ties to the
 // lower position (so that "mutual" is well defined and the build is deterministic)
-__global__ void __launch_bounds__(TPB) ploc_nn_kernel(const int* __restrict__ cluster, uint32_t m, int r, Bvh2 b, int* __restrict__ nn) {
-    extern __shared__ float4 s_box[];                 // [(TPB + 2r) x 2]
+__global__ void __launch_bounds__(TPB) ploc_nn_kernel(const int* __restrict__ cluster, uint32_t m, int r, Bvh2 b, const uint32_t* __restrict__ node_seg,
+                                                      int* __restrict__ nn) {
+    extern __shared__ float4 s_box[];                 // [(TPB + 2r) x 2] boxes, then [(TPB + 2r)] segments
     const int base = (int)(blockIdx.x * TPB) - r;
     const int span = TPB + 2 * r;
+    uint32_t* s_seg = reinterpret_cast<uint32_t*>(s_box + 2 * span);
     for (int k = threadIdx.x; k < span; k += TPB) {
         const int pos = base + k;
-        if (pos >= 0 && pos < (int)m) { const int c = cluster[pos]; s_box[2 * k] = b.lo[c]; s_box[2 * k + 1] = b.hi[c]; }
+        if (pos >= 0 && pos < (int)m) {
+            const int c = cluster[pos]; s_box[2 * k] = b.lo[c]; s_box[2 * k + 1] = b.hi[c];
+            s_seg[k] = node_seg ? node_seg[c] : 0u;
+        }
     }
     __syncthreads();
     const int i = (int)(blockIdx.x * TPB + threadIdx.x);
     if (i >= (int)m) return;
     const float4 lo = s_box[2 * (threadIdx.x + r)], hi = s_box[2 * (threadIdx.x + r) + 1];
+    const uint32_t seg = s_seg[threadIdx.x + r];
     float best = 3.4e38f; int best_j = -1;
     const int j0 = max(0, i - r), j1 = min((int)m - 1, i + r);
     for (int j = j0; j <= j1; j++) {
-        if (j == i) continue;
+        if (j == i || s_seg[j - base] != seg) continue;      // clusters of different objects never merge
         const float4 l2 = s_box[2 * (j - base)], h2 = s_box[2 * (j - base) + 1];
         const float dx = fmaxf(hi.x, h2.x) - fminf(lo.x, l2.x), dy = fmaxf(hi.y, h2.y) - fminf(lo.y, l2.y), dz = fmaxf(hi.z, h2.z) - fminf(lo.z, l2.z);
         const float a = dx * dy + dy * dz + dz * dx;
@@ -161,7 +180,7 @@ __global__ void ploc_flag_kernel(const int* __restrict__ nn, uint32_t m, uint32_
 
 __global__ void ploc_merge_kernel(const int* __restrict__ cluster, const int* __restrict__ nn, uint32_t m, const uint32_t* __restrict__ keep,
                                   const uint32_t* __restrict__ keep_pos, const uint32_t* __restrict__ lead, const uint32_t* __restrict__ lead_pos,
-                                  uint32_t next_node, Bvh2 b, int* __restrict__ cluster_out) {
+                                  uint32_t next_node, Bvh2 b, uint32_t* __restrict__ node_seg, int* __restrict__ cluster_out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= m || !keep[i]) return;
     int c = cluster[i];
@@ -172,6 +191,7 @@ __global__ void ploc_merge_kernel(const int* __restrict__ cluster, const int* __
         b.lo[id] = make_float4(fminf(a0.x, b0.x), fminf(a0.y, b0.y), fminf(a0.z, b0.z), __int_as_float(l));
         b.hi[id] = make_float4(fmaxf(a1.x, b1.x), fmaxf(a1.y, b1.y), fmaxf(a1.z, b1.z), __int_as_float(rgt));
         b.count[id] = b.count[l] + b.count[rgt];
+        if (node_seg) node_seg[id] = node_seg[l];
         c = id;
     }
     cluster_out[keep_pos[i]] = c;
@@ -258,10 +278,14 @@ __global__ void collapse_emit_kernel(const int* __restrict__ items, uint32_t n_i
                                      const uint32_t* __restrict__ inner_off, const uint32_t* __restrict__ tri_off,
                                      uint32_t level_base, uint32_t next_base, uint32_t prim_base,
                                      const float* __restrict__ tris9, uint8_t* __restrict__ nodes, uint8_t* __restrict__ tri_out,
-                                     uint32_t* __restrict__ prim_indices, int* __restrict__ items_next, uint32_t* __restrict__ flags) {
+                                     uint32_t* __restrict__ prim_indices, int* __restrict__ items_next, uint32_t* __restrict__ flags,
+                                     const uint32_t* __restrict__ items_root, uint32_t* __restrict__ items_root_next) {
+    // items_root (forest builds): node index of the root of the BLAS this item belongs to — child_base_idx is stored
+    // relative to it, because the two-level traversal adds the BLAS offset to every node index (query_tlas.hlsl:383)
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_items) return;
     const int root = items[i];
+    const uint32_t my_root = items_root ? (level_base == 0u ? i : items_root[i]) : 0u;
     Kids k; gather_kids(b, root, max_leaf, k);
     const float4 nlo = b.lo[root], nhi = b.hi[root];
     const float nmn[3] = { nlo.x, nlo.y, nlo.z }, nmx[3] = { nhi.x, nhi.y, nhi.z };
@@ -295,7 +319,7 @@ __global__ void collapse_emit_kernel(const int* __restrict__ items, uint32_t n_i
         if (ke + 127 >= 167) atomicOr(flags, 1u);          // scale >= 2^40: the traversal must use its unfused node test
         scale[a] = ldexp(1.0, ke);
     }
-    w[4] = next_base + inner_off[i];                        // child_base_idx
+    w[4] = next_base + inner_off[i] - my_root;              // child_base_idx
     w[5] = prim_base + tri_off[i];                          // primitive_base_idx
     uint32_t tri_local = 0, n_in = 0, imask = 0;
     for (int s = 0; s < 8; s++) {
@@ -313,7 +337,9 @@ __global__ void collapse_emit_kernel(const int* __restrict__ items, uint32_t n_i
         if (cnt > max_leaf) {
             imask |= 1u << s;
             nb[24 + s] = (uint8_t)((24 + s) | 0x20);
-            items_next[inner_off[i] + n_in] = c; n_in++;
+            items_next[inner_off[i] + n_in] = c;
+            if (items_root_next) items_root_next[inner_off[i] + n_in] = my_root;
+            n_in++;
         } else {
             const uint8_t unary = cnt == 1 ? 0x20 : cnt == 2 ? 0x60 : 0xE0;
             nb[24 + s] = (uint8_t)(unary | tri_local);
@@ -326,7 +352,7 @@ __global__ void collapse_emit_kernel(const int* __restrict__ items, uint32_t n_i
                     const uint32_t prim = (uint32_t)node_right(b.hi[x]);
                     const uint64_t slot = (uint64_t)prim_base + tri_off[i] + tri_local;
                     prim_indices[slot] = prim;
-                    write_tri_record<STRIDE>(tris9, prim, tri_out, slot);
+                    if (STRIDE != 0) write_tri_record<STRIDE>(tris9, prim, tri_out, slot);
                     tri_local++;
                 } else { stack[sp++] = node_right(b.hi[x]); stack[sp++] = node_left(xl); }
             }
@@ -350,20 +376,14 @@ struct Scratch {   // frees everything it owns on scope exit
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-}  // namespace
+// one PLOC run over `n` boxes already on the device; leaves are nodes [0, n), inner nodes follow.  With `prim_seg`
+// clusters only merge inside their segment and the run ends with one root per segment, in segment order.
+struct PlocOut { Bvh2 b; int* roots; uint32_t n_roots; uint32_t iters; void* d_tmp; size_t tmp_bytes; };
 
-int build(const float* tris9_host, uint64_t n_tris, uint32_t tri_stride, uint32_t max_leaf, uint32_t radius, cudaStream_t st,
-          Result* out, char* err, size_t errlen) {
-    memset(out, 0, sizeof *out);
-    if (n_tris == 0) return 0;
-    if (n_tris >= 0x7fffffffull) { snprintf(err, errlen, "too many triangles"); return -1; }
-    const uint32_t n = (uint32_t)n_tris;
-    const double t_begin = now_ms();
-    Scratch sc;
-    float* d_tris9; float4 *plo, *phi; int* d_scene; unsigned long long *keys, *keys2; uint32_t *vals, *vals2;
-    Bvh2 b; int *cl_a, *cl_b, *nn; uint32_t *keep, *keep_pos, *lead, *lead_pos;
-    BCU(sc.alloc(&d_tris9, (size_t)n * 36));
-    BCU(sc.alloc(&plo, (size_t)n * 16)); BCU(sc.alloc(&phi, (size_t)n * 16));
+int ploc_run(Scratch& sc, const float4* plo, const float4* phi, uint32_t n, const uint32_t* prim_seg, int r, cudaStream_t st,
+             PlocOut* out, char* err, size_t errlen) {
+    int* d_scene; unsigned long long *keys, *keys2; uint32_t *vals, *vals2;
+    Bvh2 b; int *cl_a, *cl_b, *nn; uint32_t *keep, *keep_pos, *lead, *lead_pos, *node_seg = nullptr;
     BCU(sc.alloc(&d_scene, 6 * 4));
     BCU(sc.alloc(&keys, (size_t)n * 8)); BCU(sc.alloc(&keys2, (size_t)n * 8));
     BCU(sc.alloc(&vals, (size_t)n * 4)); BCU(sc.alloc(&vals2, (size_t)n * 4));
@@ -371,105 +391,195 @@ int build(const float* tris9_host, uint64_t n_tris, uint32_t tri_stride, uint32_
     BCU(sc.alloc(&cl_a, (size_t)n * 4)); BCU(sc.alloc(&cl_b, (size_t)n * 4)); BCU(sc.alloc(&nn, (size_t)n * 4));
     BCU(sc.alloc(&keep, (size_t)(n + 1) * 4)); BCU(sc.alloc(&keep_pos, (size_t)(n + 1) * 4));
     BCU(sc.alloc(&lead, (size_t)(n + 1) * 4)); BCU(sc.alloc(&lead_pos, (size_t)(n + 1) * 4));
-    BCU(cudaMemcpyAsync(d_tris9, tris9_host, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+    if (prim_seg) BCU(sc.alloc(&node_seg, (size_t)2 * n * 4));
     const int scene_init[6] = { 0x7f7fffff, 0x7f7fffff, 0x7f7fffff, (int)0x80800000, (int)0x80800000, (int)0x80800000 };   // +max x3, -max x3 (ordered)
     BCU(cudaMemcpyAsync(d_scene, scene_init, sizeof scene_init, cudaMemcpyHostToDevice, st));
-    BCU(cudaStreamSynchronize(st));
-    const double t_upload = now_ms();
-
-    prim_bounds_kernel<<<blocks(n), TPB, 0, st>>>(d_tris9, n, plo, phi, d_scene);
-    morton_kernel<<<blocks(n), TPB, 0, st>>>(plo, phi, n, d_scene, keys, vals);
+    box_bounds_kernel<<<blocks(n), TPB, 0, st>>>(plo, phi, n, d_scene);
+    morton_kernel<<<blocks(n), TPB, 0, st>>>(plo, phi, n, d_scene, prim_seg, keys, vals);
     size_t tmp_bytes = 0, tmp2 = 0;
     BCU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 63, st));
     BCU(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, keep, keep_pos, (int)n + 1, st));
     if (tmp2 > tmp_bytes) tmp_bytes = tmp2;
     void* d_tmp; BCU(sc.alloc(&d_tmp, tmp_bytes));
     BCU(cub::DeviceRadixSort::SortPairs(d_tmp, tmp_bytes, keys, keys2, vals, vals2, (int)n, 0, 63, st));
-    leaf_init_kernel<<<blocks(n), TPB, 0, st>>>(plo, phi, vals2, n, b, cl_a);
+    leaf_init_kernel<<<blocks(n), TPB, 0, st>>>(plo, phi, vals2, n, prim_seg, node_seg, b, cl_a);
     BCU(cudaGetLastError());
-    BCU(cudaStreamSynchronize(st));
-    const double t_sort = now_ms();
-
-    // ---- PLOC ----
     uint32_t m = n, next_node = n, iters = 0;
     int* cl_in = cl_a; int* cl_out = cl_b;
-    const int r = (int)(radius < 1 ? 1 : (radius > 64 ? 64 : radius));
     while (m > 1) {
-        ploc_nn_kernel<<<blocks(m), TPB, (size_t)(TPB + 2 * r) * 32, st>>>(cl_in, m, r, b, nn);
+        ploc_nn_kernel<<<blocks(m), TPB, (size_t)(TPB + 2 * r) * 36, st>>>(cl_in, m, r, b, node_seg, nn);
         ploc_flag_kernel<<<blocks(m), TPB, 0, st>>>(nn, m, keep, lead);
         // scans run over m + 1 entries so that entry m holds the total (the extra input element is never a keeper)
         BCU(cudaMemsetAsync(keep + m, 0, 4, st)); BCU(cudaMemsetAsync(lead + m, 0, 4, st));
         BCU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, keep, keep_pos, (int)m + 1, st));
         BCU(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, lead, lead_pos, (int)m + 1, st));
-        ploc_merge_kernel<<<blocks(m), TPB, 0, st>>>(cl_in, nn, m, keep, keep_pos, lead, lead_pos, next_node, b, cl_out);
+        ploc_merge_kernel<<<blocks(m), TPB, 0, st>>>(cl_in, nn, m, keep, keep_pos, lead, lead_pos, next_node, b, node_seg, cl_out);
         uint32_t tot[2];
         BCU(cudaMemcpyAsync(&tot[0], keep_pos + m, 4, cudaMemcpyDeviceToHost, st));
         BCU(cudaMemcpyAsync(&tot[1], lead_pos + m, 4, cudaMemcpyDeviceToHost, st));
         BCU(cudaStreamSynchronize(st));
-        if (tot[1] == 0 || tot[0] >= m) { snprintf(err, errlen, "PLOC made no progress at %u clusters", m); return -3; }
+        BCU(cudaGetLastError());
+        if (tot[1] == 0) {
+            if (prim_seg) break;                      // every segment is down to one cluster
+            snprintf(err, errlen, "PLOC made no progress at %u clusters", m); return -3;
+        }
         next_node += tot[1]; m = tot[0]; iters++;
         int* t = cl_in; cl_in = cl_out; cl_out = t;
     }
-    int root = 0;
-    BCU(cudaMemcpyAsync(&root, cl_in, 4, cudaMemcpyDeviceToHost, st));
+    out->b = b; out->roots = cl_in; out->n_roots = m; out->iters = iters; out->d_tmp = d_tmp; out->tmp_bytes = tmp_bytes;
+    return 0;
+}
+
+// level-synchronous collapse of the BVH2 subtrees `roots` (one wide root node each, stored at node indices 0..n_roots-1 of
+// `nodes`, i.e. at `nodes` itself — pass the destination already offset).  forest = child indices relative to each root.
+struct CollapseOut { uint32_t n_nodes, n_prims, levels; bool force_exact; };
+
+int collapse_run(Scratch& sc, const PlocOut& pl, uint32_t n_prims, bool forest, uint32_t max_leaf, uint32_t tri_stride,
+                 const float* d_tris9, uint8_t* nodes, uint64_t node_cap, uint8_t* tri_out, uint32_t* prim_idx, uint32_t prim_base0,
+                 cudaStream_t st, CollapseOut* out, char* err, size_t errlen) {
+    const uint32_t n = n_prims;
+    int *items_a, *items_b; uint32_t *n_inner, *n_tri, *inner_off, *tri_off, *d_flags, *root_a = nullptr, *root_b = nullptr;
+    BCU(sc.alloc(&items_a, (size_t)(n + 1) * 4)); BCU(sc.alloc(&items_b, (size_t)(n + 1) * 4));
+    BCU(sc.alloc(&n_inner, (size_t)(n + 2) * 4)); BCU(sc.alloc(&n_tri, (size_t)(n + 2) * 4));
+    BCU(sc.alloc(&inner_off, (size_t)(n + 2) * 4)); BCU(sc.alloc(&tri_off, (size_t)(n + 2) * 4));
+    BCU(sc.alloc(&d_flags, 4));
+    if (forest) { BCU(sc.alloc(&root_a, (size_t)(n + 1) * 4)); BCU(sc.alloc(&root_b, (size_t)(n + 1) * 4)); }
+    BCU(cudaMemsetAsync(d_flags, 0, 4, st));
+    BCU(cudaMemcpyAsync(items_a, pl.roots, (size_t)pl.n_roots * 4, cudaMemcpyDeviceToDevice, st));
+    uint32_t n_items = pl.n_roots, level_base = 0, prim_base = prim_base0, levels = 0;
+    int* it_in = items_a; int* it_out = items_b; uint32_t* rt_in = root_a; uint32_t* rt_out = root_b;
+    while (n_items) {
+        if ((uint64_t)level_base + n_items > node_cap) { snprintf(err, errlen, "node count exceeds its bound"); return -3; }
+        collapse_count_kernel<<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, pl.b, max_leaf, n_inner, n_tri);
+        BCU(cudaMemsetAsync(n_inner + n_items, 0, 4, st)); BCU(cudaMemsetAsync(n_tri + n_items, 0, 4, st));
+        BCU(cub::DeviceScan::ExclusiveSum(pl.d_tmp, const_cast<size_t&>(pl.tmp_bytes), n_inner, inner_off, (int)n_items + 1, st));
+        BCU(cub::DeviceScan::ExclusiveSum(pl.d_tmp, const_cast<size_t&>(pl.tmp_bytes), n_tri, tri_off, (int)n_items + 1, st));
+        const uint32_t next_base = level_base + n_items;
+#define EMIT(S) collapse_emit_kernel<S><<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, pl.b, max_leaf, inner_off, tri_off, level_base, next_base, \
+                    prim_base, d_tris9, nodes, tri_out, prim_idx, it_out, d_flags, forest ? rt_in : nullptr, forest ? rt_out : nullptr)
+        if (tri_stride == 64) EMIT(64); else if (tri_stride == 24) EMIT(24); else if (tri_stride == 48) EMIT(48); else EMIT(0);
+#undef EMIT
+        uint32_t tot[2];
+        BCU(cudaMemcpyAsync(&tot[0], inner_off + n_items, 4, cudaMemcpyDeviceToHost, st));
+        BCU(cudaMemcpyAsync(&tot[1], tri_off + n_items, 4, cudaMemcpyDeviceToHost, st));
+        BCU(cudaStreamSynchronize(st));
+        BCU(cudaGetLastError());
+        level_base = next_base; prim_base += tot[1]; n_items = tot[0]; levels++;
+        int* t = it_in; it_in = it_out; it_out = t;
+        uint32_t* u = rt_in; rt_in = rt_out; rt_out = u;
+    }
+    if (prim_base - prim_base0 != n) { snprintf(err, errlen, "collapse placed %u of %u primitives", prim_base - prim_base0, n); return -3; }
+    uint32_t flags = 0;
+    BCU(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, st));
     BCU(cudaStreamSynchronize(st));
+    out->n_nodes = level_base; out->n_prims = n; out->levels = levels; out->force_exact = (flags & 1u) != 0;
+    return 0;
+}
+
+__global__ void seg_of_prims_kernel(const uint64_t* __restrict__ offsets, uint32_t n_obj, uint32_t n, uint32_t* __restrict__ prim_seg) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t lo = 0, hi = n_obj;                      // last k with offsets[k] <= i
+    while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (offsets[mid] <= i) lo = mid; else hi = mid; }
+    prim_seg[i] = lo;
+}
+
+// boxes of the BLAS roots (TLAS primitives), and which node each object's BLAS starts at
+__global__ void blas_boxes_kernel(const int* __restrict__ roots, uint32_t n_obj, Bvh2 b, float4* __restrict__ plo, float4* __restrict__ phi) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_obj) return;
+    plo[i] = b.lo[roots[i]]; phi[i] = b.hi[roots[i]];
+}
+__global__ void blas_offsets_kernel(const uint32_t* __restrict__ tlas_prim, uint32_t n_obj, uint32_t* __restrict__ blas_offsets) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_obj) return;
+    blas_offsets[i] = tlas_prim[i];                   // BLAS k has its root wide node at node index k (forest level 0)
+}
+
+}  // namespace
+
+int build(const float* tris9_host, uint64_t n_tris, uint32_t tri_stride, uint32_t max_leaf, uint32_t radius, cudaStream_t st,
+          Result* out, char* err, size_t errlen) {
+    return build_tlas(tris9_host, n_tris, nullptr, 0, tri_stride, max_leaf, radius, st, out, err, errlen);
+}
+
+// object_offsets == NULL: one flat BVH.  Otherwise (n_objects + 1 offsets into the triangle array): one BLAS per object —
+// built together, as a forest, by a PLOC run that never merges across objects — plus a TLAS over the BLAS boxes, laid out
+// as cwbvh_gpu_runner lays them out (src/rt_gpu/mod.rs:53-100): BLAS nodes | TLAS nodes, tlas_start, blas_offsets in
+// TLAS-leaf order, triangle indices global.
+int build_tlas(const float* tris9_host, uint64_t n_tris, const uint64_t* object_offsets, uint32_t n_objects, uint32_t tri_stride,
+               uint32_t max_leaf, uint32_t radius, cudaStream_t st, Result* out, char* err, size_t errlen) {
+    memset(out, 0, sizeof *out);
+    if (n_tris == 0) return 0;
+    if (n_tris >= 0x7fffffffull) { snprintf(err, errlen, "too many triangles"); return -1; }
+    const bool tlas = object_offsets != nullptr;
+    if (tlas) {
+        if (n_objects == 0 || n_objects >= (1u << 21)) { snprintf(err, errlen, "object count must be 1 .. 2^21 - 1"); return -1; }
+        if (object_offsets[0] != 0 || object_offsets[n_objects] != n_tris) { snprintf(err, errlen, "object_offsets must run from 0 to n_tris"); return -1; }
+        for (uint32_t k = 0; k < n_objects; k++)
+            if (object_offsets[k + 1] <= object_offsets[k]) { snprintf(err, errlen, "object %u is empty", k); return -1; }
+    }
+    const uint32_t n = (uint32_t)n_tris;
+    const int r = (int)(radius < 1 ? 1 : (radius > 64 ? 64 : radius));
+    const double t_begin = now_ms();
+    Scratch sc;
+    float* d_tris9; float4 *plo, *phi; uint32_t* prim_seg = nullptr; uint64_t* d_off = nullptr;
+    BCU(sc.alloc(&d_tris9, (size_t)n * 36));
+    BCU(sc.alloc(&plo, (size_t)n * 16)); BCU(sc.alloc(&phi, (size_t)n * 16));
+    BCU(cudaMemcpyAsync(d_tris9, tris9_host, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+    if (tlas) {
+        BCU(sc.alloc(&prim_seg, (size_t)n * 4)); BCU(sc.alloc(&d_off, (size_t)(n_objects + 1) * 8));
+        BCU(cudaMemcpyAsync(d_off, object_offsets, (size_t)(n_objects + 1) * 8, cudaMemcpyHostToDevice, st));
+        seg_of_prims_kernel<<<blocks(n), TPB, 0, st>>>(d_off, n_objects, n, prim_seg);
+    }
+    BCU(cudaStreamSynchronize(st));
+    const double t_upload = now_ms();
+    tri_boxes_kernel<<<blocks(n), TPB, 0, st>>>(d_tris9, n, plo, phi);
+    PlocOut pl;
+    int rc = ploc_run(sc, plo, phi, n, prim_seg, r, st, &pl, err, errlen);
+    if (rc) return rc;
+    if (tlas && pl.n_roots != n_objects) { snprintf(err, errlen, "PLOC left %u roots for %u objects", pl.n_roots, n_objects); return -3; }
     const double t_ploc = now_ms();
 
-    // ---- collapse, level by level ----
-    // node count is bounded by the number of BVH2 inner nodes + 1; allocate that, shrink-copy is not worth it (80 B each)
-    const uint64_t node_cap = (uint64_t)n + 1;
-    uint8_t *d_nodes = nullptr, *d_tri_out = nullptr; uint32_t* d_prim_idx = nullptr; uint32_t* d_flags;
-    int *items_a, *items_b; uint32_t *n_inner, *n_tri, *inner_off, *tri_off;
-    BCU(sc.alloc(&items_a, (size_t)n * 4)); BCU(sc.alloc(&items_b, (size_t)n * 4));
-    BCU(sc.alloc(&n_inner, (size_t)(n + 1) * 4)); BCU(sc.alloc(&n_tri, (size_t)(n + 1) * 4));
-    BCU(sc.alloc(&inner_off, (size_t)(n + 1) * 4)); BCU(sc.alloc(&tri_off, (size_t)(n + 1) * 4));
-    BCU(sc.alloc(&d_flags, 4));
-    BCU(cudaMemsetAsync(d_flags, 0, 4, st));
-    if (cudaMalloc(&d_nodes, node_cap * 80) != cudaSuccess || cudaMalloc(&d_tri_out, (size_t)n * tri_stride) != cudaSuccess ||
-        cudaMalloc(&d_prim_idx, (size_t)n * 4) != cudaSuccess) {
-        cudaFree(d_nodes); cudaFree(d_tri_out); cudaFree(d_prim_idx);
+    // node count of a BLAS is bounded by its triangle count (>= 1 node); the TLAS by the object count
+    const uint64_t blas_cap = (uint64_t)n + (tlas ? n_objects : 1), tlas_cap = tlas ? (uint64_t)n_objects + 1 : 0;
+    uint8_t *d_nodes = nullptr, *d_tri_out = nullptr; uint32_t *d_prim_idx = nullptr, *d_blas = nullptr;
+    if (cudaMalloc(&d_nodes, (blas_cap + tlas_cap) * 80) != cudaSuccess || cudaMalloc(&d_tri_out, (size_t)n * tri_stride) != cudaSuccess ||
+        cudaMalloc(&d_prim_idx, (size_t)n * 4) != cudaSuccess || (tlas && cudaMalloc(&d_blas, (size_t)n_objects * 4) != cudaSuccess)) {
+        cudaFree(d_nodes); cudaFree(d_tri_out); cudaFree(d_prim_idx); cudaFree(d_blas);
         snprintf(err, errlen, "out of device memory for the BVH"); cudaGetLastError(); return -2;
     }
-    auto bail = [&]() { cudaFree(d_nodes); cudaFree(d_tri_out); cudaFree(d_prim_idx); };
-#define BCU2(call) do { cudaError_t e2_ = (call); if (e2_ != cudaSuccess) { bail(); snprintf(err, errlen, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e2_), __FILE__, __LINE__); return -2; } } while (0)
-    BCU2(cudaMemcpyAsync(items_a, &root, 4, cudaMemcpyHostToDevice, st));
-    uint32_t n_items = 1, level_base = 0, prim_base = 0, levels = 0;
-    int* it_in = items_a; int* it_out = items_b;
-    while (n_items) {
-        collapse_count_kernel<<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, b, max_leaf, n_inner, n_tri);
-        BCU2(cudaMemsetAsync(n_inner + n_items, 0, 4, st)); BCU2(cudaMemsetAsync(n_tri + n_items, 0, 4, st));
-        BCU2(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, n_inner, inner_off, (int)n_items + 1, st));
-        BCU2(cub::DeviceScan::ExclusiveSum(d_tmp, tmp_bytes, n_tri, tri_off, (int)n_items + 1, st));
-        const uint32_t next_base = level_base + n_items;
-        if (tri_stride == 64)
-            collapse_emit_kernel<64><<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, b, max_leaf, inner_off, tri_off, level_base, next_base, prim_base,
-                                                                     d_tris9, d_nodes, d_tri_out, d_prim_idx, it_out, d_flags);
-        else if (tri_stride == 24)
-            collapse_emit_kernel<24><<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, b, max_leaf, inner_off, tri_off, level_base, next_base, prim_base,
-                                                                     d_tris9, d_nodes, d_tri_out, d_prim_idx, it_out, d_flags);
-        else
-            collapse_emit_kernel<48><<<blocks(n_items), TPB, 0, st>>>(it_in, n_items, b, max_leaf, inner_off, tri_off, level_base, next_base, prim_base,
-                                                                     d_tris9, d_nodes, d_tri_out, d_prim_idx, it_out, d_flags);
-        uint32_t tot[2];
-        BCU2(cudaMemcpyAsync(&tot[0], inner_off + n_items, 4, cudaMemcpyDeviceToHost, st));
-        BCU2(cudaMemcpyAsync(&tot[1], tri_off + n_items, 4, cudaMemcpyDeviceToHost, st));
-        BCU2(cudaStreamSynchronize(st));
-        BCU2(cudaGetLastError());
-        level_base = next_base; prim_base += tot[1]; n_items = tot[0]; levels++;
-        if ((uint64_t)level_base + n_items > node_cap) { bail(); snprintf(err, errlen, "node count exceeds its bound"); return -3; }
-        int* t = it_in; it_in = it_out; it_out = t;
+    auto bail = [&](int code) { cudaFree(d_nodes); cudaFree(d_tri_out); cudaFree(d_prim_idx); cudaFree(d_blas); return code; };
+    CollapseOut co;
+    rc = collapse_run(sc, pl, n, tlas, max_leaf, tri_stride, d_tris9, d_nodes, blas_cap, d_tri_out, d_prim_idx, 0, st, &co, err, errlen);
+    if (rc) return bail(rc);
+    uint32_t tlas_start = 0, n_nodes = co.n_nodes, tl_iters = 0, tl_levels = 0;
+    bool force_exact = co.force_exact;
+    if (tlas) {
+        // TLAS: the same pipeline over the BLAS boxes; its "triangles" are instance slots
+        Scratch sc2;
+        float4 *tlo, *thi; uint32_t* tl_prim;
+        if (sc2.alloc(&tlo, (size_t)n_objects * 16) != cudaSuccess || sc2.alloc(&thi, (size_t)n_objects * 16) != cudaSuccess ||
+            sc2.alloc(&tl_prim, (size_t)n_objects * 4) != cudaSuccess) { snprintf(err, errlen, "out of device memory"); cudaGetLastError(); return bail(-2); }
+        blas_boxes_kernel<<<blocks(n_objects), TPB, 0, st>>>(pl.roots, n_objects, pl.b, tlo, thi);
+        PlocOut tp;
+        rc = ploc_run(sc2, tlo, thi, n_objects, nullptr, r, st, &tp, err, errlen);
+        if (rc) return bail(rc);
+        CollapseOut tc;
+        tlas_start = co.n_nodes;
+        rc = collapse_run(sc2, tp, n_objects, false, max_leaf, 0, nullptr, d_nodes + (uint64_t)tlas_start * 80, tlas_cap, nullptr, tl_prim, 0, st, &tc, err, errlen);
+        if (rc) return bail(rc);
+        blas_offsets_kernel<<<blocks(n_objects), TPB, 0, st>>>(tl_prim, n_objects, d_blas);
+        if (cudaStreamSynchronize(st) != cudaSuccess) { snprintf(err, errlen, "TLAS build failed: %s", cudaGetErrorString(cudaGetLastError())); return bail(-2); }
+        n_nodes += tc.n_nodes; tl_iters = tp.iters; tl_levels = tc.levels; force_exact = force_exact || tc.force_exact;
     }
-    if (prim_base != n) { bail(); snprintf(err, errlen, "collapse placed %u of %u primitives", prim_base, n); return -3; }
-    uint32_t flags = 0;
-    BCU2(cudaMemcpyAsync(&flags, d_flags, 4, cudaMemcpyDeviceToHost, st));
-    BCU2(cudaStreamSynchronize(st));
-#undef BCU2
     const double t_end = now_ms();
-    out->d_nodes = d_nodes; out->n_nodes = level_base; out->d_tris = d_tri_out; out->d_prim_indices = d_prim_idx;
-    out->force_exact = (flags & 1u) != 0;
-    out->stats.n_tris = n; out->stats.n_nodes = level_base; out->stats.ploc_iterations = iters; out->stats.levels = levels;
-    out->stats.ms_upload = (float)(t_upload - t_begin); out->stats.ms_sort = (float)(t_sort - t_upload);
-    out->stats.ms_ploc = (float)(t_ploc - t_sort); out->stats.ms_collapse = (float)(t_end - t_ploc); out->stats.ms_total = (float)(t_end - t_begin);
+    out->d_nodes = d_nodes; out->n_nodes = n_nodes; out->d_tris = d_tri_out; out->d_prim_indices = d_prim_idx;
+    out->d_blas_offsets = d_blas; out->n_instances = tlas ? n_objects : 0; out->tlas_start = tlas_start;
+    out->force_exact = force_exact;
+    out->stats.n_tris = n; out->stats.n_nodes = n_nodes; out->stats.ploc_iterations = pl.iters + tl_iters; out->stats.levels = co.levels + tl_levels;
+    out->stats.ms_upload = (float)(t_upload - t_begin); out->stats.ms_sort = 0.f;
+    out->stats.ms_ploc = (float)(t_ploc - t_upload); out->stats.ms_collapse = (float)(t_end - t_ploc); out->stats.ms_total = (float)(t_end - t_begin);
     return 0;
 }
 

@@ -304,7 +304,7 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
     *out = nullptr;
     if (!built && ((n_nodes && !nodes) || (n_tris && !tris))) return fail(TRAY_ERR_ARG, "NULL node / triangle buffer");
     if (tri_stride != 48 && tri_stride != 64 && tri_stride != 24) return fail(TRAY_ERR_ARG, "tri_stride must be 48, 64 or 24 (got %u)", tri_stride);
-    if (n_instances && !blas_offsets) return fail(TRAY_ERR_ARG, "n_instances > 0 but blas_offsets is NULL");
+    if (n_instances && !blas_offsets && !built) return fail(TRAY_ERR_ARG, "n_instances > 0 but blas_offsets is NULL");
     if (n_instances && tlas_start >= n_nodes) return fail(TRAY_ERR_ARG, "tlas_start %u outside %llu nodes", tlas_start, (unsigned long long)n_nodes);
     if (n_nodes >= 0xffffffffull || n_tris >= 0xffffffffull) return fail(TRAY_ERR_ARG, "node / triangle indices are 32-bit");
     const int ndev = tray_cuda_device_count();
@@ -344,11 +344,12 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         const size_t nb = (size_t)(n_nodes ? n_nodes : 1) * 80, tb = (size_t)(n_tris ? n_tris : 1) * tri_stride;
         if (built && built->d_nodes) {
             s->d_nodes = (uint4*)built->d_nodes; s->d_tris = (uint4*)built->d_tris; s->d_prim_indices = built->d_prim_indices;
+            s->d_blas = built->d_blas_offsets;
         } else {
             CU(cudaMalloc(&s->d_nodes, nb));
             CU(cudaMalloc(&s->d_tris, tb));
         }
-        CU(cudaMalloc(&s->d_blas, (size_t)(n_instances ? n_instances : 1) * 4));
+        if (!s->d_blas) CU(cudaMalloc(&s->d_blas, (size_t)(n_instances ? n_instances : 1) * 4));
         CU(cudaMalloc(&s->d_cursor, 16 * sizeof(unsigned long long)));
         CU(cudaMalloc(&s->d_overflow, 4));
         CU(cudaMemsetAsync(s->d_cursor, 0, 16 * sizeof(unsigned long long), s->stream));
@@ -358,7 +359,7 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         else if (n_nodes) CU(cudaMemcpyAsync(s->d_nodes, nodes, (size_t)n_nodes * 80, cudaMemcpyHostToDevice, s->stream));
         else CU(cudaMemsetAsync(s->d_nodes, 0, 80, s->stream));   // empty scene: a root with no children, every ray misses
         if (!(built && built->d_nodes) && n_tris) CU(cudaMemcpyAsync(s->d_tris, tris, (size_t)n_tris * tri_stride, cudaMemcpyHostToDevice, s->stream));
-        if (n_instances) CU(cudaMemcpyAsync(s->d_blas, blas_offsets, (size_t)n_instances * 4, cudaMemcpyHostToDevice, s->stream));
+        if (n_instances && blas_offsets) CU(cudaMemcpyAsync(s->d_blas, blas_offsets, (size_t)n_instances * 4, cudaMemcpyHostToDevice, s->stream));
         // keep the node array hot in the 126 MB L2: persisting access-policy window, attached to every traversal launch
         if (env_int("TRAY_CUDA_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0 && n_nodes) {
             size_t want = (size_t)prop.persistingL2CacheMaxSize;
@@ -394,25 +395,52 @@ int tray_cuda_scene_create(const void* nodes, uint64_t n_nodes, const void* tris
     return scene_create_impl(nodes, n_nodes, tris, n_tris, tri_stride, blas_offsets, n_instances, tlas_start, device, nullptr, out);
 }
 
-int tray_cuda_scene_build(const float* tris9, uint64_t n_tris, uint32_t tri_stride, uint32_t max_prims_per_leaf,
-                          uint32_t search_radius, int device, tray_scene** out, tray_build_stats* out_stats) {
+}  // extern "C"
+
+namespace {
+int scene_build_impl(const float* tris9, uint64_t n_tris, const uint64_t* object_offsets, uint32_t n_objects, uint32_t tri_stride,
+                     uint32_t max_prims_per_leaf, uint32_t search_radius, int device, tray_scene** out, tray_build_stats* out_stats) {
     if (!out) return fail(TRAY_ERR_ARG, "out_scene is NULL");
     *out = nullptr;
     if (n_tris && !tris9) return fail(TRAY_ERR_ARG, "NULL triangle buffer");
     if (tri_stride != 48 && tri_stride != 64 && tri_stride != 24) return fail(TRAY_ERR_ARG, "tri_stride must be 48, 64 or 24 (got %u)", tri_stride);
     if (max_prims_per_leaf < 1 || max_prims_per_leaf > 3) return fail(TRAY_ERR_ARG, "max_prims_per_leaf must be 1..3");
     if (search_radius > 64) return fail(TRAY_ERR_ARG, "search_radius must be 0 (default 14) or 1..64");
+    if (object_offsets && n_tris == 0) return fail(TRAY_ERR_ARG, "a two-level scene needs triangles");
     const int ndev = tray_cuda_device_count();
     if (ndev == 0) return fail(TRAY_ERR_NO_DEVICE, "no CUDA device (tray_cuda has no CPU fallback)");
     if (device < 0 || device >= ndev) return fail(TRAY_ERR_ARG, "device %d out of range (0..%d)", device, ndev - 1);
     CU(cudaSetDevice(device));
     tray_build::Result r;
     char msg[400] = "";
-    const int brc = tray_build::build(tris9, n_tris, tri_stride, max_prims_per_leaf, search_radius ? search_radius : 14u, nullptr, &r, msg, sizeof msg);
+    const int brc = tray_build::build_tlas(tris9, n_tris, object_offsets, n_objects, tri_stride, max_prims_per_leaf,
+                                           search_radius ? search_radius : 14u, nullptr, &r, msg, sizeof msg);
     if (brc) return fail(brc == -1 ? TRAY_ERR_ARG : TRAY_ERR_CUDA, "device build failed: %s", msg);
-    const int rc = scene_create_impl(nullptr, r.n_nodes, nullptr, n_tris, tri_stride, nullptr, 0, 0, device, &r, out);
-    if (rc) { if (!*out) { cudaFree(r.d_nodes); cudaFree(r.d_tris); cudaFree(r.d_prim_indices); } return rc; }
+    const int rc = scene_create_impl(nullptr, r.n_nodes, nullptr, n_tris, tri_stride, nullptr, r.n_instances, r.tlas_start, device, &r, out);
+    if (rc) { if (!*out) { cudaFree(r.d_nodes); cudaFree(r.d_tris); cudaFree(r.d_prim_indices); cudaFree(r.d_blas_offsets); } return rc; }
     if (out_stats) *out_stats = r.stats;
+    return TRAY_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int tray_cuda_scene_build(const float* tris9, uint64_t n_tris, uint32_t tri_stride, uint32_t max_prims_per_leaf,
+                          uint32_t search_radius, int device, tray_scene** out, tray_build_stats* out_stats) {
+    return scene_build_impl(tris9, n_tris, nullptr, 0, tri_stride, max_prims_per_leaf, search_radius, device, out, out_stats);
+}
+
+int tray_cuda_scene_build_tlas(const float* tris9, uint64_t n_tris, const uint64_t* object_offsets, uint32_t n_objects, uint32_t tri_stride,
+                               uint32_t max_prims_per_leaf, uint32_t search_radius, int device, tray_scene** out, tray_build_stats* out_stats) {
+    if (!object_offsets || n_objects == 0) return fail(TRAY_ERR_ARG, "object_offsets is NULL / no objects");
+    return scene_build_impl(tris9, n_tris, object_offsets, n_objects, tri_stride, max_prims_per_leaf, search_radius, device, out, out_stats);
+}
+
+int tray_cuda_scene_download_instances(tray_scene* s, uint32_t* blas_offsets) {
+    if (!s || !blas_offsets) return fail(TRAY_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    if (s->n_instances) CU(cudaMemcpy(blas_offsets, s->d_blas, (size_t)s->n_instances * 4, cudaMemcpyDeviceToHost));
     return TRAY_OK;
 }
 

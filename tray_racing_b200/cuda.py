@@ -25,6 +25,7 @@ EXPORTS = (
     "tray_cuda_frame_alloc", "tray_cuda_frame_free", "tray_cuda_ipc_export", "tray_cuda_ipc_open", "tray_cuda_ipc_close",
     "tray_cuda_scene_set_frame_target", "tray_cuda_render_timed", "tray_cuda_trace_any", "tray_cuda_trace_any_device",
     "tray_cuda_scene_build", "tray_cuda_scene_download", "tray_cuda_frame_readback_begin", "tray_cuda_frame_readback_wait",
+    "tray_cuda_scene_build_tlas", "tray_cuda_scene_download_instances",
 )
 
 
@@ -89,6 +90,10 @@ def lib() -> C.CDLL:
         L.tray_cuda_trace_device.argtypes = [vp, vp, u64, vp, vp, f32p]
         L.tray_cuda_scene_build.restype = i32
         L.tray_cuda_scene_build.argtypes = [vp, u64, u32, u32, u32, i32, C.POINTER(vp), C.POINTER(BuildStats)]
+        L.tray_cuda_scene_build_tlas.restype = i32
+        L.tray_cuda_scene_build_tlas.argtypes = [vp, u64, vp, u32, u32, u32, u32, i32, C.POINTER(vp), C.POINTER(BuildStats)]
+        L.tray_cuda_scene_download_instances.restype = i32
+        L.tray_cuda_scene_download_instances.argtypes = [vp, vp]
         L.tray_cuda_scene_download.restype = i32
         L.tray_cuda_scene_download.argtypes = [vp, vp, vp, vp]
         L.tray_cuda_frame_readback_begin.restype = i32
@@ -211,14 +216,21 @@ class TrayCudaScene:
         self.frame_size = None
 
     @classmethod
-    def build(cls, tris, tri_stride=48, max_prims_per_leaf=3, search_radius=0, device=0) -> "TrayCudaScene":
+    def build(cls, tris, tri_stride=48, max_prims_per_leaf=3, search_radius=0, device=0, object_offsets=None) -> "TrayCudaScene":
         """Build the CWBVH ON THE GPU from a triangle soup (n x 3 x 3 floats) — tray_cuda_scene_build; the reference's
-        `cwbvh_from_tris` (src/cwbvh.rs:24-105) runs on the CPU.  `build_stats` holds the phase times."""
+        `cwbvh_from_tris` (src/cwbvh.rs:24-105) runs on the CPU.  With `object_offsets` (n_objects + 1 triangle offsets):
+        one BLAS per object + a TLAS (`tlas_from_blas`, src/cwbvh.rs:108-137) — tray_cuda_scene_build_tlas.
+        `build_stats` holds the phase times."""
         t = np.ascontiguousarray(tris, dtype=np.float32).reshape(-1, 9)
         self = cls.__new__(cls)
         h, st = C.c_void_p(), BuildStats()
-        _check(lib().tray_cuda_scene_build(t.ctypes.data, t.shape[0], tri_stride, max_prims_per_leaf, search_radius, device,
-                                           C.byref(h), C.byref(st)))
+        if object_offsets is not None:
+            off = np.ascontiguousarray(object_offsets, dtype=np.uint64)
+            _check(lib().tray_cuda_scene_build_tlas(t.ctypes.data, t.shape[0], off.ctypes.data, off.size - 1, tri_stride,
+                                                    max_prims_per_leaf, search_radius, device, C.byref(h), C.byref(st)))
+        else:
+            _check(lib().tray_cuda_scene_build(t.ctypes.data, t.shape[0], tri_stride, max_prims_per_leaf, search_radius, device,
+                                               C.byref(h), C.byref(st)))
         self._h = h
         self.tri_stride = tri_stride
         self.frame_size = None
@@ -233,6 +245,13 @@ class TrayCudaScene:
         pi = np.zeros(i["n_tris"], dtype=np.uint32) if prim_indices else None
         _check(lib().tray_cuda_scene_download(self._h, nodes.ctypes.data, tris.ctypes.data, None if pi is None else pi.ctypes.data))
         return nodes, tris, pi
+
+    def download_instances(self) -> np.ndarray:
+        """blas_offsets of a two-level scene (tray_cuda_scene_download_instances)"""
+        out = np.zeros(self.info()["n_instances"], dtype=np.uint32)
+        if out.size:
+            _check(lib().tray_cuda_scene_download_instances(self._h, out.ctypes.data))
+        return out
 
     @classmethod
     def from_packed(cls, p, device=0) -> "TrayCudaScene":
