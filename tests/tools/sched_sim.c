@@ -8,6 +8,8 @@
  *   policy 1  warp-level POOL of K rays: any lane can run any ray (upper bound for in-warp compaction)
  *   policy 2  one ray per lane, but a triangle phase DRAINS every participating lane's triangle group
  *             (cost = csel + ct per round, rounds = the longest group)
+ *   policy 3  one ray per lane; a node step with at most K participating lanes runs NARROW: 8 lanes test the 8
+ *             children of one ray, 4 rays per pass, cost = csel per pass (csel = slots of one narrow pass)
  * Each step costs issue slots (cn, ct, plus csel when K > 1); the result is total slots, per-phase lane occupancy
  * and the makespan over warps.  Nothing here is on the product path. */
 #include <stdint.h>
@@ -41,7 +43,7 @@ static void heap_sift(int* h, int n, int i, const warp* w) {
 }
 
 int sched_sim(const uint8_t* ops, const uint64_t* offsets, uint64_t n_rays, const sim_cfg* c, sim_out* o) {
-    const int K = c->policy == 1 ? 1 : (c->policy == 2 ? 1 : c->K), S = c->policy == 1 ? c->K : 32 * K;   /* policy 1: K is the pool size */
+    const int K = c->policy == 1 ? 1 : (c->policy >= 2 ? 1 : c->K), S = c->policy == 1 ? c->K : 32 * K;   /* policy 1: K is the pool size */
     warp* w = (warp*)calloc((size_t)c->n_warps, sizeof(warp));
     int* heap = (int*)malloc(sizeof(int) * (size_t)c->n_warps);
     for (int i = 0; i < c->n_warps; i++) {
@@ -108,7 +110,8 @@ int sched_sim(const uint8_t* ops, const uint64_t* offsets, uint64_t n_rays, cons
                         if (W->pos[s] != W->end[s] && ((ops[W->pos[s]] == 'N') == (want == 'N'))) { W->pos[s]++; done++; break; }
                     }
             }
-            const int cost = (tri_phase ? c->ct : c->cn) + ((c->K > 1 && c->policy == 0) || c->policy == 1 ? c->csel : 0);
+            int cost = (tri_phase ? c->ct : c->cn) + ((c->K > 1 && c->policy == 0) || c->policy == 1 ? c->csel : 0);
+            if (c->policy == 3 && !tri_phase && done <= c->K) cost = ((done + 3) / 4) * c->csel;
             W->t += cost; o->slots += cost;
             if (tri_phase) { o->tri_steps += 1; o->tri_lanes += done; } else { o->node_steps += 1; o->node_lanes += done; }
         }

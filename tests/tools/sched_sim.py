@@ -99,10 +99,11 @@ def main():
         for label, policy, K, rmin, tw in (("K=1 (round-1 kernel)", 0, 1, 4, 4), ("K=1 tw=2", 0, 1, 4, 2), ("K=1 tw=8", 0, 1, 4, 8),
                                            ("drain tw=4 (cn 300, loop 45 + 110/round)", 2, 1, 4, 4), ("drain tw=2", 2, 1, 4, 2), ("drain tw=1", 2, 1, 4, 1), ("drain tw=8", 2, 1, 4, 8), ("K=2 per lane", 0, 2, 8, 4), ("K=2 per lane tw=2", 0, 2, 8, 2), ("K=3 per lane", 0, 3, 8, 4),
                                            ("K=4 per lane", 0, 4, 8, 4),
+                                           ("narrow<=4 (pass 120)", 3, 4, 4, 4), ("narrow<=8 (pass 120)", 3, 8, 4, 4), ("narrow<=8 tw=8", 3, 8, 4, 8),
                                            ("pool 40 tw=1", 1, 40, 4, 1), ("pool 48 tw=1", 1, 48, 8, 1), ("pool 48 tw=2", 1, 48, 8, 2), ("pool 64 tw=4", 1, 64, 8, 4), ("pool 64 tw=2", 1, 64, 8, 2), ("pool 64 tw=1", 1, 64, 8, 1),
                                            ("pool 64 tw=1 rm=16", 1, 64, 16, 1), ("pool 64 tw=1 rm=4", 1, 64, 4, 1), ("pool 96 tw=1", 1, 96, 8, 1), ("pool 128 tw=1", 1, 128, 8, 1)):
             slots = K if policy == 1 else 32 * (K if policy == 0 else 1)
-            cfg = Cfg(policy, K, max(1, n_warps * 32 // slots), rmin, tw, a.cn, a.ct if policy != 2 else 110, a.cr, a.csel if policy != 2 else 45)
+            cfg = Cfg(policy, K, max(1, n_warps * 32 // slots), rmin, tw, a.cn, a.ct if policy != 2 else 110, a.cr, 120 if policy == 3 else (a.csel if policy != 2 else 45))
             out = Out()
             L.sched_sim(ops.ctypes.data, offsets.ctypes.data, n, C.byref(cfg), C.byref(out))
             spr = out.slots / n

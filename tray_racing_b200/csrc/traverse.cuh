@@ -121,6 +121,15 @@ template <int J> __device__ __forceinline__ uint32_t byte_u32(uint32_t w) {
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
+// dev instrumentation (-DTRAY_STEP_CLOCK, scripts/step_clock.py): where do the cycles of one dependent step go?
+#ifdef TRAY_STEP_CLOCK
+__device__ __forceinline__ long long clk() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)); return c; }
+__device__ __forceinline__ long long clk_after(uint32_t dep) { long long c; asm volatile("mov.u64 %0, %%clock64; // %1" : "=l"(c) : "r"(dep)); return c; }
+#define SC(...) __VA_ARGS__
+#else
+#define SC(...)
+#endif
+
 // ---- per-ray constants ---------------------------------------------------------------------------
 struct RayConst {
     float ox, oy, oz, dx, dy, dz, ix, iy, iz, tmin;
@@ -602,7 +611,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
         }
     };
 
+    SC(long long sc_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long sc_n[2] = {0, 0}; long long sc_t0 = clk();)
     for (;;) {
+        SC(const long long sc_top = clk();)
         const bool want_tri = tri_y != 0u;
         const bool want_node = !want_tri && cur_y >= 0x01000000u;
         const unsigned m_tri = __ballot_sync(FULL, want_tri), m_node = __ballot_sync(FULL, want_node);
@@ -643,6 +654,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
 
         // ---- warp vote: node step or triangle step ----
         const bool tri_phase = m_node == 0u || (unsigned)__popc(m_tri) * P.tri_weight >= (unsigned)__popc(m_node);
+        SC(const long long sc_voted = clk_after(tri_phase); sc_acc[0] += sc_voted - sc_top;)
 
         if (!tri_phase) {
             if (want_node) {
@@ -653,10 +665,13 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                 const uint32_t slot = (off - 24u) ^ (r.oct_inv4 & 0xffu);                      // :370
                 const uint32_t rel = (uint32_t)__popc(hits_imask & ~(0xffffffffu << slot));    // :371
                 const uint4* np = P.nodes + (size_t)(bvh_off + cur_x + rel) * 5u;              // :373, tlas:383
+                SC(const long long sc_a = clk_after(rel); sc_acc[1] += sc_a - sc_voted;)
                 const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                SC(const long long sc_b = clk_after(n0.x ^ n1.x ^ n2.x ^ n3.x ^ n4.x); sc_acc[2] += sc_b - sc_a;)
                 if (COUNT) c_nodes++;
                 const uint32_t hitmask = (r.wide || P.force_exact) ? node_test(r, best_t, n0, n1, n2, n3, n4, k4b)
                                                 : node_test_fast(r, best_t, n0, n1, n2, n3, n4, k4b, P.zero);   // :380
+                SC(const long long sc_c = clk_after(hitmask); sc_acc[3] += sc_c - sc_b; sc_n[0]++;)
                 cur_x = n1.x; tri_x = n1.y;                                                    // :383-384
                 cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386
                 tri_y = hitmask & 0x00ffffffu;                                                 // :387
@@ -672,6 +687,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                         prefetch_l1(q); prefetch_l1(q + 4);
                     }
                 }
+                SC(sc_acc[4] += clk_after(cur_y ^ tri_y) - sc_c;)
             }
         } else {
             if (want_tri) {
@@ -688,15 +704,27 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                     cur_x = 0; cur_y = 0x80000000u; tri_y = 0;
                 } else {
                     if (COUNT) c_tris++;
+                    SC(const long long sc_a = clk_after(g); sc_acc[5] += sc_a - sc_voted;)
+                    SC({ const uint4 q0 = __ldg(P.tris + (size_t)g * (TRI_STRIDE / 16)), q2 = __ldg(P.tris + (size_t)g * (TRI_STRIDE / 16) + 2);
+                         sc_acc[6] -= sc_a; sc_acc[6] += clk_after(q0.x ^ q2.x); })
+                    SC(const long long sc_b = clk();)
                     const float t = tri_test<TRI_STRIDE>(r, best_t, P.tris, g);
                     if (t < best_t) { best_t = t; best_prim = g; }          // CPU tie rule: first of equal t wins (§8a a11)
                     if (ANYHIT && best_prim != INVALID) { sp = 0; tri_y = 0u; cur_y = 0u; }   // drop the rest of the traversal
                     if (tri_y == 0u && cur_y < 0x01000000u) pop_or_retire();
+                    SC(sc_acc[7] += clk_after(cur_y ^ tri_y ^ __float_as_uint(best_t)) - sc_b; sc_n[1]++;)
                 }
             }
         }
     }
 
+#ifdef TRAY_STEP_CLOCK
+    if (P.spill && lane == 0) {       // per warp: cycles in [vote, node pre, node load wait, node test, node post, tri pre, tri load wait, tri test+post], steps, total
+        long long* o = (long long*)P.spill + 12 * (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5));
+        for (int i = 0; i < 8; i++) o[i] = sc_acc[i];
+        o[8] = sc_n[0]; o[9] = sc_n[1]; o[10] = clk() - sc_t0; o[11] = 1;
+    }
+#endif
 #ifdef TRAY_EXIT_LOG
     if (P.spill && lane == 0) {       // dev instrumentation (scripts/exit_log.py): when this warp exited (ns)
         unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));

@@ -174,9 +174,14 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, boo
         attr[0].val.accessPolicyWindow = s->window;
         cfg.attrs = attr; cfg.numAttrs = 1;
     }
-#ifdef TRAY_EXIT_LOG
-    static unsigned long long* d_log = nullptr;
+#if defined(TRAY_EXIT_LOG) || defined(TRAY_STEP_CLOCK)
+#ifdef TRAY_STEP_CLOCK
+#define TRAY_EXIT_LOG 1              // from here on: the host side of both dev logs is the same dump
+    const size_t log_n = 12 * grid * (threads / 32);
+#else
     const size_t log_n = 2 * grid * (threads / 32);
+#endif
+    static unsigned long long* d_log = nullptr;
     if (!pool) {
         if (!d_log) CU(cudaMalloc(&d_log, 1 << 24));
         CU(cudaMemsetAsync(d_log, 0, log_n * 8, st));
