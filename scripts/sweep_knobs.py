@@ -22,4 +22,4 @@ for combo in itertools.product(*[knobs[n] for n in names]):
         if f >= 1:
             best = ms if best is None else (min(best[0], ms[0]), min(best[1], ms[1]))
     sc.close()
-    print(scene, dict(zip(names, combo)), "primary %.3f bounce %.3f" % best, flush=True)
+    print(scene, dict(zip(names, combo)), "primary %.3f bounce %.3f  sum %.3f" % (best + (best[0] + best[1],)), flush=True)
