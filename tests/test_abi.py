@@ -28,6 +28,25 @@ def test_cuda_library_exports_every_declared_symbol():
     assert L.tray_cuda_abi_version() == 2
 
 
+def test_rust_mirror_declares_every_entry_point():
+    """tray_cuda/src/lib.rs (the crate the Rust host links) cannot be compiled in this image, so its extern
+    block is at least kept complete: every function of include/tray_cuda.h is declared there, with the same arity."""
+    header = re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "include", "tray_cuda.h")).read(), flags=re.S)
+    rust = re.sub(r"//.*", "", open(os.path.join(ROOT, "tray_cuda", "src", "lib.rs")).read())
+    ext = rust[rust.index('extern "C" {'):]
+    ext = ext[:ext.index("\n}")]
+    for n in declared_functions("tray_cuda.h"):
+        m = re.search(r"pub fn " + n + r"\s*\((.*?)\)", ext, flags=re.S)
+        assert m, f"{n} missing from tray_cuda/src/lib.rs"
+        c = re.search(r"\b" + n + r"\s*\((.*?)\)\s*;", header, flags=re.S).group(1).strip()
+        n_c = 0 if c in ("", "void") else c.count(",") + 1
+        r = m.group(1).strip()
+        n_r = 0 if r == "" else r.count(",") + 1
+        assert n_c == n_r, f"{n}: {n_c} arguments in the header, {n_r} in the Rust declaration"
+    build_rs = open(os.path.join(ROOT, "tray_cuda", "build.rs")).read()
+    assert "tray_cuda.cu" in build_rs and "build_gpu.cu" in build_rs and "sm_100a" in build_rs
+
+
 def test_host_library_exports_every_declared_symbol():
     L = host.lib()
     for n in declared_functions("tray_host.h"):

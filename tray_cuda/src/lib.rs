@@ -34,7 +34,51 @@ pub struct TrayBuildStats {
     pub ms_upload: f32, pub ms_sort: f32, pub ms_ploc: f32, pub ms_collapse: f32, pub ms_total: f32,
 }
 
+/// `tray_counters` of include/tray_cuda.h (the algorithmic bytes per ray come from these)
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct TrayCounters { pub rays: u64, pub nodes: u64, pub tris: u64, pub instances: u64, pub hits: u64 }
+
+/// `tray_scene_info` of include/tray_cuda.h
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct TraySceneInfo {
+    pub n_nodes: u64, pub n_tris: u64, pub tri_stride: u32, pub n_instances: u32, pub tlas_start: u32, pub is_tlas: u32,
+    pub device: i32, pub sm_count: u32, pub device_bytes: u64, pub l2_bytes: u64, pub l2_persist_bytes: u64,
+}
+
+pub const RENDER_BOUNCE: u32 = 0x1;
+pub const RENDER_RGBA: u32 = 0x2;
+pub const RENDER_COUNTERS: u32 = 0x4;
+pub const RENDER_KEEP_RAYS: u32 = 0x8;
+pub const RENDER_ANYHIT_AO: u32 = 0x10;
+
 extern "C" {
+    pub fn tray_cuda_abi_version() -> u32;
+    pub fn tray_cuda_scene_info(scene: *const TrayScene, out_info: *mut TraySceneInfo) -> c_int;
+    pub fn tray_cuda_scene_build_tlas(tris9: *const f32, n_tris: u64, object_offsets: *const u64, n_objects: u32, tri_stride: u32,
+        max_prims_per_leaf: u32, search_radius: u32, device: c_int, out: *mut *mut TrayScene, stats: *mut TrayBuildStats) -> c_int;
+    pub fn tray_cuda_scene_download_instances(scene: *mut TrayScene, blas_offsets: *mut u32) -> c_int;
+    pub fn tray_cuda_trace_device(scene: *mut TrayScene, d_rays: *const TrayRay, n: u64, d_hits: *mut TrayHit,
+        stream: *mut c_void, ms_kernel: *mut f32) -> c_int;
+    pub fn tray_cuda_trace_any_device(scene: *mut TrayScene, d_rays: *const TrayRay, n: u64, d_hits: *mut TrayHit,
+        stream: *mut c_void, ms_kernel: *mut f32) -> c_int;
+    pub fn tray_cuda_shard_pixels(width: u32, height: u32, shard_index: u32, shard_count: u32) -> u64;
+    pub fn tray_cuda_frame_device_ptrs(scene: *mut TrayScene, d_primary: *mut *mut c_void, d_bounce: *mut *mut c_void,
+        d_rgba: *mut *mut c_void) -> c_int;
+    pub fn tray_cuda_untile_rgba(scene: *mut TrayScene, d_compact: *const c_void, width: u32, height: u32, shard_index: u32,
+        shard_count: u32, d_frame: *mut c_void) -> c_int;
+    pub fn tray_cuda_frame_alloc(device: c_int, bytes: u64, d_ptr: *mut *mut c_void) -> c_int;
+    pub fn tray_cuda_frame_free(device: c_int, d_ptr: *mut c_void) -> c_int;
+    pub fn tray_cuda_ipc_export(device: c_int, d_ptr: *mut c_void, handle: *mut u8) -> c_int;         // handle: [u8; 64]
+    pub fn tray_cuda_ipc_open(device: c_int, handle: *const u8, d_ptr: *mut *mut c_void) -> c_int;
+    pub fn tray_cuda_ipc_close(device: c_int, d_ptr: *mut c_void) -> c_int;
+    pub fn tray_cuda_scene_set_frame_target(scene: *mut TrayScene, d_frame: *mut c_void) -> c_int;
+    pub fn tray_cuda_scene_set_stream(scene: *mut TrayScene, stream: *mut c_void) -> c_int;
+    pub fn tray_cuda_sync(scene: *mut TrayScene) -> c_int;
+    pub fn tray_cuda_counters(scene: *mut TrayScene, primary: *mut TrayCounters, bounce: *mut TrayCounters) -> c_int;
+    pub fn tray_cuda_set_counting(scene: *mut TrayScene, enabled: c_int) -> c_int;
+    pub fn tray_cuda_bandwidth_probe(device: c_int, bytes: u64, iters: c_int, out_gbs: *mut f32) -> c_int;
     pub fn tray_cuda_device_count() -> c_int;
     pub fn tray_cuda_last_error() -> *const c_char;
     pub fn tray_cuda_scene_create(nodes: *const c_void, n_nodes: u64, tris: *const c_void, n_tris: u64, tri_stride: u32,
@@ -84,4 +128,79 @@ pub fn start(a: StartArgs) -> f32 {
             &mut min_ms, &mut mean_ms, &mut frames)
     });
     min_ms
+}
+
+/// Owning handle of a device-resident scene: the batch-grain face of `Traversable` (traversable/src/lib.rs:13-28).
+/// Like the reference, every error panics.
+pub struct Scene { raw: *mut TrayScene }
+
+impl Scene {
+    /// Upload the buffers `cwbvh_gpu_runner` builds (src/rt_gpu/mod.rs:16-112); `blas_offsets` empty = single-level.
+    pub fn new(bvh_bytes: &[u8], tri_bytes: &[u8], tri_stride: u32, blas_offsets: &[u32], tlas_start: u32, device: i32) -> Scene {
+        let mut raw = std::ptr::null_mut();
+        check(unsafe {
+            tray_cuda_scene_create(bvh_bytes.as_ptr().cast(), (bvh_bytes.len() / 80) as u64, tri_bytes.as_ptr().cast(),
+                (tri_bytes.len() / tri_stride as usize) as u64, tri_stride,
+                if blas_offsets.is_empty() { std::ptr::null() } else { blas_offsets.as_ptr() }, blas_offsets.len() as u32,
+                tlas_start, device, &mut raw)
+        });
+        Scene { raw }
+    }
+
+    /// Build the CWBVH on the device from a triangle soup (9 floats per triangle), the step `cwbvh_from_tris` does on the CPU.
+    pub fn build(tris9: &[f32], max_prims_per_leaf: u32, search_radius: u32, device: i32) -> (Scene, TrayBuildStats) {
+        let (mut raw, mut stats) = (std::ptr::null_mut(), TrayBuildStats::default());
+        check(unsafe { tray_cuda_scene_build(tris9.as_ptr(), (tris9.len() / 9) as u64, 48, max_prims_per_leaf, search_radius, device, &mut raw, &mut stats) });
+        (Scene { raw }, stats)
+    }
+
+    /// One BLAS per object (`object_offsets[k]..object_offsets[k + 1]` are object k's triangles) plus a TLAS: `--tlas`.
+    pub fn build_tlas(tris9: &[f32], object_offsets: &[u64], max_prims_per_leaf: u32, search_radius: u32, device: i32) -> (Scene, TrayBuildStats) {
+        let (mut raw, mut stats) = (std::ptr::null_mut(), TrayBuildStats::default());
+        check(unsafe {
+            tray_cuda_scene_build_tlas(tris9.as_ptr(), (tris9.len() / 9) as u64, object_offsets.as_ptr(), (object_offsets.len() - 1) as u32,
+                48, max_prims_per_leaf, search_radius, device, &mut raw, &mut stats)
+        });
+        (Scene { raw }, stats)
+    }
+
+    pub fn info(&self) -> TraySceneInfo {
+        let mut i = TraySceneInfo::default();
+        check(unsafe { tray_cuda_scene_info(self.raw, &mut i) });
+        i
+    }
+
+    /// Closest hit per ray (`Traversable::traverse` for a batch); `any_hit` stops each ray at its first accepted triangle.
+    pub fn traverse(&mut self, rays: &[TrayRay], any_hit: bool) -> Vec<TrayHit> {
+        let mut hits = vec![TrayHit { t: f32::INFINITY, prim: u32::MAX }; rays.len()];
+        let f = if any_hit { tray_cuda_trace_any } else { tray_cuda_trace };
+        check(unsafe { f(self.raw, rays.as_ptr(), rays.len() as u64, hits.as_mut_ptr(), std::ptr::null_mut(), std::ptr::null_mut()) });
+        hits
+    }
+
+    /// One frame (primary + bounce rays) of shard `shard` of `shards`; returns (ms primary, ms bounce) of the kernels.
+    pub fn render(&mut self, view: &TrayView, width: u32, height: u32, frame_count: u32, flags: u32, shard: u32, shards: u32) -> (f32, f32) {
+        let (mut a, mut b) = (0f32, 0f32);
+        check(unsafe { tray_cuda_render(self.raw, view, width, height, frame_count, flags, shard, shards, &mut a, &mut b) });
+        (a, b)
+    }
+
+    /// RGBA8 of the last frame, row-major (the reference's PNG input, rt_cpu.rs:102-112).
+    pub fn download_rgba(&mut self, width: u32, height: u32) -> Vec<u8> {
+        let mut px = vec![0u8; width as usize * height as usize * 4];
+        check(unsafe { tray_cuda_frame_download(self.raw, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut(), px.as_mut_ptr()) });
+        px
+    }
+
+    pub fn counters(&mut self) -> (TrayCounters, TrayCounters) {
+        let (mut p, mut b) = (TrayCounters::default(), TrayCounters::default());
+        check(unsafe { tray_cuda_counters(self.raw, &mut p, &mut b) });
+        (p, b)
+    }
+
+    pub fn as_raw(&self) -> *mut TrayScene { self.raw }
+}
+
+impl Drop for Scene {
+    fn drop(&mut self) { unsafe { tray_cuda_scene_destroy(self.raw) } }
 }
