@@ -29,10 +29,20 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SCENE, SEED = "hairball", 3
-BASE_W, BASE_H = 1920, 1080
 METRIC, UNIT = "Mrays/s primary+diffuse", "Mrays/s"
 TRI_STRIDE = 48
+# BASELINE.json configs that are bench lines.  c3 (configs[2], the one the metric's 1-GPU target is quoted on) is the default
+# and the only one the driver runs; c4 / c5 (configs[3], configs[4]) are the multi-GPU configs: a FIXED 3840x2160 frame
+# tile-sharded over the ranks (strong scaling), c5 through the two-level (--tlas) traversal.
+WORKLOADS = {
+    "c3": dict(scene="hairball", seed=3, w=1920, h=1080, tlas=False, scaling="weak",
+               label="C3 hairball-like 2.88M-tri soup"),
+    "c4": dict(scene="sanmiguel", seed=4, w=3840, h=2160, tlas=False, scaling="strong",
+               label="C4 San-Miguel-sized 5.08M-tri scene"),
+    "c5": dict(scene="caldera", seed=5, w=3840, h=2160, tlas=True, scaling="strong",
+               label="C5 Caldera-sized 19.26M-tri scene, 4096 BLAS + TLAS (--tlas)"),
+}
+WL = WORKLOADS["c3"]
 
 
 _RESULT_FD = None
@@ -57,12 +67,15 @@ def emit(line: dict):
 
 
 def frame_size(n_gpus: int):
+    if WL["scaling"] == "strong":
+        return WL["w"], WL["h"]
     s = n_gpus ** 0.5
-    return int(round(BASE_W * s / 8)) * 8, int(round(BASE_H * s / 8)) * 8
+    return int(round(WL["w"] * s / 8)) * 8, int(round(WL["h"] * s / 8)) * 8
 
 
 def workload_name(w, h, n):
-    return f"C3 hairball-like 2.88M-tri soup, {w}x{h} ({n} x 1920x1080 px), primary + 1spp diffuse bounce, ploc-style CWBVH"
+    px = f"{n} x {WL['w']}x{WL['h']} px" if WL["scaling"] == "weak" else f"fixed frame, 1/{n} of the tiles per GPU"
+    return f"{WL['label']}, {w}x{h} ({px}), primary + 1spp diffuse bounce, ploc-style CWBVH"
 
 
 class ClockSampler:
@@ -121,8 +134,8 @@ def ncu_traffic():
 
 def build_scene(nthreads=0):
     from tray_racing_b200 import host
-    mesh = host.Mesh.generate(SCENE, SEED, 1.0)
-    packed = host.PackedScene(mesh, use_tlas=False, tri_stride=TRI_STRIDE, nthreads=nthreads)
+    mesh = host.Mesh.generate(WL["scene"], WL["seed"], 1.0)
+    packed = host.PackedScene(mesh, use_tlas=WL["tlas"], tri_stride=TRI_STRIDE, nthreads=nthreads)
     return mesh, packed
 
 
@@ -134,7 +147,7 @@ def cpu_oracle_run(packed, mesh, seconds_budget: float, frames_min: int, w=960, 
     import oracle_binding as ob
     from tray_racing_b200 import host
     orc = ob.Oracle.from_packed(packed)
-    view = host.view_from_camera(mesh.camera, w, h)
+    view = host.view_from_camera(mesh.camera, w, h, packed.tlas_start)
     threads = ob.lib().orc_max_threads()
     orc.render(view, w, h, 0)                      # warm-up frame (page in the BVH)
     times, rays = [], 0
@@ -149,7 +162,7 @@ def cpu_oracle_run(packed, mesh, seconds_budget: float, frames_min: int, w=960, 
     mean = sum(times) / len(times)
     return {"value": rays / mean / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
             "simd": "AVX2 node test (8 children per vector), scalar triangle test" if ob.simd() else "scalar",
-            "sample": f"{len(times)} frames of the same scene+camera at {w}x{h} ({rays} rays/frame, primary+bounce), mean frame time",
+            "sample": f"{len(times)} frames of the same scene+camera at {w}x{h} (decimated {WL['w']}x{WL['h']}; {rays} rays/frame, primary+bounce), mean frame time",
             "ms_per_frame": mean * 1e3, "rays_per_frame": rays}, times
 
 
@@ -166,7 +179,7 @@ def run_reference(args):
     import oracle_binding as ob
     from tray_racing_b200 import host
     orc = ob.Oracle.from_packed(packed)
-    view = host.view_from_camera(mesh.camera, sw, sh)
+    view = host.view_from_camera(mesh.camera, sw, sh, packed.tlas_start)
     threads = ob.lib().orc_max_threads()
     for _ in range(args.warmup):
         orc.render(view, sw, sh, 0)
@@ -177,9 +190,9 @@ def run_reference(args):
         rays += r["primary_totals"]["rays"] + r["bounce_totals"]["rays"]
     dt = time.perf_counter() - t0
     val = rays / dt / 1e6
-    sample = f"each step = one {sw}x{sh} frame (2x2-decimated 1080p) of the same scene+camera, primary+bounce"
+    sample = f"each step = one {sw}x{sh} frame (decimated {WL['w']}x{WL['h']}) of the same scene+camera, primary+bounce"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": WL["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(w, h, args.gpus), "sample": sample, "n_tris": packed.n_tris, "n_nodes": packed.n_nodes},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -212,7 +225,7 @@ def run_ours(args):
     ncpu = os.cpu_count() or 8
     mesh, packed = build_scene(nthreads=max(1, ncpu // world))
     w, h = frame_size(world)
-    view = host.view_from_camera(mesh.camera, w, h)
+    view = host.view_from_camera(mesh.camera, w, h, packed.tlas_start)
     scene = cuda.TrayCudaScene.from_packed(packed, device=local_rank)
     # one explicit (non-default) torch stream carries the kernels, the NCCL gather, the untile and the timing events
     stream = torch.cuda.Stream()
@@ -343,8 +356,8 @@ def run_ours(args):
         a, b = scene.render(view, w, h, 0, flags, rank, world, timed=True)
         kp.append(a); kb.append(b)
     kp_ms, kb_ms = sum(kp) / len(kp), sum(kb) / len(kb)
-    bytes_p = 80 * cp["nodes"] + TRI_STRIDE * cp["tris"] + 8 * cp["rays"]
-    bytes_b = 80 * cb["nodes"] + TRI_STRIDE * cb["tris"] + 8 * cb["rays"] + 8 * cp["rays"]
+    bytes_p = 80 * cp["nodes"] + TRI_STRIDE * cp["tris"] + 4 * cp["instances"] + 8 * cp["rays"]
+    bytes_b = 80 * cb["nodes"] + TRI_STRIDE * cb["tris"] + 4 * cb["instances"] + 8 * cb["rays"] + 8 * cp["rays"]
     peak, peak_src = measured_peaks()
     l2_peak = cuda.bandwidth_probe(48 << 20, 50, local_rank)          # streaming read of an L2-resident 48 MiB buffer
     hbm_read = cuda.bandwidth_probe(2048 << 20, 8, local_rank)        # same kernel, buffer >> L2
@@ -414,7 +427,7 @@ def run_ours(args):
 
     # ---- beside the headline (N = 1 only, outside every timed region above): the rows SURVEY.md §8 marks "next" ----
     extras = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and args.workload == "c3":
         extras = {}
         # f4: AO rays as an any-hit query (rt_cpu.rs:78-79) — same rays, each stopped at its first hit
         ka = [scene.render(view, w, h, 0, flags | cuda.RENDER_ANYHIT_AO, rank, world, timed=True) for _ in range(6)][1:]
@@ -439,7 +452,7 @@ def run_ours(args):
         cpu_base, _ = cpu_oracle_run(packed, mesh, seconds_budget=10.0, frames_min=3) if world == 1 else (None, None)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": WL["scaling"], "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(w, h, world), "n_tris": packed.n_tris, "n_nodes": packed.n_nodes,
                        "working_set_mb": round(packed.working_set_bytes() / 1e6, 1), "tri_stride": TRI_STRIDE,
@@ -496,9 +509,13 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
+                    help="c3 (default, the metric's config; weak scaling) | c4 | c5 (fixed 3840x2160 frame sharded over the GPUs)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="how shards reach rank 0's frame: peer-mapped frame written by the kernels, or NCCL gather + untile")
     args = ap.parse_args()
+    global WL
+    WL = WORKLOADS[args.workload]
     claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
