@@ -1,9 +1,9 @@
 """Dev: cycle breakdown of the traversal loop, from the instrumented build (`make -C tray_racing_b200/csrc stepclock`).
-Run on a GPU:  TRAY_CUDA_LIB=$PWD/tray_racing_b200/libtray_cuda_stepclock.so python scripts/step_clock.py [scene]
+Run on a GPU:  TRAY_CUDA_LIB=$PWD/tray_racing_b200/libtray_cuda_stepclock.so python tests/tools/step_clock.py [scene]
 Cases: the 32 / 4736 longest primary rays one per warp (the drain phase in isolation) and the whole 1080p primary batch."""
 import glob, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 os.environ.setdefault("TRAY_EXIT_LOG_FILE", "/tmp/stepclock")
 import oracle_binding as ob

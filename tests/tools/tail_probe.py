@@ -1,13 +1,13 @@
 """Dev: what does one DEPENDENT traversal step cost when a warp holds a single long ray (the drain phase of a launch)?
 
-Takes the longest primary rays of a scene (step counts from the CPU oracle — analysis only), and times launches of
+Test infrastructure (it uses the CPU oracle for the step counts): takes the longest primary rays of a scene, and times launches of
   (a) the L longest rays packed 32 to a warp,
   (b) the same rays one per warp: every aligned group of 32 rays is 1 long ray + 31 rays that miss the root (tmax = 0),
 for each setting of the knobs given on the command line, e.g.
-  python scripts/tail_probe.py hairball '{"TRAY_CUDA_NARROW_MAX": [0, 4], "TRAY_CUDA_LOOKAHEAD": [0, 1, 3]}'"""
+  python tests/tools/tail_probe.py hairball '{"TRAY_CUDA_NARROW_MAX": [0, 4], "TRAY_CUDA_LOOKAHEAD": [0, 1, 3]}'"""
 import itertools, os, sys
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_binding as ob
 from tray_racing_b200 import cuda, host

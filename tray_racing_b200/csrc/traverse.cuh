@@ -121,7 +121,7 @@ template <int J> __device__ __forceinline__ uint32_t byte_u32(uint32_t w) {
 #endif
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" :: "l"(p)); }
 
-// dev instrumentation (-DTRAY_STEP_CLOCK, scripts/step_clock.py): where do the cycles of one dependent step go?
+// dev instrumentation (-DTRAY_STEP_CLOCK, tests/tools/step_clock.py): where do the cycles of one dependent step go?
 #ifdef TRAY_STEP_CLOCK
 __device__ __forceinline__ long long clk() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)); return c; }
 __device__ __forceinline__ long long clk_after(uint32_t dep) { long long c; asm volatile("mov.u64 %0, %%clock64; // %1" : "=l"(c) : "r"(dep)); return c; }
