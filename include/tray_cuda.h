@@ -206,8 +206,12 @@ int tray_cuda_scene_info(const tray_scene* scene, tray_scene_info* out_info);
 /* ---- ray-batch operator: Traversable::traverse at batch grain (traversable/src/lib.rs:20) ----- */
 
 /* Closest hit for `n` rays.  HOST buffers: the copy H2D of rays and D2H of hits are inside the
- * call (and inside *ms_total); *ms_kernel is the CUDA-event time of the traversal kernel alone.
- * Either timing pointer may be NULL.                                                             */
+ * call (and inside *ms_total).  Batches of >= 2^18 rays run as a pipeline over chunks of 2^20 rays —
+ * host threads stage the caller's rays into pinned slots, a copy stream uploads chunk i+1 while the
+ * traversal kernel runs on chunk i and chunk i-1 is read back — so the caller's (pageable) memory is
+ * only borrowed, never registered.  *ms_kernel is the CUDA-event time of the traversal kernel alone
+ * for small batches, and the span of the GPU work (uploads it waited for included) for pipelined
+ * ones.  Either timing pointer may be NULL.                                                       */
 int tray_cuda_trace(tray_scene* scene, const tray_ray* rays, uint64_t n, tray_hit* hits,
                     float* ms_kernel, float* ms_total);
 

@@ -96,6 +96,29 @@ def test_traverse_random_rays(cornell):
         sc.close()
 
 
+@pytest.mark.parametrize("any_hit", [False, True])
+def test_large_host_batches_take_the_copy_pipeline(cornell, any_hit):
+    """Batches of >= 2^18 rays go through the chunked upload / trace / read-back pipeline of tray_cuda_trace (pinned staging
+    slots, three streams): ragged last chunk, exactly one chunk, several chunks; hits and counters as the oracle's."""
+    p = host.PackedScene(cornell)
+    orc = ob.Oracle.from_packed(p)
+    sc = cuda.TrayCudaScene.from_packed(p)
+    try:
+        for n, seed in [((1 << 18), 7), ((1 << 20), 8), (3 * (1 << 20) + 12345, 9)]:
+            rays = random_rays(n, seed, axis_fraction=0.05, bounded_fraction=0.2)
+            assert_hits_identical(sc.traverse(rays, any_hit=any_hit), orc.trace(rays, any_hit=any_hit), f"n={n}")
+        if not any_hit:
+            sc.set_counting(True)
+            rays = random_rays(2 * (1 << 20) + 77, 10)
+            got = sc.traverse(rays)
+            ref, _, tot = orc.trace(rays, counts=True)
+            assert_hits_identical(got, ref)
+            cp, _ = sc.counters()
+            assert cp["rays"] == len(rays) and cp["nodes"] == tot["nodes"] and cp["tris"] == tot["tris"]
+    finally:
+        sc.close()
+
+
 def test_tiny_direction_components_take_the_unfused_node_test(cornell, monkeypatch):
     """The fused node test (fma(2^23 + q, A, -2^23 A) == fl(q A)) needs 2^23 * A finite.  Rays with |1/d| >= 2^64 on an
     axis, and scenes with node scales >= 2^40, fall back to the unfused test; both paths must match the oracle, and

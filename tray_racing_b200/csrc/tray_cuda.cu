@@ -7,7 +7,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "build_gpu.h"
@@ -71,6 +74,10 @@ struct tray_scene {
     int blocks_per_sm[2] = { 0, 0 };         // resident CTAs per SM of the lane kernel [0] and the pooled kernel [1]
     // ray-batch staging
     tray_ray* d_rays = nullptr; tray_hit* d_hits = nullptr; uint64_t batch_cap = 0;
+    // host <-> device pipeline of tray_cuda_trace: two pinned staging slots per direction, copy streams, events
+    tray_ray* h_rays[2] = { nullptr, nullptr }; tray_hit* h_hits[2] = { nullptr, nullptr };
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t e_in[2] = { nullptr, nullptr }, e_k[2] = { nullptr, nullptr }, e_out[2] = { nullptr, nullptr };
     // frame state (compact local order)
     uint32_t fw = 0, fh = 0, fshard = 0, fshards = 1;
     uint64_t f_items = 0, f_cap = 0;
@@ -133,7 +140,7 @@ void base_params(const tray_scene* s, TraceParams& P) {
 }
 
 // one launch: reset the cursor, run the persistent grid (sized to the chip, or to the work if that is smaller)
-int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, bool anyhit = false) {
+int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, bool anyhit = false, bool keep_counters = false) {
     const bool pool = s->pool && !anyhit && s->tri_stride != 24;      // the pooled kernel covers closest hit on f32 records
     kernel_fn k = pool ? pick_pool_kernel(s->tlas, s->counting, s->tri_stride) : pick_kernel(s->tlas, s->counting, s->tri_stride, anyhit);
     const int threads = pool ? POOL_WARPS * 32 : BLOCK_THREADS;
@@ -148,7 +155,7 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, boo
     }
     P.counters = s->d_cursor + 1 + 5 * counter_slot;
     CU(cudaMemsetAsync(s->d_cursor, 0, sizeof(unsigned long long), st));
-    if (s->counting) CU(cudaMemsetAsync(P.counters, 0, 5 * sizeof(unsigned long long), st));
+    if (s->counting && !keep_counters) CU(cudaMemsetAsync(P.counters, 0, 5 * sizeof(unsigned long long), st));
     const uint64_t blocks_needed = ((uint64_t)P.n_work + rays_per_block - 1) / rays_per_block;
     uint64_t grid = (uint64_t)s->sm_count * bps;
     if (blocks_needed < grid) grid = blocks_needed;
@@ -284,6 +291,15 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_blas); cudaFree(s->d_prim_indices); cudaFree(s->d_cursor); cudaFree(s->d_overflow);
     cudaFree(s->d_rays); cudaFree(s->d_hits); cudaFree(s->d_spill);
+    for (int i = 0; i < 2; i++) {
+        if (s->h_rays[i]) cudaFreeHost(s->h_rays[i]);
+        if (s->h_hits[i]) cudaFreeHost(s->h_hits[i]);
+        if (s->e_in[i]) cudaEventDestroy(s->e_in[i]);
+        if (s->e_k[i]) cudaEventDestroy(s->e_k[i]);
+        if (s->e_out[i]) cudaEventDestroy(s->e_out[i]);
+    }
+    if (s->s_in) cudaStreamDestroy(s->s_in);
+    if (s->s_out) cudaStreamDestroy(s->s_out);
     cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba); cudaFree(s->d_untiled);
     cudaFree(s->d_prays); cudaFree(s->d_bitem); cudaFree(s->d_brays_item);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
@@ -574,6 +590,80 @@ int trace_device_impl(tray_scene* s, const tray_ray* d_rays, uint64_t n, tray_hi
     return TRAY_OK;
 }
 
+// Host-side copy spread over a few persistent worker threads: one thread moves ~10 GB/s, the PCIe link of a B200 takes ~50.
+class CopyPool {
+public:
+    static CopyPool& get() { static CopyPool p; return p; }
+    void copy(void* dst, const void* src, size_t bytes) {
+        const size_t nt = bytes < (2u << 20) ? 1 : workers_.size() + 1;
+        if (nt <= 1) { memcpy(dst, src, bytes); return; }
+        std::lock_guard<std::mutex> call(call_mu_);                  // one copy at a time (scenes on several host threads)
+        const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; per_ = per;
+            pending_ = (int)workers_.size(); generation_++;
+        }
+        cv_.notify_all();
+        memcpy(dst, src, per < bytes ? per : bytes);                 // part 0 on the calling thread
+        std::unique_lock<std::mutex> g(mu_);
+        done_cv_.wait(g, [&] { return pending_ == 0; });
+    }
+private:
+    CopyPool() {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const unsigned n = hw >= 16 ? 7 : hw >= 4 ? hw / 2 - 1 : 0;
+        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this, i] { run(i + 1); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : workers_) t.join();
+    }
+    void run(size_t part) {
+        unsigned long long seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> g(mu_);
+            cv_.wait(g, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            char* d = dst_; const char* s = src_; const size_t bytes = bytes_, per = per_;
+            g.unlock();
+            const size_t a = part * per;
+            if (a < bytes) memcpy(d + a, s + a, a + per <= bytes ? per : bytes - a);
+            g.lock();
+            if (--pending_ == 0) done_cv_.notify_one();
+        }
+    }
+    std::vector<std::thread> workers_;
+    std::mutex mu_, call_mu_;
+    std::condition_variable cv_, done_cv_;
+    char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0, per_ = 0;
+    int pending_ = 0; unsigned long long generation_ = 0; bool stop_ = false;
+};
+void par_copy(void* dst, const void* src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
+
+constexpr uint64_t PIPE_CHUNK = 1ull << 20;       // rays per pipeline stage (32 MiB in, 8 MiB out)
+constexpr uint64_t PIPE_MIN = 1ull << 18;         // smaller batches take the plain copy-launch-copy path
+
+int ensure_pipeline(tray_scene* s) {
+    if (s->s_in) return TRAY_OK;
+    CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaMallocHost(&s->h_rays[i], PIPE_CHUNK * sizeof(tray_ray)));
+        CU(cudaMallocHost(&s->h_hits[i], PIPE_CHUNK * sizeof(tray_hit)));
+        CU(cudaEventCreateWithFlags(&s->e_in[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->e_k[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&s->e_out[i], cudaEventDisableTiming));
+    }
+    return TRAY_OK;
+}
+
+// Batch operator with HOST buffers (Traversable::traverse for a slice of rays).  Large batches run as a three-stage pipeline
+// over chunks of PIPE_CHUNK rays: [host threads: caller's rays -> pinned slot] [copy stream: H2D] [scene stream: traversal]
+// [copy stream: D2H into a pinned slot] [host threads: -> caller's hits]; chunk i+1 is staged and uploaded while chunk i is
+// traced and chunk i-1 is read back.  The caller's memory is only borrowed for the call and never registered.
 int trace_impl(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, float* ms_kernel, float* ms_total, bool anyhit) {
     if (!s || (n && (!rays || !hits))) return fail(TRAY_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(s->device));
@@ -584,12 +674,52 @@ int trace_impl(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, 
         CU(cudaMalloc(&s->d_hits, n * sizeof(tray_hit)));
         s->batch_cap = n;
     }
-    if (n) CU(cudaMemcpyAsync(s->d_rays, rays, n * sizeof(tray_ray), cudaMemcpyHostToDevice, s->stream));
     float k = 0.f;
-    int rc = trace_device_impl(s, s->d_rays, n, s->d_hits, s->stream, &k, anyhit);
-    if (rc) return rc;
-    if (n) CU(cudaMemcpyAsync(hits, s->d_hits, n * sizeof(tray_hit), cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    int rc = TRAY_OK;
+    if (n < PIPE_MIN) {
+        if (n) CU(cudaMemcpyAsync(s->d_rays, rays, n * sizeof(tray_ray), cudaMemcpyHostToDevice, s->stream));
+        rc = trace_device_impl(s, s->d_rays, n, s->d_hits, s->stream, &k, anyhit);
+        if (rc) return rc;
+        if (n) CU(cudaMemcpyAsync(hits, s->d_hits, n * sizeof(tray_hit), cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+    } else {
+        rc = ensure_pipeline(s);
+        if (rc) return rc;
+        const uint64_t n_chunks = (n + PIPE_CHUNK - 1) / PIPE_CHUNK;
+        auto chunk_len = [&](uint64_t i) { return i + 1 < n_chunks ? PIPE_CHUNK : n - i * PIPE_CHUNK; };
+        if (s->counting) CU(cudaMemsetAsync(s->d_cursor + 1, 0, 5 * sizeof(unsigned long long), s->stream));
+        CU(cudaEventRecord(s->ev[0], s->stream));
+        for (uint64_t i = 0; i < n_chunks + 2; i++) {
+            const int slot = (int)(i & 1);
+            if (i < n_chunks) {
+                const uint64_t off = i * PIPE_CHUNK, len = chunk_len(i);
+                if (i >= 2) CU(cudaEventSynchronize(s->e_in[slot]));                 // the slot's previous upload has left it
+                par_copy(s->h_rays[slot], rays + off, len * sizeof(tray_ray));
+                CU(cudaMemcpyAsync(s->d_rays + off, s->h_rays[slot], len * sizeof(tray_ray), cudaMemcpyHostToDevice, s->s_in));
+                CU(cudaEventRecord(s->e_in[slot], s->s_in));
+                CU(cudaStreamWaitEvent(s->stream, s->e_in[slot], 0));
+                TraceParams P; base_params(s, P);
+                P.rays = s->d_rays + off; P.n_work = (uint32_t)len; P.hits_out = s->d_hits + off;
+                rc = launch(s, P, s->stream, 0, anyhit, /*keep_counters=*/true);
+                if (rc) return rc;
+                CU(cudaEventRecord(s->e_k[slot], s->stream));
+            }
+            if (i >= 1 && i - 1 < n_chunks) {                                           // chunk i-1: start its read-back
+                const uint64_t j = i - 1; const int ps = (int)(j & 1);
+                CU(cudaStreamWaitEvent(s->s_out, s->e_k[ps], 0));
+                CU(cudaMemcpyAsync(s->h_hits[ps], s->d_hits + j * PIPE_CHUNK, chunk_len(j) * sizeof(tray_hit), cudaMemcpyDeviceToHost, s->s_out));
+                CU(cudaEventRecord(s->e_out[ps], s->s_out));
+            }
+            if (i >= 2) {                                                               // chunk i-2: hand its hits to the caller
+                const uint64_t j = i - 2; const int ps = (int)(j & 1);
+                CU(cudaEventSynchronize(s->e_out[ps]));
+                par_copy(hits + j * PIPE_CHUNK, s->h_hits[ps], chunk_len(j) * sizeof(tray_hit));
+            }
+        }
+        CU(cudaEventRecord(s->ev[1], s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaEventElapsedTime(&k, s->ev[0], s->ev[1]));       // span of the GPU work, uploads it waited for included
+    }
     if (s->counting) { rc = read_counters(s, 0, &s->cnt_primary); if (rc) return rc; memset(&s->cnt_bounce, 0, sizeof s->cnt_bounce); }
     rc = check_overflow(s);
     if (rc) return rc;
