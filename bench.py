@@ -436,12 +436,19 @@ def run_ours(args):
                                "closest_hit_bounce_kernel_ms": kb_ms, "note": "TRAY_RENDER_ANYHIT_AO: visibility only, not the reference image"}
         # f3: the same triangles built into a CWBVH on the device (PLOC) instead of by the host producer
         tris = mesh.tris()
-        cuda.TrayCudaScene.build(tris[:4096], device=local_rank).close()              # module / allocator warm-up
-        t0 = time.perf_counter()
-        g = cuda.TrayCudaScene.build(tris, tri_stride=TRI_STRIDE, device=local_rank)
-        wall = (time.perf_counter() - t0) * 1e3
+        cuda.TrayCudaScene.build(tris, tri_stride=TRI_STRIDE, device=local_rank).close()      # warm-up: modules, pinned upload slots, allocator
+        g, wall = None, None
+        for _ in range(3):                                                                    # best of 3 (host wall clock around the call)
+            if g is not None:
+                g.close()
+            t0 = time.perf_counter()
+            g2 = cuda.TrayCudaScene.build(tris, tri_stride=TRI_STRIDE, device=local_rank)
+            w2 = (time.perf_counter() - t0) * 1e3
+            if wall is None or w2 < wall:
+                wall, stats_best = w2, dict(g2.build_stats)
+            g = g2
         kg = [g.render(view, w, h, 0, flags) for _ in range(6)][1:]
-        extras["device_builder"] = {"wall_ms": wall, **{k: v for k, v in g.build_stats.items()},
+        extras["device_builder"] = {"wall_ms": wall, **stats_best, "protocol": "one untimed warm-up build, then the best of 3",
                                     "host_producer_ms": packed.build_seconds * 1e3,
                                     "primary_kernel_ms_on_device_built_bvh": min(a for a, _ in kg),
                                     "bounce_kernel_ms_on_device_built_bvh": min(b for _, b in kg),

@@ -28,6 +28,7 @@
 #include <cstring>
 
 #include "build_gpu.h"
+#include "host_copy.h"
 
 namespace tray_build {
 
@@ -526,7 +527,7 @@ int build_tlas(const float* tris9_host, uint64_t n_tris, const uint64_t* object_
     float* d_tris9; float4 *plo, *phi; uint32_t* prim_seg = nullptr; uint64_t* d_off = nullptr;
     BCU(sc.alloc(&d_tris9, (size_t)n * 36));
     BCU(sc.alloc(&plo, (size_t)n * 16)); BCU(sc.alloc(&phi, (size_t)n * 16));
-    BCU(cudaMemcpyAsync(d_tris9, tris9_host, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+    BCU(tray::upload_pipelined(d_tris9, tris9_host, (size_t)n * 36, st));
     if (tlas) {
         BCU(sc.alloc(&prim_seg, (size_t)n * 4)); BCU(sc.alloc(&d_off, (size_t)(n_objects + 1) * 8));
         BCU(cudaMemcpyAsync(d_off, object_offsets, (size_t)(n_objects + 1) * 8, cudaMemcpyHostToDevice, st));

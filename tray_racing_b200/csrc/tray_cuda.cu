@@ -7,13 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <condition_variable>
-#include <mutex>
 #include <new>
-#include <thread>
 #include <vector>
 
 #include "build_gpu.h"
+#include "host_copy.h"
 #include "traverse.cuh"
 #include "traverse_pool.cuh"
 
@@ -377,9 +375,9 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         CU(cudaMemsetAsync(s->d_overflow, 0, 4, s->stream));
         s->device_bytes = nb + tb + (size_t)n_instances * 4;
         if (built && built->d_nodes) {}
-        else if (n_nodes) CU(cudaMemcpyAsync(s->d_nodes, nodes, (size_t)n_nodes * 80, cudaMemcpyHostToDevice, s->stream));
+        else if (n_nodes) CU(tray::upload_pipelined(s->d_nodes, nodes, (size_t)n_nodes * 80, s->stream));
         else CU(cudaMemsetAsync(s->d_nodes, 0, 80, s->stream));   // empty scene: a root with no children, every ray misses
-        if (!(built && built->d_nodes) && n_tris) CU(cudaMemcpyAsync(s->d_tris, tris, (size_t)n_tris * tri_stride, cudaMemcpyHostToDevice, s->stream));
+        if (!(built && built->d_nodes) && n_tris) CU(tray::upload_pipelined(s->d_tris, tris, (size_t)n_tris * tri_stride, s->stream));
         if (n_instances && blas_offsets) CU(cudaMemcpyAsync(s->d_blas, blas_offsets, (size_t)n_instances * 4, cudaMemcpyHostToDevice, s->stream));
         // keep the node array hot in the 126 MB L2: persisting access-policy window, attached to every traversal launch
         if (env_int("TRAY_CUDA_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0 && n_nodes) {
@@ -590,59 +588,6 @@ int trace_device_impl(tray_scene* s, const tray_ray* d_rays, uint64_t n, tray_hi
     return TRAY_OK;
 }
 
-// Host-side copy spread over a few persistent worker threads: one thread moves ~10 GB/s, the PCIe link of a B200 takes ~50.
-class CopyPool {
-public:
-    static CopyPool& get() { static CopyPool p; return p; }
-    void copy(void* dst, const void* src, size_t bytes) {
-        const size_t nt = bytes < (2u << 20) ? 1 : workers_.size() + 1;
-        if (nt <= 1) { memcpy(dst, src, bytes); return; }
-        std::lock_guard<std::mutex> call(call_mu_);                  // one copy at a time (scenes on several host threads)
-        const size_t per = ((bytes + nt - 1) / nt + 4095) & ~(size_t)4095;
-        {
-            std::lock_guard<std::mutex> g(mu_);
-            dst_ = (char*)dst; src_ = (const char*)src; bytes_ = bytes; per_ = per;
-            pending_ = (int)workers_.size(); generation_++;
-        }
-        cv_.notify_all();
-        memcpy(dst, src, per < bytes ? per : bytes);                 // part 0 on the calling thread
-        std::unique_lock<std::mutex> g(mu_);
-        done_cv_.wait(g, [&] { return pending_ == 0; });
-    }
-private:
-    CopyPool() {
-        const unsigned hw = std::thread::hardware_concurrency();
-        const unsigned n = hw >= 16 ? 7 : hw >= 4 ? hw / 2 - 1 : 0;
-        for (unsigned i = 0; i < n; i++) workers_.emplace_back([this, i] { run(i + 1); });
-    }
-    ~CopyPool() {
-        { std::lock_guard<std::mutex> g(mu_); stop_ = true; }
-        cv_.notify_all();
-        for (auto& t : workers_) t.join();
-    }
-    void run(size_t part) {
-        unsigned long long seen = 0;
-        for (;;) {
-            std::unique_lock<std::mutex> g(mu_);
-            cv_.wait(g, [&] { return stop_ || generation_ != seen; });
-            if (stop_) return;
-            seen = generation_;
-            char* d = dst_; const char* s = src_; const size_t bytes = bytes_, per = per_;
-            g.unlock();
-            const size_t a = part * per;
-            if (a < bytes) memcpy(d + a, s + a, a + per <= bytes ? per : bytes - a);
-            g.lock();
-            if (--pending_ == 0) done_cv_.notify_one();
-        }
-    }
-    std::vector<std::thread> workers_;
-    std::mutex mu_, call_mu_;
-    std::condition_variable cv_, done_cv_;
-    char* dst_ = nullptr; const char* src_ = nullptr; size_t bytes_ = 0, per_ = 0;
-    int pending_ = 0; unsigned long long generation_ = 0; bool stop_ = false;
-};
-void par_copy(void* dst, const void* src, size_t bytes) { CopyPool::get().copy(dst, src, bytes); }
-
 constexpr uint64_t PIPE_CHUNK = 1ull << 20;       // rays per pipeline stage (32 MiB in, 8 MiB out)
 constexpr uint64_t PIPE_MIN = 1ull << 18;         // smaller batches take the plain copy-launch-copy path
 
@@ -694,7 +639,7 @@ int trace_impl(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, 
             if (i < n_chunks) {
                 const uint64_t off = i * PIPE_CHUNK, len = chunk_len(i);
                 if (i >= 2) CU(cudaEventSynchronize(s->e_in[slot]));                 // the slot's previous upload has left it
-                par_copy(s->h_rays[slot], rays + off, len * sizeof(tray_ray));
+                tray::par_copy(s->h_rays[slot], rays + off, len * sizeof(tray_ray));
                 CU(cudaMemcpyAsync(s->d_rays + off, s->h_rays[slot], len * sizeof(tray_ray), cudaMemcpyHostToDevice, s->s_in));
                 CU(cudaEventRecord(s->e_in[slot], s->s_in));
                 CU(cudaStreamWaitEvent(s->stream, s->e_in[slot], 0));
@@ -713,7 +658,7 @@ int trace_impl(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, 
             if (i >= 2) {                                                               // chunk i-2: hand its hits to the caller
                 const uint64_t j = i - 2; const int ps = (int)(j & 1);
                 CU(cudaEventSynchronize(s->e_out[ps]));
-                par_copy(hits + j * PIPE_CHUNK, s->h_hits[ps], chunk_len(j) * sizeof(tray_hit));
+                tray::par_copy(hits + j * PIPE_CHUNK, s->h_hits[ps], chunk_len(j) * sizeof(tray_hit));
             }
         }
         CU(cudaEventRecord(s->ev[1], s->stream));
