@@ -119,6 +119,39 @@ def test_large_host_batches_take_the_copy_pipeline(cornell, any_hit):
         sc.close()
 
 
+def test_two_host_threads_trace_concurrently(cornell, box):
+    """Two scenes driven from two host threads at once (ctypes drops the GIL): the copy threads and the pinned upload slots
+    are shared by the process, the pipeline slots are per scene — results stay those of the oracle."""
+    import threading
+    jobs = []
+    for mesh, use_tlas, stride, seed in ((cornell, False, 48, 31), (cornell, True, 64, 32), (box, False, 24, 33)):
+        p = host.PackedScene(mesh, use_tlas=use_tlas, tri_stride=stride)
+        rays = random_rays(700001, seed)
+        jobs.append((p, rays, ob.Oracle.from_packed(p).trace(rays)))
+    out, errs = [None] * len(jobs), []
+
+    def work(i):
+        try:
+            p, rays, _ = jobs[i]
+            sc = cuda.TrayCudaScene.from_packed(p)
+            try:
+                for _ in range(3):
+                    out[i] = sc.traverse(rays)
+            finally:
+                sc.close()
+        except Exception as e:          # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert not errs, errs
+    for i, (_, _, ref) in enumerate(jobs):
+        assert_hits_identical(out[i], ref, f"job {i}")
+
+
 def test_tiny_direction_components_take_the_unfused_node_test(cornell, monkeypatch):
     """The fused node test (fma(2^23 + q, A, -2^23 A) == fl(q A)) needs 2^23 * A finite.  Rays with |1/d| >= 2^64 on an
     axis, and scenes with node scales >= 2^40, fall back to the unfused test; both paths must match the oracle, and
