@@ -132,6 +132,27 @@ def test_build_is_deterministic_and_comparable_to_the_host_producer():
         a.close(); b.close()
 
 
+@pytest.mark.parametrize("radius", [0, 3, 40])
+def test_single_block_ploc_tail_builds_the_same_bvh(cornell, monkeypatch, radius):
+    """The last PLOC iterations (<= 1024 clusters) run in one block; TRAY_BUILD_PLOC_TAIL=0 keeps the multi-kernel loop to the
+    end.  Both must produce the same bytes: flat scenes, a two-level scene (segmented run + TLAS run), several radii."""
+    meshes = [(cornell.tris(), None), (host.Mesh.generate("kitchen", 1, 1.0).tris(), None), (cornell.tris()[:700], None),
+              (cornell.tris(), cornell.object_offsets())]
+    cal = host.Mesh.generate("caldera", 5, 0.02)
+    meshes.append((cal.tris(), cal.object_offsets()))
+    for tris, offs in meshes:
+        got = []
+        for tail in ("1", "0"):
+            monkeypatch.setenv("TRAY_BUILD_PLOC_TAIL", tail)
+            sc = cuda.TrayCudaScene.build(tris, search_radius=radius, object_offsets=offs)
+            try:
+                got.append(sc.download_bvh() + ((sc.download_instances(),) if offs is not None else ()) + (sc.build_stats["ploc_iterations"],))
+            finally:
+                sc.close()
+        for a, b in zip(*got):
+            assert np.array_equal(a, b)
+
+
 def two_level_check(mesh, w, h, stride=48, max_leaf=3):
     """device-built BLAS forest + TLAS: layout invariants, oracle parity in two-level mode, and the same picture as a flat
     device build of the same triangles"""

@@ -25,6 +25,7 @@
 
 #include <chrono>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "build_gpu.h"
@@ -196,6 +197,83 @@ __global__ void ploc_merge_kernel(const int* __restrict__ cluster, const int* __
         c = id;
     }
     cluster_out[keep_pos[i]] = c;
+}
+
+// The last iterations of a PLOC run work on a handful of clusters each and are pure launch + synchronisation latency
+// (68 iterations for 2.88 M triangles, ~55 of them below a thousand clusters).  Once m <= PLOC_TAIL they all run in ONE block:
+// the same nearest-neighbour rule, the same flags, the same prefix-sum numbering of clusters and new nodes as the
+// three kernels above, so the BVH2 is the one the multi-kernel loop would have produced.
+constexpr int PLOC_TAIL = 1024;
+struct PlocTailOut { uint32_t m, next_node, iters, stalled; };
+
+__global__ void __launch_bounds__(PLOC_TAIL) ploc_tail_kernel(int* __restrict__ cluster, uint32_t m, int r, Bvh2 b, uint32_t* __restrict__ node_seg,
+                                                              uint32_t next_node, PlocTailOut* __restrict__ out) {
+    __shared__ float s_b[6][PLOC_TAIL];                       // min.xyz, max.xyz per cluster position
+    __shared__ uint32_t s_seg[PLOC_TAIL];
+    __shared__ int s_nn[PLOC_TAIL], s_cl[PLOC_TAIL], s_cl2[PLOC_TAIL];
+    __shared__ uint32_t s_tot[2];
+    typedef cub::BlockScan<uint32_t, PLOC_TAIL> Scan;
+    __shared__ typename Scan::TempStorage s_scan;
+    const int i = (int)threadIdx.x;
+    if (i < (int)m) s_cl[i] = cluster[i];
+    __syncthreads();
+    uint32_t iters = 0, stalled = 0;
+    while (m > 1) {
+        if (i < (int)m) {
+            const int c = s_cl[i]; const float4 lo = b.lo[c], hi = b.hi[c];
+            s_b[0][i] = lo.x; s_b[1][i] = lo.y; s_b[2][i] = lo.z; s_b[3][i] = hi.x; s_b[4][i] = hi.y; s_b[5][i] = hi.z;
+            s_seg[i] = node_seg ? node_seg[c] : 0u;
+        }
+        __syncthreads();
+        if (i < (int)m) {
+            const float3 lo = make_float3(s_b[0][i], s_b[1][i], s_b[2][i]), hi = make_float3(s_b[3][i], s_b[4][i], s_b[5][i]);
+            const uint32_t seg = s_seg[i];
+            float best = 3.4e38f; int best_j = -1;
+            const int j0 = max(0, i - r), j1 = min((int)m - 1, i + r);
+            for (int j = j0; j <= j1; j++) {
+                if (j == i || s_seg[j] != seg) continue;
+                const float dx = fmaxf(hi.x, s_b[3][j]) - fminf(lo.x, s_b[0][j]), dy = fmaxf(hi.y, s_b[4][j]) - fminf(lo.y, s_b[1][j]),
+                            dz = fmaxf(hi.z, s_b[5][j]) - fminf(lo.z, s_b[2][j]);
+                const float a = dx * dy + dy * dz + dz * dx;
+                if (a < best) { best = a; best_j = j; }
+            }
+            s_nn[i] = best_j;
+        }
+        __syncthreads();
+        uint32_t keep = 0, lead = 0;
+        if (i < (int)m) {
+            const int j = s_nn[i];
+            const bool mutual = j >= 0 && s_nn[j] == i;
+            keep = (mutual && i > j) ? 0u : 1u;
+            lead = (mutual && i < j) ? 1u : 0u;
+        }
+        uint32_t keep_pos, lead_pos, tot_keep, tot_lead;
+        Scan(s_scan).ExclusiveSum(keep, keep_pos, tot_keep);
+        __syncthreads();
+        Scan(s_scan).ExclusiveSum(lead, lead_pos, tot_lead);
+        if (i < (int)m && keep) {
+            int c = s_cl[i];
+            if (lead) {
+                const int l = c, rgt = s_cl[s_nn[i]];
+                const int j = s_nn[i];
+                const int id = (int)(next_node + lead_pos);
+                b.lo[id] = make_float4(fminf(s_b[0][i], s_b[0][j]), fminf(s_b[1][i], s_b[1][j]), fminf(s_b[2][i], s_b[2][j]), __int_as_float(l));
+                b.hi[id] = make_float4(fmaxf(s_b[3][i], s_b[3][j]), fmaxf(s_b[4][i], s_b[4][j]), fmaxf(s_b[5][i], s_b[5][j]), __int_as_float(rgt));
+                b.count[id] = b.count[l] + b.count[rgt];
+                if (node_seg) node_seg[id] = s_seg[i];
+                c = id;
+            }
+            s_cl2[keep_pos] = c;
+        }
+        if (i == 0) { s_tot[0] = tot_keep; s_tot[1] = tot_lead; }
+        __syncthreads();
+        if (s_tot[1] == 0u) { stalled = 1; break; }           // no mutual pair left: every segment is down to one cluster (or an error, flat)
+        next_node += s_tot[1]; m = s_tot[0]; iters++;
+        if (i < (int)m) s_cl[i] = s_cl2[i];
+        __syncthreads();
+    }
+    if (i < (int)m) cluster[i] = s_cl[i];
+    if (i == 0) { out->m = m; out->next_node = next_node; out->iters = iters; out->stalled = stalled; }
 }
 
 // ---- 4. collapse to 8-wide ------------------------------------------------------------------------------------------
@@ -407,7 +485,21 @@ int ploc_run(Scratch& sc, const float4* plo, const float4* phi, uint32_t n, cons
     BCU(cudaGetLastError());
     uint32_t m = n, next_node = n, iters = 0;
     int* cl_in = cl_a; int* cl_out = cl_b;
+    const char* tail_env = getenv("TRAY_BUILD_PLOC_TAIL");       // 0: keep the multi-kernel loop to the end (tests compare the two)
+    const bool use_tail = !(tail_env && tail_env[0] == '0');
+    PlocTailOut* d_tail = nullptr;
+    BCU(sc.alloc(&d_tail, sizeof(PlocTailOut)));
     while (m > 1) {
+        if (use_tail && m <= (uint32_t)PLOC_TAIL) {       // the rest of the run in one block, one synchronisation
+            ploc_tail_kernel<<<1, PLOC_TAIL, 0, st>>>(cl_in, m, r, b, node_seg, next_node, d_tail);
+            PlocTailOut t;
+            BCU(cudaMemcpyAsync(&t, d_tail, sizeof t, cudaMemcpyDeviceToHost, st));
+            BCU(cudaStreamSynchronize(st));
+            BCU(cudaGetLastError());
+            if (t.stalled && !prim_seg) { snprintf(err, errlen, "PLOC made no progress at %u clusters", t.m); return -3; }
+            m = t.m; next_node = t.next_node; iters += t.iters;
+            break;
+        }
         ploc_nn_kernel<<<blocks(m), TPB, (size_t)(TPB + 2 * r) * 36, st>>>(cl_in, m, r, b, node_seg, nn);
         ploc_flag_kernel<<<blocks(m), TPB, 0, st>>>(nn, m, keep, lead);
         // scans run over m + 1 entries so that entry m holds the total (the extra input element is never a keeper)
