@@ -119,6 +119,30 @@ def test_large_host_batches_take_the_copy_pipeline(cornell, any_hit):
         sc.close()
 
 
+def test_two_devices_in_one_process_assemble_the_frame(cornell):
+    """INTEGRATION.md §4 without torchrun: one scene per device in ONE process (uploads through the shared pinned slots with
+    per-device events), each renders its tile shard, the shards assemble to the single-GPU frame.  Needs two GPUs."""
+    if cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    p = host.PackedScene(host.Mesh.generate("kitchen", 1, 1.0))      # > 8 MiB of triangles: takes the pipelined upload
+    w, h = 640, 360
+    view = host.view_from_camera(cornell.camera, w, h)
+    ref = ob.Oracle.from_packed(p).render(view, w, h, 0)
+    scenes = [cuda.TrayCudaScene.from_packed(p, device=d) for d in (0, 1)]
+    try:
+        acc = {}
+        for d, sc in enumerate(scenes):
+            sc.render(view, w, h, 0, cuda.RENDER_BOUNCE, shard=d, shards=2)
+            sc.download(primary=True, bounce=True, into=acc, merge=True)
+        for k in ("primary", "bounce"):
+            assert_hits_identical(acc[k], ref[k], k)
+        rays = random_rays(400000, 5)
+        assert_hits_identical(scenes[1].traverse(rays), ob.Oracle.from_packed(p).trace(rays), "device 1 batch")
+    finally:
+        for sc in scenes:
+            sc.close()
+
+
 def test_two_host_threads_trace_concurrently(cornell, box):
     """Two scenes driven from two host threads at once (ctypes drops the GIL): the copy threads and the pinned upload slots
     are shared by the process, the pipeline slots are per scene — results stay those of the oracle."""
