@@ -443,14 +443,26 @@ __global__ void collapse_emit_kernel(const int* __restrict__ items, uint32_t n_i
     for (int q = 0; q < 5; q++) dst[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
-struct Scratch {   // frees everything it owns on scope exit
-    void* p[48]; int n = 0;
+// Device scratch of one build: ONE cudaMalloc (reserve) carved up by a bump allocator — a build makes ~35 allocations, and
+// in a process that already holds a lot of device memory each cudaMalloc / cudaFree costs up to a millisecond.  Requests
+// that do not fit the arena fall back to their own cudaMalloc.  Everything is freed on scope exit.
+struct Scratch {
+    void* p[64]; int n = 0;
+    char* arena = nullptr; size_t cap = 0, used = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (cudaMalloc((void**)&arena, bytes) != cudaSuccess) { arena = nullptr; cap = 0; cudaGetLastError(); }   // fall back to per-array allocations
+        else cap = bytes;
+        return cudaSuccess;
+    }
     template <typename T> cudaError_t alloc(T** out, size_t bytes) {
-        void* q = nullptr; cudaError_t e = cudaMalloc(&q, bytes ? bytes : 16);
+        const size_t need = ((bytes ? bytes : 16) + 255) & ~(size_t)255;
+        if (arena && used + need <= cap) { *out = (T*)(arena + used); used += need; return cudaSuccess; }
+        if (n >= 64) return cudaErrorMemoryAllocation;
+        void* q = nullptr; cudaError_t e = cudaMalloc(&q, need);
         if (e == cudaSuccess) { p[n++] = q; *out = (T*)q; }
         return e;
     }
-    ~Scratch() { for (int i = 0; i < n; i++) cudaFree(p[i]); }
+    ~Scratch() { for (int i = 0; i < n; i++) cudaFree(p[i]); if (arena) cudaFree(arena); }
 };
 
 double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
@@ -616,6 +628,7 @@ int build_tlas(const float* tris9_host, uint64_t n_tris, const uint64_t* object_
     const int r = (int)(radius < 1 ? 1 : (radius > 64 ? 64 : radius));
     const double t_begin = now_ms();
     Scratch sc;
+    sc.reserve((size_t)n * 288 + (size_t)(tlas ? n_objects : 0) * 16 + (64u << 20));      // every array of the run (~270 B per triangle) + slack
     float* d_tris9; float4 *plo, *phi; uint32_t* prim_seg = nullptr; uint64_t* d_off = nullptr;
     BCU(sc.alloc(&d_tris9, (size_t)n * 36));
     BCU(sc.alloc(&plo, (size_t)n * 16)); BCU(sc.alloc(&phi, (size_t)n * 16));
@@ -651,6 +664,7 @@ int build_tlas(const float* tris9_host, uint64_t n_tris, const uint64_t* object_
     if (tlas) {
         // TLAS: the same pipeline over the BLAS boxes; its "triangles" are instance slots
         Scratch sc2;
+        sc2.reserve((size_t)n_objects * 288 + (16u << 20));
         float4 *tlo, *thi; uint32_t* tl_prim;
         if (sc2.alloc(&tlo, (size_t)n_objects * 16) != cudaSuccess || sc2.alloc(&thi, (size_t)n_objects * 16) != cudaSuccess ||
             sc2.alloc(&tl_prim, (size_t)n_objects * 4) != cudaSuccess) { snprintf(err, errlen, "out of device memory"); cudaGetLastError(); return bail(-2); }
