@@ -630,14 +630,19 @@ int trace_impl(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, 
     } else {
         rc = ensure_pipeline(s);
         if (rc) return rc;
-        const uint64_t n_chunks = (n + PIPE_CHUNK - 1) / PIPE_CHUNK;
-        auto chunk_len = [&](uint64_t i) { return i + 1 < n_chunks ? PIPE_CHUNK : n - i * PIPE_CHUNK; };
+        // chunk size: the pipeline only pays once it has a few stages, and every stage is a kernel launch with its own
+        // drain phase — 2^19 rays below 4 M rays, 2^20 above (TRAY_CUDA_PIPE_CHUNK overrides, <= 2^20)
+        uint64_t chunk = n < (4ull << 20) ? (PIPE_CHUNK >> 1) : PIPE_CHUNK;
+        const int chunk_env = env_int("TRAY_CUDA_PIPE_CHUNK", 0);
+        if (chunk_env >= 4096 && (uint64_t)chunk_env <= PIPE_CHUNK) chunk = (uint64_t)chunk_env;
+        const uint64_t n_chunks = (n + chunk - 1) / chunk;
+        auto chunk_len = [&](uint64_t i) { return i + 1 < n_chunks ? chunk : n - i * chunk; };
         if (s->counting) CU(cudaMemsetAsync(s->d_cursor + 1, 0, 5 * sizeof(unsigned long long), s->stream));
         CU(cudaEventRecord(s->ev[0], s->stream));
         for (uint64_t i = 0; i < n_chunks + 2; i++) {
             const int slot = (int)(i & 1);
             if (i < n_chunks) {
-                const uint64_t off = i * PIPE_CHUNK, len = chunk_len(i);
+                const uint64_t off = i * chunk, len = chunk_len(i);
                 if (i >= 2) CU(cudaEventSynchronize(s->e_in[slot]));                 // the slot's previous upload has left it
                 tray::par_copy(s->h_rays[slot], rays + off, len * sizeof(tray_ray));
                 CU(cudaMemcpyAsync(s->d_rays + off, s->h_rays[slot], len * sizeof(tray_ray), cudaMemcpyHostToDevice, s->s_in));
@@ -652,13 +657,13 @@ int trace_impl(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, 
             if (i >= 1 && i - 1 < n_chunks) {                                           // chunk i-1: start its read-back
                 const uint64_t j = i - 1; const int ps = (int)(j & 1);
                 CU(cudaStreamWaitEvent(s->s_out, s->e_k[ps], 0));
-                CU(cudaMemcpyAsync(s->h_hits[ps], s->d_hits + j * PIPE_CHUNK, chunk_len(j) * sizeof(tray_hit), cudaMemcpyDeviceToHost, s->s_out));
+                CU(cudaMemcpyAsync(s->h_hits[ps], s->d_hits + j * chunk, chunk_len(j) * sizeof(tray_hit), cudaMemcpyDeviceToHost, s->s_out));
                 CU(cudaEventRecord(s->e_out[ps], s->s_out));
             }
             if (i >= 2) {                                                               // chunk i-2: hand its hits to the caller
                 const uint64_t j = i - 2; const int ps = (int)(j & 1);
                 CU(cudaEventSynchronize(s->e_out[ps]));
-                tray::par_copy(hits + j * PIPE_CHUNK, s->h_hits[ps], chunk_len(j) * sizeof(tray_hit));
+                tray::par_copy(hits + j * chunk, s->h_hits[ps], chunk_len(j) * sizeof(tray_hit));
             }
         }
         CU(cudaEventRecord(s->ev[1], s->stream));
