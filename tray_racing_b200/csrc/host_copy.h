@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <condition_variable>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -33,7 +34,11 @@ public:
 private:
     CopyPool() {
         const unsigned hw = std::thread::hardware_concurrency();
-        const unsigned n = hw >= 16 ? 7 : hw >= 4 ? hw / 2 - 1 : 0;
+        unsigned n = hw >= 16 ? 7 : hw >= 4 ? hw / 2 - 1 : 0;
+        if (const char* e = getenv("TRAY_CUDA_COPY_THREADS")) {          // total threads taking part in a copy (caller included)
+            const int v = atoi(e);
+            if (v >= 1 && v <= 64) n = (unsigned)v - 1;
+        }
         for (unsigned i = 0; i < n; i++) workers_.emplace_back([this, i] { run(i + 1); });
     }
     ~CopyPool() {
