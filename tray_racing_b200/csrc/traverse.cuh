@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
 #ifdef TRAY_EXIT_LOG
                 if (base + n_idle >= n_work && !exhausted && P.spill && lane == 0) {   // ... and when it ran dry
                     unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-                    ((unsigned long long*)P.spill)[2 * (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5))] = t;
+                    ((unsigned long long*)P.spill)[6 * (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5))] = t;
                 }
 #endif
                 if (base + n_idle >= n_work) exhausted = true;
@@ -652,6 +652,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
             if (busy == 0u) break;                           // cursor exhausted and nothing in flight
         }
 
+#ifdef TRAY_EXIT_LOG
+        if (exhausted && P.spill) {       // first time the warp is down to <= 8 / 4 / 2 / 1 rays after the cursor ran dry
+            const int nb = __popc(busy);
+            unsigned long long* rec = (unsigned long long*)P.spill + 6 * (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5));
+            if (lane == 0 && nb <= 8) {
+                unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                if (rec[2] == 0) rec[2] = t;
+                if (nb <= 4 && rec[3] == 0) rec[3] = t;
+                if (nb <= 2 && rec[4] == 0) rec[4] = t;
+                if (nb <= 1 && rec[5] == 0) rec[5] = t;
+            }
+        }
+#endif
         // ---- warp vote: node step or triangle step ----
         const bool tri_phase = m_node == 0u || (unsigned)__popc(m_tri) * P.tri_weight >= (unsigned)__popc(m_node);
         SC(const long long sc_voted = clk_after(tri_phase); sc_acc[0] += sc_voted - sc_top;)
@@ -728,7 +741,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
 #ifdef TRAY_EXIT_LOG
     if (P.spill && lane == 0) {       // dev instrumentation (scripts/exit_log.py): when this warp exited (ns)
         unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-        ((unsigned long long*)P.spill)[2 * (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5)) + 1] = t;
+        ((unsigned long long*)P.spill)[6 * (blockIdx.x * (BLOCK_THREADS / 32) + (threadIdx.x >> 5)) + 1] = t;
     }
 #endif
     if (COUNT) {

@@ -184,7 +184,7 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, boo
 #define TRAY_EXIT_LOG 1              // from here on: the host side of both dev logs is the same dump
     const size_t log_n = 12 * grid * (threads / 32);
 #else
-    const size_t log_n = 2 * grid * (threads / 32);
+    const size_t log_n = 6 * grid * (threads / 32);
 #endif
     static unsigned long long* d_log = nullptr;
     if (!pool) {
