@@ -188,3 +188,28 @@ def test_runner_options_mirror_reference_defaults():
     o = Options()
     # reference src/main.rs:78-83,104-108,139-142: render_time 1.0, max_prims_per_leaf 3, 1920x1080
     assert (o.width, o.height, o.render_time, o.max_prims_per_leaf, o.build) == (1920, 1080, 1.0, 3, "ploc_cwbvh")
+
+
+def test_bench_workloads_and_frame_sizes():
+    """bench.py: c3 grows the frame with the GPU count (weak scaling, ~N x 1080p pixels, multiples of 8); c4 / c5 keep the
+    3840x2160 frame of BASELINE.json's multi-GPU configs (strong scaling), c5 through the two-level traversal."""
+    import importlib
+    import sys
+    from conftest import ROOT
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    assert set(bench.WORKLOADS) == {"c3", "c4", "c5"}
+    old = bench.WL
+    try:
+        bench.WL = bench.WORKLOADS["c3"]
+        assert bench.frame_size(1) == (1920, 1080)
+        for n in (2, 4, 8):
+            w, h = bench.frame_size(n)
+            assert w % 8 == 0 and h % 8 == 0 and abs(w * h / (n * 1920 * 1080) - 1) < 0.01
+        for key in ("c4", "c5"):
+            bench.WL = bench.WORKLOADS[key]
+            assert all(bench.frame_size(n) == (3840, 2160) for n in (1, 2, 4, 8)) and bench.WL["scaling"] == "strong"
+        assert bench.WORKLOADS["c5"]["tlas"] and not bench.WORKLOADS["c4"]["tlas"]
+        assert "fixed frame" in bench.workload_name(3840, 2160, 8)
+    finally:
+        bench.WL = old
