@@ -32,8 +32,11 @@ constexpr int BLOCK_THREADS = 128;
 #ifndef TRAY_MIN_BLOCKS
 #define TRAY_MIN_BLOCKS 8
 #endif
-constexpr int STACK_SMEM = 12;     // entries per thread in shared memory
-constexpr int STACK_SPILL = 36;    // further entries per thread in local memory (total 48 > obvhs' 32, cwbvh.rs:88)
+#ifndef TRAY_STACK_SMEM
+#define TRAY_STACK_SMEM 12
+#endif
+constexpr int STACK_SMEM = TRAY_STACK_SMEM;      // entries per thread in shared memory
+constexpr int STACK_SPILL = 48 - STACK_SMEM;     // further entries per thread in local memory (total 48 > obvhs' 32, cwbvh.rs:88)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t INVALID = 0xffffffffu;
 constexpr float F32_MAX_ = 3.402823466e+38f;
