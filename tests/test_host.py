@@ -213,3 +213,19 @@ def test_bench_workloads_and_frame_sizes():
         assert "fixed frame" in bench.workload_name(3840, 2160, 8)
     finally:
         bench.WL = old
+
+
+def test_host_copy_pool(tmp_path):
+    """The persistent copy threads behind tray_cuda_trace's pipeline and the pinned uploads (csrc/host_copy.h): random
+    sizes, three caller threads at once, byte-exact — compiled for the host alone, no CUDA call is made."""
+    import subprocess
+    from conftest import ROOT
+    exe = tmp_path / "copy_pool_test"
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-pthread", "-I" + cuda_inc, "-I" + os.path.join(ROOT, "tray_racing_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "tools", "copy_pool_test.cpp"), "-o", str(exe),
+                           "-L" + os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64"), "-lcudart"])
+    env = dict(os.environ, LD_LIBRARY_PATH=os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "lib64") + ":" + os.environ.get("LD_LIBRARY_PATH", ""),
+               TRAY_CUDA_COPY_THREADS="6")
+    out = subprocess.run([str(exe)], env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == "ok", out.stdout + out.stderr
