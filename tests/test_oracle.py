@@ -169,21 +169,6 @@ def test_tie_rule_first_wins_vs_hlsl_last_wins():
     ob.set_variant(ob.VARIANT_TIE_LAST)
     try:
         last = o.trace(r)[0]["prim"]
-        # two-level traversal (rt_gpu_software_query_tlas.hlsl:333-500) on the buffers cwbvh_gpu_runner's layout prescribes
-        for mesh, n, seed in ((cornell, 200, 43), (box, 100, 44)):
-            p = host.PackedScene(mesh, use_tlas=True)
-            orc = ob.Oracle.from_packed(p)
-            rays = random_rays(n, seed, axis_fraction=0.15, bounded_fraction=0.0)
-            hits, cnt, _ = orc.trace(rays, counts=True)
-            sc = hl.Scene(p.bvh_bytes, p.tri_bytes, p.tri_stride, p.blas_offsets, p.tlas_start)
-            for i in range(n):
-                t, prim, nn, nt, ni = hl.traverse_bvh_tlas(sc, rays["o"][i], rays["d"][i])
-                if prim < 0:
-                    assert hits["prim"][i] == ob.INVALID_PRIM, i
-                else:
-                    assert hits["prim"][i] == prim, (i, hits["prim"][i], prim)
-                    assert np.float32(hits["t"][i]).view(np.uint32) == np.float32(t).view(np.uint32), (i, hits["t"][i], t)
-                assert cnt["nodes"][i] == nn and cnt["tris"][i] == nt and cnt["insts"][i] == ni, (i, cnt[i], nn, nt, ni)
     finally:
         ob.set_variant(0)
     assert {int(first), int(last)} == {0, 1} and first == 1      # bit 1 is tested before bit 0
@@ -397,5 +382,20 @@ def test_oracle_matches_a_line_by_line_transliteration_of_the_shader(cornell, bo
                     assert np.float32(hits["t"][i]).view(np.uint32) == np.float32(t).view(np.uint32), (i, hits["t"][i], t)
                 assert cnt["nodes"][i] == nn and cnt["tris"][i] == nt, (i, cnt[i], nn, nt)
             assert n_hit > n // 4
+        # two-level traversal (rt_gpu_software_query_tlas.hlsl:333-500) on the buffers cwbvh_gpu_runner's layout prescribes
+        for mesh, n, seed in ((cornell, 200, 43), (box, 100, 44)):
+            p = host.PackedScene(mesh, use_tlas=True)
+            orc = ob.Oracle.from_packed(p)
+            rays = random_rays(n, seed, axis_fraction=0.15, bounded_fraction=0.0)
+            hits, cnt, _ = orc.trace(rays, counts=True)
+            sc = hl.Scene(p.bvh_bytes, p.tri_bytes, p.tri_stride, p.blas_offsets, p.tlas_start)
+            for i in range(n):
+                t, prim, nn, nt, ni = hl.traverse_bvh_tlas(sc, rays["o"][i], rays["d"][i])
+                if prim < 0:
+                    assert hits["prim"][i] == ob.INVALID_PRIM, i
+                else:
+                    assert hits["prim"][i] == prim, (i, hits["prim"][i], prim)
+                    assert np.float32(hits["t"][i]).view(np.uint32) == np.float32(t).view(np.uint32), (i, hits["t"][i], t)
+                assert cnt["nodes"][i] == nn and cnt["tris"][i] == nt and cnt["insts"][i] == ni, (i, cnt[i], nn, nt, ni)
     finally:
         ob.set_variant(0)
