@@ -32,9 +32,13 @@ sys.path.insert(0, ROOT)
 METRIC, UNIT = "Mrays/s primary+diffuse", "Mrays/s"
 TRI_STRIDE = 48
 # BASELINE.json configs that are bench lines.  c3 (configs[2], the one the metric's 1-GPU target is quoted on) is the default
-# and the only one the driver runs; c4 / c5 (configs[3], configs[4]) are the multi-GPU configs: a FIXED 3840x2160 frame
+# and the only one the driver runs; c1 / c2 (configs[0], configs[1]) are the small 1080p scenes; c4 / c5 (configs[3], configs[4]) are the multi-GPU configs: a FIXED 3840x2160 frame
 # tile-sharded over the ranks (strong scaling), c5 through the two-level (--tlas) traversal.
 WORKLOADS = {
+    "c1": dict(scene="kitchen", seed=1, w=1920, h=1080, tlas=False, scaling="weak",
+               label="C1 kitchen-sized 56,939-tri interior (kitchen.ron camera)"),
+    "c2": dict(scene="demoscene", seed=2, w=1920, h=1080, tlas=False, scaling="weak",
+               label="C2 demoscene stand-in, 2.10M-tri fBm height field"),
     "c3": dict(scene="hairball", seed=3, w=1920, h=1080, tlas=False, scaling="weak",
                label="C3 hairball-like 2.88M-tri soup"),
     "c4": dict(scene="sanmiguel", seed=4, w=3840, h=2160, tlas=False, scaling="strong",
@@ -534,7 +538,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
-                    help="c3 (default, the metric's config; weak scaling) | c4 | c5 (fixed 3840x2160 frame sharded over the GPUs)")
+                    help="c3 (default, the metric's config; weak scaling) | c1 | c2 (1080p) | c4 | c5 (fixed 3840x2160 frame sharded over the GPUs)")
     ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
                     help="how shards reach rank 0's frame: peer-mapped frame written by the kernels, or NCCL gather + untile")
     args = ap.parse_args()

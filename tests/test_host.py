@@ -198,7 +198,7 @@ def test_bench_workloads_and_frame_sizes():
     from conftest import ROOT
     sys.path.insert(0, ROOT)
     bench = importlib.import_module("bench")
-    assert set(bench.WORKLOADS) == {"c3", "c4", "c5"}
+    assert set(bench.WORKLOADS) == {"c1", "c2", "c3", "c4", "c5"}
     old = bench.WL
     try:
         bench.WL = bench.WORKLOADS["c3"]
