@@ -577,7 +577,7 @@ int trace_device_impl(tray_scene* s, const tray_ray* d_rays, uint64_t n, tray_hi
     for (uint64_t off = 0; off < n; off += chunk) {
         TraceParams P; base_params(s, P);
         P.rays = d_rays + off; P.n_work = (uint32_t)(n - off < chunk ? n - off : chunk); P.hits_out = d_hits + off;
-        int rc = launch(s, P, st, 0, anyhit);
+        int rc = launch(s, P, st, 0, anyhit, /*keep_counters=*/off > 0);      // counters accumulate over the chunks of one batch
         if (rc) return rc;
     }
     if (ms_kernel) {
