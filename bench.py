@@ -39,7 +39,7 @@ WORKLOADS = {
                label="C1 kitchen-sized 56,939-tri interior (kitchen.ron camera)"),
     "c2": dict(scene="demoscene", seed=2, w=1920, h=1080, tlas=False, scaling="weak",
                label="C2 demoscene stand-in, 2.10M-tri fBm height field"),
-    "c3": dict(scene="hairball", seed=3, w=1920, h=1080, tlas=False, scaling="weak",
+    "c3": dict(scene="hairball", seed=3, w=1920, h=1080, tlas=False, scaling="weak", overlap=True,
                label="C3 hairball-like 2.88M-tri soup"),
     "c4": dict(scene="sanmiguel", seed=4, w=3840, h=2160, tlas=False, scaling="strong",
                label="C4 San-Miguel-sized 5.08M-tri scene"),
@@ -127,11 +127,11 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
+def ncu_traffic(kernel="primary"):
     """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
-        return json.load(open(p))["primary_kernel_dram_bytes_per_launch"]
+        return json.load(open(p))[f"{kernel}_kernel_dram_bytes_per_launch"]
     except Exception:
         return None
 
@@ -236,12 +236,16 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     scene.set_stream(stream.cuda_stream)
-    flags = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA
+    # the one-launch frame kernel (TRAY_RENDER_OVERLAP) where it is the faster way to render the frame: measured -4 % on C3,
+    # +0.5 % / +3.7 % on the kitchen- and San-Miguel-sized scenes, which therefore keep the two-launch path
+    overlap = bool(WL.get("overlap")) and os.environ.get("TRAY_BENCH_OVERLAP", "1") != "0"
+    flags = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA | (cuda.RENDER_OVERLAP if overlap else 0)
+    flags2 = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA            # the two-launch path: per-kernel figures, counters
     n_items = cuda.local_items(w, h, rank, world)
     max_items = cuda.local_items(w, h, 0, world)
 
     # one counting frame (outside the timed region): rays and algorithmic bytes per step
-    scene.render(view, w, h, 0, flags | cuda.RENDER_COUNTERS, rank, world)
+    scene.render(view, w, h, 0, flags2 | cuda.RENDER_COUNTERS, rank, world)
     cp, cb = scene.counters()
     scene.render(view, w, h, 0, flags, rank, world)       # switch back to the non-counting kernels
     _, _, d_rgba = scene.frame_device_ptrs()
@@ -372,16 +376,26 @@ def run_ours(args):
     kp, kb = [], []
     for _ in range(max(5, min(args.steps, 20))):
         flush_buf.fill_(3)
-        a, b = scene.render(view, w, h, 0, flags, rank, world, timed=True)
+        a, b = scene.render(view, w, h, 0, flags2, rank, world, timed=True)
         kp.append(a); kb.append(b)
     kp_ms, kb_ms = sum(kp) / len(kp), sum(kb) / len(kb)
+    kf_ms = None
+    if overlap:                                        # the frame kernel (+ primary ray generation), CUDA events, L2 flushed
+        kf = []
+        for _ in range(max(5, min(args.steps, 20))):
+            flush_buf.fill_(3)
+            kf.append(scene.render(view, w, h, 0, flags, rank, world, timed=True)[0])
+        kf_ms = sum(kf) / len(kf)
     bytes_p = 80 * cp["nodes"] + TRI_STRIDE * cp["tris"] + 4 * cp["instances"] + 8 * cp["rays"]
     bytes_b = 80 * cb["nodes"] + TRI_STRIDE * cb["tris"] + 4 * cb["instances"] + 8 * cb["rays"] + 8 * cp["rays"]
     peak, peak_src = measured_peaks()
     l2_peak = cuda.bandwidth_probe(48 << 20, 50, local_rank)          # streaming read of an L2-resident 48 MiB buffer
     hbm_read = cuda.bandwidth_probe(2048 << 20, 8, local_rank)        # same kernel, buffer >> L2
-    dominant = "primary" if kp_ms >= kb_ms else "bounce"
-    ach = (bytes_p / kp_ms if dominant == "primary" else bytes_b / kb_ms) / 1e6      # GB/s
+    dominant = "frame" if overlap else ("primary" if kp_ms >= kb_ms else "bounce")
+    # frame kernel: both ray kinds in one launch (the 8 B/pixel primary hit is written and read back inside it)
+    dom_bytes = {"frame": bytes_p + bytes_b, "primary": bytes_p, "bounce": bytes_b}[dominant]
+    dom_ms = {"frame": kf_ms, "primary": kp_ms, "bounce": kb_ms}[dominant]
+    ach = dom_bytes / dom_ms / 1e6                     # GB/s
 
     # ---- end to end through the public API with HOST buffers ----
     # Every step: tray_cuda_render on every rank (view + frame parameters go in by value, 160 B per rank), the exchange
@@ -451,7 +465,7 @@ def run_ours(args):
     if rank == 0 and world == 1 and args.workload == "c3":
         extras = {}
         # f4: AO rays as an any-hit query (rt_cpu.rs:78-79) — same rays, each stopped at its first hit
-        ka = [scene.render(view, w, h, 0, flags | cuda.RENDER_ANYHIT_AO, rank, world, timed=True) for _ in range(6)][1:]
+        ka = [scene.render(view, w, h, 0, flags2 | cuda.RENDER_ANYHIT_AO, rank, world, timed=True) for _ in range(6)][1:]
         kb_any = min(b for _, b in ka)
         extras["anyhit_ao"] = {"bounce_kernel_ms": kb_any, "bounce_kernel_mrays_s": cb["rays"] / kb_any / 1e3,
                                "closest_hit_bounce_kernel_ms": kb_ms, "note": "TRAY_RENDER_ANYHIT_AO: visibility only, not the reference image"}
@@ -468,7 +482,7 @@ def run_ours(args):
             if wall is None or w2 < wall:
                 wall, stats_best = w2, dict(g2.build_stats)
             g = g2
-        kg = [g.render(view, w, h, 0, flags) for _ in range(6)][1:]
+        kg = [g.render(view, w, h, 0, flags2) for _ in range(6)][1:]
         extras["device_builder"] = {"wall_ms": wall, **stats_best, "protocol": "one untimed warm-up build, then the best of 3",
                                     "host_producer_ms": packed.build_seconds * 1e3,
                                     "primary_kernel_ms_on_device_built_bvh": min(a for a, _ in kg),
@@ -485,6 +499,8 @@ def run_ours(args):
             "config": {"workload": workload_name(w, h, world), "n_tris": packed.n_tris, "n_nodes": packed.n_nodes,
                        "working_set_mb": round(packed.working_set_bytes() / 1e6, 1), "tri_stride": TRI_STRIDE,
                        "rays_per_step": {"primary": rays_p, "bounce": rays_b},
+                       "frame_path": ("one launch per frame (TRAY_RENDER_OVERLAP: raygen_primary + trace_kernel<FRAME>)" if overlap
+                                      else "two launches per frame (raygen_primary, trace, raygen_bounce, trace)"),
                        "l2": "flushed between timed steps (256 MiB device write)", "parallelism": f"tile-sharded x{world}, BVH replicated",
                        "exchange": ("peer: kernels store pixels into rank 0's IPC-mapped row-major frame over NVLink + 4-byte all-reduce barrier"
                                     if exchange == "peer" else "NCCL gather of RGBA8 shards to rank 0 + untile per shard") if world > 1
@@ -493,14 +509,17 @@ def run_ours(args):
             "warm_l2": {"value": rays_all / (warm_ms * 1e-3) / 1e6, "ms_per_step": warm_ms, "steps": warm_steps,
                         "note": "same steps back to back without the L2 flush (working set 174 MB > 126 MB L2; node array under the persisting-L2 window)"},
             "mrays_s": {"primary_kernel": cp["rays"] / kp_ms / 1e3, "bounce_kernel": (cb["rays"] / kb_ms / 1e3) if cb["rays"] else None,
-                        "note": "rank-0 shard, kernel alone, CUDA events"},
-            "roofline": {"bound": "hbm", "kernel": f"trace_kernel<{dominant}>", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "peak_source": peak_src, "traffic": ncu_traffic(),
+                        "note": "rank-0 shard, the two-launch path's kernels alone, CUDA events"},
+            "roofline": {"bound": "hbm", "kernel": "trace_kernel<FRAME> (primary + bounce rays in one launch; span includes raygen_primary)" if overlap else f"trace_kernel<{dominant}>", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "peak_source": peak_src, "traffic": ncu_traffic(dominant) if args.workload == "c3" else None,
                          "l2_peak_gbs_measured_here": l2_peak, "frac_of_l2_peak": ach / l2_peak, "hbm_read_gbs_measured_here": hbm_read,
-                         "algorithmic_bytes_per_launch": bytes_p if dominant == "primary" else bytes_b,
-                         "bytes_per_ray": (bytes_p / cp["rays"]) if dominant == "primary" else (bytes_b / max(1, cb["rays"])),
-                         "ms_per_launch": kp_ms if dominant == "primary" else kb_ms,
-                         "nodes_per_ray": cp["nodes"] / cp["rays"], "tris_per_ray": cp["tris"] / cp["rays"]},
+                         "algorithmic_bytes_per_launch": dom_bytes,
+                         "bytes_per_ray": dom_bytes / {"frame": cp["rays"] + cb["rays"], "primary": cp["rays"], "bounce": max(1, cb["rays"])}[dominant],
+                         "ms_per_launch": dom_ms,
+                         "nodes_per_ray": cp["nodes"] / cp["rays"], "tris_per_ray": cp["tris"] / cp["rays"],
+                         "two_launch_path": {"primary_kernel_gbs": bytes_p / kp_ms / 1e6, "primary_kernel_frac": bytes_p / kp_ms / 1e6 / peak,
+                                             "bounce_kernel_gbs": bytes_b / kb_ms / 1e6, "bounce_kernel_frac": bytes_b / kb_ms / 1e6 / peak,
+                                             "note": "the same frame as two launches (the roofline object of earlier bench lines was the primary kernel of this path)"}},
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 160 * world, "d2h_bytes_per_step": w * h * 4,
                     "synchronous_note": "per rank: render, then tray_cuda_frame_download of a full-size frame (other shards zero), no exchange, no overlap",
                     "synchronous_value": e2e_sync_val,
@@ -509,7 +528,7 @@ def run_ours(args):
                             "synchronous_value = render then tray_cuda_frame_download, no overlap"},
             # per step and rank: raygen_primary, trace (primary), raygen_bounce, trace (bounce); the NCCL path adds one
             # untile per shard on rank 0
-            "gpu_launches": args.steps * world * (4 if exchange == "peer" else 5),
+            "gpu_launches": args.steps * world * ((2 if overlap else 4) + (0 if exchange == "peer" else 1)),
             "clocks": clocks,
         }
         if cpu_base is not None:

@@ -140,6 +140,11 @@ typedef struct tray_scene_info {
 #define TRAY_RENDER_KEEP_RAYS  0x8u /* also store the generated bounce rays (for checkers)                    */
 #define TRAY_RENDER_ANYHIT_AO  0x10u /* bounce rays stop at their FIRST hit (rt_cpu.rs:78-79 "a faster anyhit query"):
                                       * the bounce buffer holds that hit, RGBA is visibility (0 / 1) — not the reference image */
+#define TRAY_RENDER_OVERLAP    0x20u /* ONE kernel launch for the frame: once the primary rays have all been handed out, warps with idle
+                                      * lanes generate and trace the bounce rays of the 256-pixel tiles whose primary rays have all
+                                      * retired, so the primary pass's drain phase is filled with bounce work.  Same hits, bounce rays
+                                      * and image as the two-launch path; ms_primary is then the whole frame, ms_bounce 0.  Needs
+                                      * TRAY_RENDER_BOUNCE; ignored with TRAY_RENDER_ANYHIT_AO. */
 
 typedef struct tray_scene tray_scene;
 

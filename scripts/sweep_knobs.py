@@ -18,7 +18,7 @@ for combo in itertools.product(*[knobs[n] for n in names]):
     sc = cuda.TrayCudaScene.from_packed(p)
     best = None
     for f in range(6):
-        ms = sc.render(view, w, h, 0, cuda.RENDER_BOUNCE | cuda.RENDER_RGBA)
+        ms = sc.render(view, w, h, 0, cuda.RENDER_BOUNCE | cuda.RENDER_RGBA | (cuda.RENDER_OVERLAP if os.environ.get("SWEEP_OVERLAP") == "1" else 0))
         if f >= 1:
             best = ms if best is None else (min(best[0], ms[0]), min(best[1], ms[1]))
     sc.close()

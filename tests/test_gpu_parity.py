@@ -26,13 +26,14 @@ def assert_hits_identical(gpu, ref, what=""):
     assert (np.abs(gpu["t"][hit] - ref["t"][hit]) <= 1e-5 * np.abs(ref["t"][hit])).all()
 
 
-def render_and_compare(mesh, w, h, use_tlas=False, stride=48, frame=0, counters=True):
+def render_and_compare(mesh, w, h, use_tlas=False, stride=48, frame=0, counters=True, overlap=False):
     p = host.PackedScene(mesh, use_tlas=use_tlas, tri_stride=stride)
     view = host.view_from_camera(mesh.camera, w, h, p.tlas_start)
     ref = ob.Oracle.from_packed(p).render(view, w, h, frame_count=frame, rgba=True)
     sc = cuda.TrayCudaScene.from_packed(p)
     try:
-        sc.render(view, w, h, frame, FLAGS | (cuda.RENDER_COUNTERS if counters else 0))
+        sc.render(view, w, h, frame, FLAGS | (cuda.RENDER_COUNTERS if counters else 0) | (cuda.RENDER_OVERLAP if overlap else 0))
+        sc.sync()                                                            # raises if a kernel flagged an overflow / watchdog
         out = sc.download(primary=True, bounce=True, bounce_rays=True, rgba=True)
         assert_hits_identical(out["primary"], ref["primary"], "primary")
         assert (out["bounce_rays"].view(np.uint32) == ref["bounce_rays"].view(np.uint32)).all(), "bounce rays differ"
@@ -72,6 +73,23 @@ def test_odd_resolution_and_other_frame(cornell):
                                                  ("caldera", 5, 0.02, True), ("caldera", 5, 0.02, False)])
 def test_synthetic_scenes_frame(name, seed, size, tlas):
     render_and_compare(host.Mesh.generate(name, seed, size), 480, 270, use_tlas=tlas)
+
+
+@pytest.mark.parametrize("use_tlas,stride", [(False, 48), (False, 64), (True, 48), (True, 64), (False, 24)])
+def test_one_launch_frame_kernel_is_bit_identical(cornell, use_tlas, stride):
+    """TRAY_RENDER_OVERLAP: one launch per frame; bounce rays of finished tiles are generated and traced while the primary
+    pass drains.  Primary hits, bounce rays, bounce hits, image and the per-kind node / triangle / instance counters are those
+    of the oracle (and so of the two-launch path)."""
+    render_and_compare(cornell, 640, 360, use_tlas, stride, overlap=True)
+    render_and_compare(cornell, 101, 37, use_tlas, stride, frame=5, overlap=True)
+    render_and_compare(cornell, 640, 360, use_tlas, stride, counters=False, overlap=True)
+
+
+@pytest.mark.parametrize("gen_min", [1, 32])
+@pytest.mark.parametrize("name,seed,size,tlas", [("hairball", 3, 0.1, False), ("caldera", 5, 0.02, True), ("kitchen", 1, 1.0, False)])
+def test_one_launch_frame_kernel_on_synthetic_scenes(monkeypatch, name, seed, size, tlas, gen_min):
+    monkeypatch.setenv("TRAY_CUDA_GEN_MIN", str(gen_min))
+    render_and_compare(host.Mesh.generate(name, seed, size), 480, 270, use_tlas=tlas, overlap=True)
 
 
 def test_traverse_random_rays(cornell):

@@ -52,6 +52,7 @@ pub const RENDER_RGBA: u32 = 0x2;
 pub const RENDER_COUNTERS: u32 = 0x4;
 pub const RENDER_KEEP_RAYS: u32 = 0x8;
 pub const RENDER_ANYHIT_AO: u32 = 0x10;
+pub const RENDER_OVERLAP: u32 = 0x20;
 
 extern "C" {
     pub fn tray_cuda_abi_version() -> u32;

@@ -82,6 +82,14 @@ struct TraceParams {
     float zero;                               // 0.0f, passed at run time (see child_test_fast)
     uint32_t refill_min;                      // idle lanes needed before a partial warp refills
     uint32_t tri_weight;                      // vote: triangle phase when n_tri * tri_weight >= n_node
+    // FRAME kernel only (one launch per frame: bounce rays of finished 32-item groups start while the primary pass drains)
+    FrameParams frame;                        // camera, frame geometry, frame_count (rays = the primary rays in item order)
+    tray_hit* __restrict__ bounce_out;        // bounce hits by item
+    tray_ray* __restrict__ rays_by_item;      // optional: the generated bounce rays by item (checkers)
+    tray_ray* gen_rays;                       // bounce rays by item: written full-width when a group is claimed, read back lane by lane
+    uint32_t* __restrict__ unit_cursor;       // next tile whose bounce rays have not been claimed (zeroed by the host)
+    uint32_t n_units;                         // n_work / 32: bounce work is claimed in groups of 32 items
+    uint32_t gen_min;                         // idle lanes needed before the warp generates bounce rays into them
 };
 
 // ---- exact float helpers (no contraction, IEEE rounding) --------------------------------------
@@ -561,7 +569,17 @@ __global__ void __launch_bounds__(BOUNCE_BLOCK) raygen_bounce_kernel(const __gri
 // so one pair of ballots per iteration drives everything (refill, phase vote, exit).
 // ANYHIT: a ray retires at its FIRST accepted triangle (the "faster anyhit query" rt_cpu.rs:78-79 asks for AO rays);
 // the sequence of tests up to that point is the closest-hit one, so "found a hit" is the same predicate.
-template <bool TLAS, bool COUNT, int TRI_STRIDE, bool ANYHIT = false>
+// FRAME: ONE launch traces a whole frame (TRAY_RENDER_OVERLAP).  Phase 1 is the primary pass as ever.  Once the primary cursor
+// has run dry, a warp with idle lanes claims the next group of 32 items (one atomicAdd per group, in item order), waits until
+// the group's 32 primary hits are THERE, generates the group's bounce rays full-width (bounce_ray, the code of
+// raygen_bounce_kernel), parks them in the bounce-ray buffer and hands them to its idle lanes one by one — so the drain phase of
+// the primary pass is filled with bounce work instead of idle SMs, and the frame has one drain phase instead of two.
+// The hand-shake needs neither counters nor fences: the host fills the primary-hit buffer with 0xFFFFFFFF'FFFFFFFF before the
+// launch, no hit record looks like that (its t would be a NaN), and a lane publishes its record with ONE aligned 8-byte store;
+// a reader that sees something else than the fill pattern sees the whole record.  A warp with nothing else in hand polls with
+// __nanosleep and a watchdog (the device is never hung: after ~2 s it raises the overflow flag and leaves).
+// Per ray nothing changes: same node order, same triangle order, same (prim, t).
+template <bool TLAS, bool COUNT, int TRI_STRIDE, bool ANYHIT = false, bool FRAME = false>
 __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
     uint2 spill[STACK_SPILL];
@@ -579,6 +597,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
     uint32_t ray_idx = 0;
     bool exhausted = false;                      // warp-uniform
     unsigned long long c_rays = 0, c_nodes = 0, c_tris = 0, c_insts = 0, c_hits = 0;
+    unsigned long long b_rays = 0, b_nodes = 0, b_tris = 0, b_insts = 0, b_hits = 0;    // FRAME && COUNT: the bounce rays' share
+    // FRAME: bit 31 of ray_idx marks a bounce ray (items are < 2^31, checked by the host)
+#define TRAY_CNT(name) do { if (COUNT) { if (FRAME && (ray_idx >> 31)) b_##name++; else c_##name++; } } while (0)
+    uint32_t cur_unit = INVALID, cand_unit = INVALID, H = 0, sleeps = 0;   // FRAME, warp-uniform: 32-pixel group being fed from, claimed group, its pixels still to shoot
+    bool units_done = false;
 
     auto push = [&](uint32_t x, uint32_t y) {
         if (sp < STACK_SMEM) my_stack[sp * BLOCK_THREADS] = make_uint2(x, y);
@@ -593,6 +616,22 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
             tray_hit h;
             h.t = best_prim != INVALID ? best_t : __int_as_float(0x7f800000);   // RayHit::none()
             h.prim = best_prim;
+            if (FRAME) {
+                const uint32_t it = ray_idx & 0x7fffffffu;
+                if (COUNT && best_prim != INVALID) TRAY_CNT(hits);
+                if (!(ray_idx >> 31))      // ONE aligned 8-byte store (never two halves): the record itself tells a reader that it is there
+                    *reinterpret_cast<uint2*>(P.hits_out + it) = make_uint2(__float_as_uint(h.t), h.prim);
+                else {
+                    P.bounce_out[it] = h;
+                    if (P.rgba_out) {
+                        const float col = h.t < F32_MAX_ ? __fdiv_rn(h.t, add(1.0f, h.t)) : 1.0f;    // rt_cpu.rs:82-87
+                        const long long o = rgba_slot(it, P.frame_w, P.frame_h, P.frame_tiles_x, P.frame_shard, P.frame_shards);
+                        if (o >= 0) P.rgba_out[o] = shade(col);
+                    }
+                }
+                cur_x = 0; cur_y = 0;
+                return;
+            }
             const uint32_t item = P.ray_item ? __ldg(P.ray_item + ray_idx) : ray_idx;
             P.hits_out[item] = h;
             if (P.rgba_out) {
@@ -652,7 +691,90 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                 }
                 continue;                                    // re-vote with the new rays
             }
-            if (busy == 0u) break;                           // cursor exhausted and nothing in flight
+            if (!FRAME && busy == 0u) break;                 // cursor exhausted and nothing in flight
+        }
+        if (FRAME) {
+            const unsigned idle = ~busy;
+            if (exhausted && idle != 0u) {
+                if (H != 0u) {
+                    if ((unsigned)__popc(idle) >= P.gen_min || busy == 0u) {
+                        // the k-th idle lane shoots the k-th pending pixel of the group (rt_cpu.rs:61-76)
+                        const unsigned rank = (unsigned)__popc(idle & ((1u << lane) - 1u));
+                        const bool take = ((idle >> lane) & 1u) && rank < (unsigned)__popc(H);
+                        if (take) {
+                            const uint32_t pix = __fns(H, 0, (int)rank + 1);
+                            const uint32_t item = cur_unit * 32u + pix;
+                            const float4* gp = reinterpret_cast<const float4*>(P.gen_rays + item);     // written by this warp at the claim
+                            const float4 ga = __ldcg(gp), gb = __ldcg(gp + 1);
+                            const float ox = ga.x, oy = ga.y, oz = ga.z, dx = gb.x, dy = gb.y, dz = gb.z;
+                            prepare_ray(r, ox, oy, oz, dx, dy, dz, 0.0f);                       // Ray::new(o, dir, 0.0, f32::MAX)
+                            best_t = F32_MAX_; best_prim = INVALID;
+                            cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp = 0;
+                            tlas_sp = INVALID; bvh_off = TLAS ? P.tlas_start : 0u;
+                            ray_idx = item | 0x80000000u;
+                            if (COUNT) b_rays++;
+                        }
+                        int n_take = min(__popc(idle), __popc(H));
+                        while (n_take-- > 0) H &= H - 1u;                                     // the lowest bits are the ones taken
+                        continue;
+                    }
+                } else {
+                    // the group in hand is used up: claim the next 32-pixel group (in item order) and wait for its tile
+                    if (cand_unit == INVALID && !units_done) {
+                        uint32_t u = 0;
+                        if (lane == 0) u = atomicAdd(P.unit_cursor, 1u);
+                        u = __shfl_sync(FULL, u, 0);
+                        if (u >= P.n_units) units_done = true; else cand_unit = u;
+                    }
+                    if (cand_unit != INVALID) {
+                        // the group is ready when the primary hits of its 32 items are all there: the host fills the hit buffer
+                        // with the pattern 0xFFFFFFFF'FFFFFFFF before the launch, no hit record looks like that (t would be a NaN),
+                        // and a record is one aligned 8-byte store — no counters, no fences in the primary pass
+                        const uint32_t item = cand_unit * 32u + lane;
+                        const float2 ph = __ldcv(reinterpret_cast<const float2*>(P.hits_out + item));
+                        const bool there = !(__float_as_uint(ph.x) == 0xffffffffu && __float_as_uint(ph.y) == 0xffffffffu);
+                        if (__ballot_sync(FULL, there) == FULL) {
+                            cur_unit = cand_unit; cand_unit = INVALID; sleeps = 0;
+                            // the group's 32 pixels: who shoots?  Missed pixels get their final results here (rt_cpu.rs:59)
+                            uint32_t px, py;
+                            const bool inside = item_to_pixel(P.frame, item, px, py);
+                            const bool shoot = inside && ph.x < F32_MAX_;                     // rt_cpu.rs:61
+                            if (!shoot) {
+                                tray_hit miss; miss.t = __int_as_float(0x7f800000); miss.prim = INVALID;
+                                P.bounce_out[item] = miss;
+                                if (P.rgba_out) {
+                                    const long long o = rgba_slot(item, P.frame_w, P.frame_h, P.frame_tiles_x, P.frame_shard, P.frame_shards);
+                                    if (o >= 0) P.rgba_out[o] = shade(__fdiv_rn(1.0f, ph.x));
+                                }
+                                if (P.rays_by_item) {
+                                    float4* o2 = reinterpret_cast<float4*>(P.rays_by_item + item);
+                                    o2[0] = make_float4(0.f, 0.f, 0.f, 0.f); o2[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                }
+                            }
+                            else {
+                                const float4 pb = __ldg(reinterpret_cast<const float4*>(P.rays + item) + 1);   // the primary direction as generated
+                                float ox, oy, oz, dx, dy, dz;
+                                bounce_ray<TRI_STRIDE>(P.frame, P.tris, px, py, pb.x, pb.y, pb.z, ph.x, __float_as_uint(ph.y), ox, oy, oz, dx, dy, dz);
+                                float4* go = reinterpret_cast<float4*>(P.gen_rays + item);
+                                go[0] = make_float4(ox, oy, oz, 0.0f); go[1] = make_float4(dx, dy, dz, F32_MAX_);
+                                if (P.rays_by_item) {
+                                    float4* o2 = reinterpret_cast<float4*>(P.rays_by_item + item);
+                                    o2[0] = make_float4(ox, oy, oz, 0.0f); o2[1] = make_float4(dx, dy, dz, F32_MAX_);
+                                }
+                            }
+                            __syncwarp();                      // the group's rays are read back by other lanes of this warp
+                            H = __ballot_sync(FULL, shoot);
+                            continue;
+                        }
+                        if (busy == 0u) {                     // nothing else in hand: wait for the tile's last primary rays
+                            __nanosleep(500);
+                            if (++sleeps > 4000000u) { atomicOr(P.overflow, 4u); break; }       // watchdog: never hang the device
+                            continue;
+                        }
+                    } else if (busy == 0u) break;             // no group left, nothing in flight
+                }
+            }
+            if (busy == 0u) { if (exhausted && units_done && cand_unit == INVALID && H == 0u) break; continue; }
         }
 
 #ifdef TRAY_EXIT_LOG
@@ -684,7 +806,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                 SC(const long long sc_a = clk_after(rel); sc_acc[1] += sc_a - sc_voted;)
                 const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                 SC(const long long sc_b = clk_after(n0.x ^ n1.x ^ n2.x ^ n3.x ^ n4.x); sc_acc[2] += sc_b - sc_a;)
-                if (COUNT) c_nodes++;
+                TRAY_CNT(nodes);
                 const uint32_t hitmask = (r.wide || P.force_exact) ? node_test(r, best_t, n0, n1, n2, n3, n4, k4b)
                                                 : node_test_fast(r, best_t, n0, n1, n2, n3, n4, k4b, P.zero);   // :380
                 SC(const long long sc_c = clk_after(hitmask); sc_acc[3] += sc_c - sc_b; sc_n[0]++;)
@@ -716,10 +838,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                     if (cur_y & 0xff000000u) push(cur_x, cur_y);
                     tlas_sp = (uint32_t)sp;
                     bvh_off = __ldg(P.blas_offsets + g);
-                    if (COUNT) c_insts++;
+                    TRAY_CNT(insts);
                     cur_x = 0; cur_y = 0x80000000u; tri_y = 0;
                 } else {
-                    if (COUNT) c_tris++;
+                    TRAY_CNT(tris);
                     SC(const long long sc_a = clk_after(g); sc_acc[5] += sc_a - sc_voted;)
                     SC({ const uint4 q0 = __ldg(P.tris + (size_t)g * (TRI_STRIDE / 16)), q2 = __ldg(P.tris + (size_t)g * (TRI_STRIDE / 16) + 2);
                          sc_acc[6] -= sc_a; sc_acc[6] += clk_after(q0.x ^ q2.x); })
@@ -758,7 +880,20 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
             atomicAdd(P.counters + 0, c_rays); atomicAdd(P.counters + 1, c_nodes); atomicAdd(P.counters + 2, c_tris);
             atomicAdd(P.counters + 3, c_insts); atomicAdd(P.counters + 4, c_hits);
         }
+        if (FRAME) {          // the bounce rays' counters live in the next counter slot
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                b_rays += __shfl_xor_sync(FULL, b_rays, o); b_nodes += __shfl_xor_sync(FULL, b_nodes, o);
+                b_tris += __shfl_xor_sync(FULL, b_tris, o); b_insts += __shfl_xor_sync(FULL, b_insts, o);
+                b_hits += __shfl_xor_sync(FULL, b_hits, o);
+            }
+            if (lane == 0) {
+                atomicAdd(P.counters + 5, b_rays); atomicAdd(P.counters + 6, b_nodes); atomicAdd(P.counters + 7, b_tris);
+                atomicAdd(P.counters + 8, b_insts); atomicAdd(P.counters + 9, b_hits);
+            }
+        }
     }
+#undef TRAY_CNT
 }
 
 // compact local order -> row-major frame (one thread per local work item)

@@ -65,7 +65,9 @@ struct tray_scene {
     cudaAccessPolicyWindow window{};
     uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
     bool counting = false;
-    uint32_t refill_min = 4, tri_weight = 4;
+    uint32_t refill_min = 4, tri_weight = 4, gen_min = 4;
+    bool overlap_default = false;            // TRAY_CUDA_OVERLAP=1: tray_cuda_render always takes the one-launch frame kernel
+    uint32_t* d_units = nullptr;             // FRAME kernel: cursor over the 32-item groups of bounce work
     bool pool = false;                       // pooled kernel (traverse_pool.cuh) or one-ray-per-lane kernel (traverse.cuh)
     uint32_t pool_refill_min = 8, pool_tri_weight = 1;
     uint2* d_spill = nullptr; uint64_t spill_cap = 0;
@@ -107,6 +109,15 @@ kernel_fn pick_stride(uint32_t stride) {
     return stride == 64 ? (kernel_fn)trace_kernel<TLAS, COUNT, 64, ANYHIT>
          : stride == 24 ? (kernel_fn)trace_kernel<TLAS, COUNT, 24, ANYHIT> : (kernel_fn)trace_kernel<TLAS, COUNT, 48, ANYHIT>;
 }
+template <bool TLAS, bool COUNT>
+kernel_fn pick_frame_stride(uint32_t stride) {
+    return stride == 64 ? (kernel_fn)trace_kernel<TLAS, COUNT, 64, false, true>
+         : stride == 24 ? (kernel_fn)trace_kernel<TLAS, COUNT, 24, false, true> : (kernel_fn)trace_kernel<TLAS, COUNT, 48, false, true>;
+}
+kernel_fn pick_frame_kernel(bool tlas, bool count, uint32_t stride) {
+    if (tlas) return count ? pick_frame_stride<true, true>(stride) : pick_frame_stride<true, false>(stride);
+    return count ? pick_frame_stride<false, true>(stride) : pick_frame_stride<false, false>(stride);
+}
 kernel_fn pick_kernel(bool tlas, bool count, uint32_t stride, bool anyhit) {
     if (anyhit) {
         if (tlas) return count ? pick_stride<true, true, true>(stride) : pick_stride<true, false, true>(stride);
@@ -138,9 +149,10 @@ void base_params(const tray_scene* s, TraceParams& P) {
 }
 
 // one launch: reset the cursor, run the persistent grid (sized to the chip, or to the work if that is smaller)
-int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, bool anyhit = false, bool keep_counters = false) {
-    const bool pool = s->pool && !anyhit && s->tri_stride != 24;      // the pooled kernel covers closest hit on f32 records
-    kernel_fn k = pool ? pick_pool_kernel(s->tlas, s->counting, s->tri_stride) : pick_kernel(s->tlas, s->counting, s->tri_stride, anyhit);
+int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, bool anyhit = false, bool keep_counters = false, bool frame = false) {
+    const bool pool = s->pool && !anyhit && !frame && s->tri_stride != 24;      // the pooled kernel covers closest hit on f32 records
+    kernel_fn k = pool ? pick_pool_kernel(s->tlas, s->counting, s->tri_stride)
+                : frame ? pick_frame_kernel(s->tlas, s->counting, s->tri_stride) : pick_kernel(s->tlas, s->counting, s->tri_stride, anyhit);
     const int threads = pool ? POOL_WARPS * 32 : BLOCK_THREADS;
     const uint64_t rays_per_block = pool ? (uint64_t)POOL_WARPS * POOL_SLOTS : (uint64_t)BLOCK_THREADS;
     int& bps = s->blocks_per_sm[pool ? 1 : 0];
@@ -153,7 +165,7 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, boo
     }
     P.counters = s->d_cursor + 1 + 5 * counter_slot;
     CU(cudaMemsetAsync(s->d_cursor, 0, sizeof(unsigned long long), st));
-    if (s->counting && !keep_counters) CU(cudaMemsetAsync(P.counters, 0, 5 * sizeof(unsigned long long), st));
+    if (s->counting && !keep_counters) CU(cudaMemsetAsync(P.counters, 0, (frame ? 10 : 5) * sizeof(unsigned long long), st));
     const uint64_t blocks_needed = ((uint64_t)P.n_work + rays_per_block - 1) / rays_per_block;
     uint64_t grid = (uint64_t)s->sm_count * bps;
     if (blocks_needed < grid) grid = blocks_needed;
@@ -228,6 +240,10 @@ int check_overflow(tray_scene* s) {
     uint32_t f = 0;
     CU(cudaMemcpyAsync(&f, s->d_overflow, 4, cudaMemcpyDeviceToHost, s->stream));
     CU(cudaStreamSynchronize(s->stream));
+    if (f & 4u) {
+        cudaMemsetAsync(s->d_overflow, 0, 4, s->stream);
+        return fail(TRAY_ERR_CUDA, "frame kernel watchdog: a group of primary hits never arrived (the frame is incomplete)");
+    }
     if (f) {
         cudaMemsetAsync(s->d_overflow, 0, 4, s->stream);
         return fail(TRAY_ERR_OVERFLOW, "traversal stack overflow: BVH needs more than %d stack entries", STACK_SMEM + STACK_SPILL);
@@ -288,7 +304,7 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_blas); cudaFree(s->d_prim_indices); cudaFree(s->d_cursor); cudaFree(s->d_overflow);
-    cudaFree(s->d_rays); cudaFree(s->d_hits); cudaFree(s->d_spill);
+    cudaFree(s->d_rays); cudaFree(s->d_hits); cudaFree(s->d_spill); cudaFree(s->d_units);
     for (int i = 0; i < 2; i++) {
         if (s->h_rays[i]) cudaFreeHost(s->h_rays[i]);
         if (s->h_hits[i]) cudaFreeHost(s->h_hits[i]);
@@ -341,6 +357,8 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         if (e[0] >= 167 || e[1] >= 167 || e[2] >= 167) s->force_exact = true;   // scale = 2^(e-127) >= 2^40
     }
     s->tri_weight = (uint32_t)env_int("TRAY_CUDA_TRI_WEIGHT", 4);
+    s->gen_min = (uint32_t)env_int("TRAY_CUDA_GEN_MIN", 4);
+    s->overlap_default = env_int("TRAY_CUDA_OVERLAP", 0) != 0;
     s->pool = env_int("TRAY_CUDA_POOL", 0) != 0;
     s->pool_refill_min = (uint32_t)env_int("TRAY_CUDA_POOL_REFILL_MIN", 8);
     s->pool_tri_weight = (uint32_t)env_int("TRAY_CUDA_POOL_TRI_WEIGHT", 1);
@@ -719,6 +737,7 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     const bool bounce = (flags & TRAY_RENDER_BOUNCE) != 0, rgba = (flags & TRAY_RENDER_RGBA) != 0;
     const bool keep_rays = (flags & TRAY_RENDER_KEEP_RAYS) != 0;
     const bool any_ao = (flags & TRAY_RENDER_ANYHIT_AO) != 0;
+    const bool overlap = bounce && !any_ao && ((flags & TRAY_RENDER_OVERLAP) != 0 || s->overlap_default);
     if (items_cap > s->f_cap || (keep_rays && !s->d_brays_item)) {
         const uint64_t cap = items_cap > s->f_cap ? items_cap : s->f_cap;
         cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba);
@@ -760,13 +779,24 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
         T.frame_w = w; T.frame_h = h; T.frame_tiles_x = F.tiles_x; T.frame_shard = shard; T.frame_shards = shards;
     };
     P.rgba_out = (rgba && !bounce) ? rgba_dst : nullptr; P.shade_mode = SHADE_PRIMARY;
+    if (overlap) {
+        // one launch for the whole frame (trace_kernel<FRAME>): the bounce rays of finished tiles fill the primary pass's drain
+        if (!s->d_units) CU(cudaMalloc(&s->d_units, sizeof(uint32_t)));
+        CU(cudaMemsetAsync(s->d_units, 0, sizeof(uint32_t), s->stream));
+        CU(cudaMemsetAsync(s->d_primary, 0xff, (size_t)F.n_items * sizeof(tray_hit), s->stream));     // "not there yet" for every primary hit
+        P.rgba_out = rgba ? rgba_dst : nullptr;
+        P.frame = F; P.bounce_out = s->d_bounce; P.rays_by_item = keep_rays ? s->d_brays_item : nullptr; P.gen_min = s->gen_min;
+        P.gen_rays = s->d_brays;
+        P.unit_cursor = s->d_units; P.n_units = (uint32_t)(F.n_items / 32);
+    }
     if (P.rgba_out) set_frame(P);
-    int rc = launch(s, P, s->stream, 0);
+    int rc = launch(s, P, s->stream, 0, false, false, overlap);
     if (rc) return rc;
     if (timed) CU(cudaEventRecord(s->ev[1], s->stream));
+    if (overlap && timed) CU(cudaEventRecord(s->ev[2], s->stream));
 
     // ---- bounce: generate + compact rays of hit pixels, trace ----
-    if (bounce) {
+    if (bounce && !overlap) {
         CU(cudaMemsetAsync(d_nbrays, 0, sizeof(uint32_t), s->stream));
         auto gen = s->tri_stride == 64 ? tray::raygen_bounce_kernel<64> : s->tri_stride == 24 ? tray::raygen_bounce_kernel<24> : tray::raygen_bounce_kernel<48>;
         gen<<<(F.n_items + BOUNCE_BLOCK - 1) / BOUNCE_BLOCK, BOUNCE_BLOCK, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays, s->d_bounce,

@@ -14,7 +14,7 @@ from .host import HIT_DTYPE, RAY_DTYPE, TrayView
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("TRAY_CUDA_LIB") or os.path.join(_HERE, "libtray_cuda.so")   # override: A/B builds only
 
-RENDER_BOUNCE, RENDER_RGBA, RENDER_COUNTERS, RENDER_KEEP_RAYS, RENDER_ANYHIT_AO = 1, 2, 4, 8, 16
+RENDER_BOUNCE, RENDER_RGBA, RENDER_COUNTERS, RENDER_KEEP_RAYS, RENDER_ANYHIT_AO, RENDER_OVERLAP = 1, 2, 4, 8, 16, 32
 
 EXPORTS = (
     "tray_cuda_device_count", "tray_cuda_abi_version", "tray_cuda_scene_create", "tray_cuda_scene_destroy",
