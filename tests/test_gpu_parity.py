@@ -92,6 +92,36 @@ def test_one_launch_frame_kernel_on_synthetic_scenes(monkeypatch, name, seed, si
     render_and_compare(host.Mesh.generate(name, seed, size), 480, 270, use_tlas=tlas, overlap=True)
 
 
+def test_one_launch_frame_kernel_edge_frames(cornell, box):
+    """The frame kernel on frames where its hand-shake has little to chew on: a camera that sees nothing (every group of
+    32 pixels is all misses), a frame smaller than one tile, tile shards (each shard a frame of its own), two frames in a row."""
+    away = host.Camera((0.0, 1.0, 50.0), (0.0, 1.0, 100.0), 40.0)            # looks away from the box
+    p = host.PackedScene(cornell)
+    sc = cuda.TrayCudaScene.from_packed(p)
+    orc = ob.Oracle.from_packed(p)
+    try:
+        for cam, w, h in ((away, 320, 184), (cornell.camera, 7, 3), (cornell.camera, 33, 9)):
+            view = host.view_from_camera(cam, w, h)
+            ref = orc.render(view, w, h, 0)
+            for _ in range(2):
+                sc.render(view, w, h, 0, FLAGS | cuda.RENDER_OVERLAP)
+                sc.sync()
+                out = sc.download(primary=True, bounce=True)
+                for k in ("primary", "bounce"):
+                    assert_hits_identical(out[k], ref[k], f"{k} {w}x{h}")
+        w, h = 200, 120
+        view = host.view_from_camera(cornell.camera, w, h)
+        ref = orc.render(view, w, h, 0)
+        acc = {}
+        for s in range(3):
+            sc.render(view, w, h, 0, FLAGS | cuda.RENDER_OVERLAP, shard=s, shards=3)
+            sc.download(primary=True, bounce=True, into=acc, merge=True)
+        for k in ("primary", "bounce"):
+            assert_hits_identical(acc[k], ref[k], f"{k} shards")
+    finally:
+        sc.close()
+
+
 def test_traverse_random_rays(cornell):
     """Batch operator (Traversable::traverse at batch grain) on rays with exact-zero direction components
     (zero-direction fix-up, query.hlsl:334) and finite [tmin, tmax] windows; ragged batch sizes."""
