@@ -47,6 +47,18 @@ def test_rust_mirror_declares_every_entry_point():
     assert "tray_cuda.cu" in build_rs and "build_gpu.cu" in build_rs and "sm_100a" in build_rs
 
 
+def test_render_flags_agree_between_header_python_and_rust():
+    header = open(os.path.join(ROOT, "include", "tray_cuda.h")).read()
+    flags = {m.group(1): int(m.group(2), 16) for m in re.finditer(r"#define TRAY_RENDER_([A-Z_]+)\s+0x([0-9a-fA-F]+)u", header)}
+    assert set(flags) == {"BOUNCE", "RGBA", "COUNTERS", "KEEP_RAYS", "ANYHIT_AO", "OVERLAP"}
+    assert len(set(flags.values())) == len(flags)
+    rust = open(os.path.join(ROOT, "tray_cuda", "src", "lib.rs")).read()
+    for name, value in flags.items():
+        assert getattr(cuda, "RENDER_" + name) == value, name
+        m = re.search(r"pub const RENDER_" + name + r": u32 = 0x([0-9a-fA-F]+);", rust)
+        assert m and int(m.group(1), 16) == value, name
+
+
 def test_host_library_exports_every_declared_symbol():
     L = host.lib()
     for n in declared_functions("tray_host.h"):
