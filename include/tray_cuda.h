@@ -322,7 +322,9 @@ int tray_cuda_set_counting(tray_scene* scene, int enabled);
  * `render_time_s` seconds with the reference's timing protocol (one untimed warm-up frame before
  * each timed frame when `benchmark` != 0, rt_gpu_software.rs:289-301), and return in *out_min_ms the
  * MIN frame time in ms (rt_gpu_software.rs:339,376) and in *out_mean_ms the mean (rt_cpu.rs:113).
- * `animate` advances frame_count per frame (rt_cpu.rs:95-97).                                     */
+ * `animate` advances frame_count per frame (rt_cpu.rs:95-97).  Before the timed loop a few untimed
+ * frames of each of the two bit-identical frame paths (two launches / TRAY_RENDER_OVERLAP) pick the
+ * faster one for this scene and frame size; the environment variable TRAY_CUDA_OVERLAP=0|1 forces it. */
 int tray_cuda_start(const void* bvh_bytes, uint64_t bvh_len,
                     const void* instance_bytes, uint64_t instance_len,
                     const void* tri_bytes, uint64_t tri_len, uint32_t tri_stride,

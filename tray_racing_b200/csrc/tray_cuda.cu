@@ -961,7 +961,20 @@ int tray_cuda_start(const void* bvh_bytes, uint64_t bvh_len, const void* instanc
                                     use_tlas ? (const uint32_t*)instance_bytes : nullptr,
                                     use_tlas ? (uint32_t)(instance_len / 4) : 0u, tlas_start, device, &s);
     if (rc) return rc;
-    const uint32_t flags = TRAY_RENDER_BOUNCE | TRAY_RENDER_RGBA;
+    uint32_t flags = TRAY_RENDER_BOUNCE | TRAY_RENDER_RGBA;
+    // Two bit-identical ways to render the frame (two launches, or the one-launch frame kernel): which is faster depends on
+    // how long the scene's drain phases are, so a short untimed calibration picks one (TRAY_CUDA_OVERLAP=0/1 forces it).
+    if (!getenv("TRAY_CUDA_OVERLAP")) {
+        float best[2] = { 3.402823466e+38f, 3.402823466e+38f };
+        for (int rep = 0; rep < 4 && !rc; rep++)
+            for (int path = 0; path < 2 && !rc; path++) {
+                float ms = 0.f;
+                rc = tray_cuda_render_timed(s, view, width, height, 0, flags | (path ? TRAY_RENDER_OVERLAP : 0u), 0, 1, &ms);
+                if (!rc && rep > 0 && ms < best[path]) best[path] = ms;          // the first frame of each path allocates
+            }
+        if (rc) { tray_cuda_scene_destroy(s); return rc; }
+        if (best[1] < best[0]) flags |= TRAY_RENDER_OVERLAP;
+    }
     float min_ms = 3.402823466e+38f; double sum = 0; uint32_t frames = 0, frame_count = 0;
     const auto t0 = std::chrono::steady_clock::now();
     for (;;) {
