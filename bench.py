@@ -39,7 +39,7 @@ WORKLOADS = {
                label="C1 kitchen-sized 56,939-tri interior (kitchen.ron camera)"),
     "c2": dict(scene="demoscene", seed=2, w=1920, h=1080, tlas=False, scaling="weak",
                label="C2 demoscene stand-in, 2.10M-tri fBm height field"),
-    "c3": dict(scene="hairball", seed=3, w=1920, h=1080, tlas=False, scaling="weak", overlap=True,
+    "c3": dict(scene="hairball", seed=3, w=1920, h=1080, tlas=False, scaling="weak",
                label="C3 hairball-like 2.88M-tri soup"),
     "c4": dict(scene="sanmiguel", seed=4, w=3840, h=2160, tlas=False, scaling="strong",
                label="C4 San-Miguel-sized 5.08M-tri scene"),
@@ -236,11 +236,27 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     scene.set_stream(stream.cuda_stream)
-    # the one-launch frame kernel (TRAY_RENDER_OVERLAP) where it is the faster way to render the frame: measured -4 % on C3,
-    # +0.5 % / +3.7 % on the kitchen- and San-Miguel-sized scenes, which therefore keep the two-launch path
-    overlap = bool(WL.get("overlap")) and os.environ.get("TRAY_BENCH_OVERLAP", "1") != "0"
-    flags = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA | (cuda.RENDER_OVERLAP if overlap else 0)
+    # two bit-identical ways to render the frame: two launches, or the one-launch frame kernel (TRAY_RENDER_OVERLAP).  Which is
+    # faster depends on the scene's drain phases (measured: -4 % on C3, +0.5 % / +3.7 % on the kitchen- and San-Miguel-sized
+    # scenes), so the bench picks it the way tray_cuda_start does; TRAY_BENCH_OVERLAP=0|1 forces it
     flags2 = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA            # the two-launch path: per-kernel figures, counters
+    forced = os.environ.get("TRAY_BENCH_OVERLAP")
+    if forced is not None:
+        overlap, calib = forced != "0", None
+    else:
+        # untimed calibration, as tray_cuda_start does it: a few frames of each path on this rank's shard, the slowest rank counts
+        best = [float("inf"), float("inf")]
+        for rep in range(5):
+            for path in (0, 1):
+                a, b = scene.render(view, w, h, 0, flags2 | (cuda.RENDER_OVERLAP if path else 0), rank, world, timed=True)
+                if rep > 0:
+                    best[path] = min(best[path], a + b)
+        bt = torch.tensor(best, dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+        calib = {"two_launches_ms": float(bt[0]), "one_launch_ms": float(bt[1])}
+        overlap = calib["one_launch_ms"] < calib["two_launches_ms"]
+    flags = flags2 | (cuda.RENDER_OVERLAP if overlap else 0)
     n_items = cuda.local_items(w, h, rank, world)
     max_items = cuda.local_items(w, h, 0, world)
 
@@ -501,6 +517,7 @@ def run_ours(args):
                        "rays_per_step": {"primary": rays_p, "bounce": rays_b},
                        "frame_path": ("one launch per frame (TRAY_RENDER_OVERLAP: raygen_primary + trace_kernel<FRAME>)" if overlap
                                       else "two launches per frame (raygen_primary, trace, raygen_bounce, trace)"),
+                       "frame_path_calibration": calib if calib is not None else "forced by TRAY_BENCH_OVERLAP",
                        "l2": "flushed between timed steps (256 MiB device write)", "parallelism": f"tile-sharded x{world}, BVH replicated",
                        "exchange": ("peer: kernels store pixels into rank 0's IPC-mapped row-major frame over NVLink + 4-byte all-reduce barrier"
                                     if exchange == "peer" else "NCCL gather of RGBA8 shards to rank 0 + untile per shard") if world > 1
