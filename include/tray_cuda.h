@@ -14,7 +14,8 @@
  * Plain pointers and sizes only; no C++/torch types.  All functions return 0 on success and a
  * negative tray_status on failure; `tray_cuda_last_error()` returns a thread-local message.
  * Host buffers are borrowed for the duration of a call.  A `tray_scene` owns all device memory of
- * ONE device (the BVH is replicated: one scene per GPU, rays sharded by image tile).
+ * ONE device (the BVH is replicated: one scene per GPU, rays sharded by image tile); a `tray_group` is the
+ * one-process form of that (devices[], n_devices — the SURVEY.md §8b proposal).
  * Not re-entrant per scene; distinct scenes may be driven from distinct host threads.
  */
 #ifndef TRAY_CUDA_H
@@ -27,7 +28,7 @@
 extern "C" {
 #endif
 
-#define TRAY_CUDA_ABI_VERSION 2u
+#define TRAY_CUDA_ABI_VERSION 3u
 
 /* ---- status codes -------------------------------------------------------------------------- */
 typedef enum tray_status {
@@ -148,6 +149,19 @@ typedef struct tray_scene_info {
 
 typedef struct tray_scene tray_scene;
 
+/* ---- semantic switches (parity hardening) ---------------------------------------------------------------------------
+ * Three semantics of the reference's CPU path are not in /root/reference but in the un-vendored obvhs crate, and a fourth
+ * differs between that path and its in-tree HLSL twin.  The DEFAULT kernels hard-code the CPU-path reading;
+ * these flags make a scene run the other reading through a slower kernel with the switches at run time, so that a real
+ * obvhs dump can settle each one with a flag.  tests/ and scripts/variant_census.py count how many rays of
+ * every BASELINE config change (prim, t) under each.  Closest-hit tray_cuda_trace* / tray_cuda_render without counters only. */
+#define TRAY_VARIANT_BOX_DIVIDE       0x1u /* box test divides by the direction (query.hlsl:237-242) instead of * 1/d        */
+#define TRAY_VARIANT_TIE_LAST         0x2u /* an equal-t triangle replaces the hit (query.hlsl:120 `tt <= t`), not first-wins */
+#define TRAY_VARIANT_BOX_TMIN_RAY     0x4u /* slab test clamps at ray.tmin instead of EPSILON = 1e-4 (query.hlsl:274,288)     */
+#define TRAY_VARIANT_ZERODIR_BOX_ONLY 0x8u /* the zero-direction patch (query.hlsl:334) feeds the box test only; the triangle
+                                            * test sees the caller's direction                                               */
+int tray_cuda_scene_set_variant(tray_scene* scene, uint32_t variant_flags);
+
 /* ---- device / lifetime ---------------------------------------------------------------------- */
 
 /* Number of CUDA devices visible; 0 (not an error) when there is none. */
@@ -257,6 +271,8 @@ int tray_cuda_render_timed(tray_scene* scene, const tray_view* view, uint32_t wi
 
 /* Number of pixels (= primary rays) shard `shard_index` owns for a width x height frame. */
 uint64_t tray_cuda_shard_pixels(uint32_t width, uint32_t height, uint32_t shard_index, uint32_t shard_count);
+/* Entries of that shard's compact buffers: its tiles x 256 (pixels outside the frame included as padding). */
+uint64_t tray_cuda_shard_items(uint32_t width, uint32_t height, uint32_t shard_index, uint32_t shard_count);
 
 /* Copy the last rendered frame to HOST buffers, each width*height entries in row-major pixel order
  * (pixels that belong to other shards are written as zero bytes).  Any pointer may be NULL.  `bounce_rays` receives the
@@ -274,8 +290,12 @@ int tray_cuda_frame_download(tray_scene* scene, tray_hit* primary, tray_hit* bou
 int tray_cuda_frame_readback_begin(tray_scene* scene, uint8_t* rgba_host, uint32_t slot);
 int tray_cuda_frame_readback_wait(tray_scene* scene, uint32_t slot);
 
-/* Device pointers of the last frame's buffers, for a caller that gathers them itself (NCCL / peer
- * copy).  Layout: row-major full-frame arrays, see tray_cuda_frame_download.                        */
+/* Device pointers of the last frame's buffers, for a caller that gathers them itself (NCCL / peer copy).
+ * Layout: the COMPACT per-shard arrays in tile order — tray_cuda_shard_items(w, h, 0, shards) entries each (every shard's
+ * buffers have shard 0's size), work item j = pixel (tile k = shard + (j / 256) * shards in row-major 32x8 tiles; inside a
+ * tile 8 sub-tiles of 8x4 pixels) — NOT row-major frames: assemble a frame with tray_cuda_untile_rgba (or render into a
+ * frame target).  The pointers are invalidated by a later tray_cuda_render that grows the buffers (a larger frame, fewer
+ * shards, or the first TRAY_RENDER_KEEP_RAYS).                                                                         */
 int tray_cuda_frame_device_ptrs(tray_scene* scene, void** d_primary, void** d_bounce, void** d_rgba);
 
 /* Assemble a row-major width x height RGBA8 frame on the device from the compact buffer of ONE shard
@@ -303,6 +323,22 @@ int tray_cuda_ipc_close(int device, void* d_ptr);
 /* RGBA8 of every later tray_cuda_render goes to `d_frame` (row-major, width*height*4 bytes, on this or a peer
  * device) instead of the scene's compact buffer; NULL restores the compact buffer.  The pointer is borrowed.        */
 int tray_cuda_scene_set_frame_target(tray_scene* scene, void* d_frame);
+
+/* ---- frames in flight ---------------------------------------------------------------------------------------------------
+ * A persistent-warp launch ends with a drain phase: the work cursor runs dry 0.2-0.4 ms before the last long rays finish and the
+ * SMs empty out.  With n = 2 a scene keeps TWO frames in flight: it owns two sets of frame buffers and work
+ * cursors, consecutive tray_cuda_render calls alternate between them, the first on the scene stream and the second on a
+ * stream of its own, so the ray generation and primary pass of frame k+1 fill the SM slots frame k's drain phases leave empty
+ * (the reference's wgpu loop also keeps frames in flight when it is not timing them: queue.submit + frame.present without a
+ * wait, rt_gpu_software.rs:333-335; under --benchmark it waits for each frame's timestamps, :337-338 — which is what
+ * tray_cuda_start does).  Per frame nothing changes — same launches, same results.  "The last frame" of the
+ * download / readback / device_ptrs calls is the frame of the latest tray_cuda_render.  A caller that orders its own work
+ * (a collective, a timing event) against the frames uses the two calls below.  n = 1 (default) restores one frame at a time. */
+int tray_cuda_scene_set_frames_in_flight(tray_scene* scene, uint32_t n);
+/* `stream` (NULL = the scene stream) waits for every frame enqueued so far, whichever slot it runs in. */
+int tray_cuda_scene_fence(tray_scene* scene, void* stream);
+/* Frames enqueued from now on start after the work already enqueued on `stream`. */
+int tray_cuda_scene_after(tray_scene* scene, void* stream);
 
 /* Run all subsequent work of this scene on `stream` (a cudaStream_t as void*; NULL restores the scene's own
  * stream) — lets a host that already owns a stream (torch, NCCL) order its collectives after the kernels. */
@@ -332,6 +368,60 @@ int tray_cuda_start(const void* bvh_bytes, uint64_t bvh_len,
                     const tray_view* view, uint32_t width, uint32_t height,
                     float render_time_s, int benchmark, int animate, int device,
                     float* out_min_ms, float* out_mean_ms, uint32_t* out_frames);
+
+/* ---- CPU-style hit records -----------------------------------------------------------------------------------------------
+ * `Traversable::traverse` returns RayHit {primitive_id, geometry_id, ..} (traversable/src/lib.rs:13-28): on the CPU `--tlas`
+ * path geometry_id is the BLAS (= object) index and primitive_id indexes that BLAS's own BVH-ordered triangle array
+ * (src/cwbvh.rs:144-166), where the GPU path — and tray_hit — carry ONE global triangle index
+ * (`primitive_base_idx += tri_offset`, src/rt_gpu/mod.rs:45-47).  Give the scene the runner's running `tri_offset` per object
+ * (n_geometries + 1 entries, tri_offsets[0] = 0, tri_offsets[n] = n_tris) and convert:
+ *   geometry_id[i]  = g with tri_offsets[g] <= hits[i].prim < tri_offsets[g + 1]     (0xFFFFFFFF for a miss, as RayHit::none())
+ *   primitive_id[i] = hits[i].prim - tri_offsets[g]                                   (0xFFFFFFFF for a miss)
+ * Without a table (n_geometries = 0: a flat scene, `CwBvhScene`) geometry_id is 0xFFFFFFFF and primitive_id = prim.
+ * HOST buffers; the lookup runs on the scene's device. */
+int tray_cuda_scene_set_geometry_offsets(tray_scene* scene, const uint32_t* tri_offsets, uint32_t n_geometries);
+int tray_cuda_hits_to_geometry(tray_scene* scene, const tray_hit* hits, uint64_t n, uint32_t* geometry_id, uint32_t* primitive_id);
+
+/* ---- one process, several GPUs --------------------------------------------------------------------------------------------
+ * The slot `start(..) -> f32` is one call from one host thread (rt_gpu_software.rs:24-32).  A tray_group keeps that shape on
+ * a box with several GPUs: the BVH is replicated on `devices[0..n)` (NULL = devices 0..n-1), the frame's 32x8 tiles are dealt
+ * round-robin to the devices, and every device's traversal kernels store their finished pixels straight into ONE row-major
+ * RGBA8 frame on devices[0] through peer access (cudaDeviceEnablePeerAccess — no IPC handles, no NCCL, no second process).
+ * Frame completion is a set of events: devices[0]'s stream waits for the event each other device records behind its last
+ * launch.  Results are bit-identical to the single-GPU frame (tests/test_gpu_group.py).
+ *   tray_cuda_group_render          enqueue one frame on every device (shard i of n on devices[i]); asynchronous
+ *   tray_cuda_group_render_timed    same, synchronous: *ms_frame = CUDA-event time on devices[0] from before the first launch
+ *                                   (no device starts earlier) to the frame being complete
+ *   tray_cuda_group_readback_begin / _wait   the complete frame -> HOST memory (pinned for overlap), double-buffered like
+ *                                   tray_cuda_frame_readback_begin; with two frames in flight the group alternates two targets
+ *   tray_cuda_group_scene           borrow the scene of devices[i] (counters, hit downloads of its shard, set_variant ..)   */
+typedef struct tray_group tray_group;
+int  tray_cuda_group_create(const void* nodes, uint64_t n_nodes, const void* tris, uint64_t n_tris, uint32_t tri_stride,
+                            const uint32_t* blas_offsets, uint32_t n_instances, uint32_t tlas_start,
+                            const int* devices, int n_devices, tray_group** out_group);
+void tray_cuda_group_destroy(tray_group* group);
+int  tray_cuda_group_size(const tray_group* group);
+int  tray_cuda_group_scene(tray_group* group, int i, tray_scene** out_scene);
+int  tray_cuda_group_set_frames_in_flight(tray_group* group, uint32_t n);
+int  tray_cuda_group_render(tray_group* group, const tray_view* view, uint32_t width, uint32_t height,
+                            uint32_t frame_count, uint32_t flags);
+int  tray_cuda_group_render_timed(tray_group* group, const tray_view* view, uint32_t width, uint32_t height,
+                                  uint32_t frame_count, uint32_t flags, float* ms_frame);
+int  tray_cuda_group_readback_begin(tray_group* group, uint8_t* rgba_host, uint32_t slot);
+int  tray_cuda_group_readback_wait(tray_group* group, uint32_t slot);
+int  tray_cuda_group_frame_ptr(tray_group* group, void** d_frame);      /* devices[0] pointer of the last frame (row-major RGBA8) */
+int  tray_cuda_group_sync(tray_group* group);
+
+/* tray_cuda_start on several GPUs of the box: same arguments (the device list replaces `device`), same timing protocol, the
+ * frame time being tray_cuda_group_render_timed's. */
+int tray_cuda_start_multi(const int* devices, int n_devices,
+                          const void* bvh_bytes, uint64_t bvh_len,
+                          const void* instance_bytes, uint64_t instance_len,
+                          const void* tri_bytes, uint64_t tri_len, uint32_t tri_stride,
+                          uint32_t tlas_start, int use_tlas,
+                          const tray_view* view, uint32_t width, uint32_t height,
+                          float render_time_s, int benchmark, int animate,
+                          float* out_min_ms, float* out_mean_ms, uint32_t* out_frames);
 
 /* Roofline denominators measured on this device: streaming 16-byte read bandwidth (GB/s) over a buffer of `bytes`
  * swept `iters` times by a chip-filling grid.  A buffer well under the L2 size measures L2 bandwidth (the roof the

@@ -69,7 +69,9 @@ static inline void normalize3(float v[3]) {
 /* ---- prepared ray: the state `Ray::new` + traverse_bvh set up once per ray ------------------- */
 typedef struct prep_ray {
     float o[3], d[3], inv[3];
+    float dt[3];        /* the direction the TRIANGLE test sees: d, or the unpatched one (ORC_VARIANT_ZERODIR_BOX_ONLY) */
     float tmin;
+    float box_tmin;     /* lower clamp of the slab test: EPSILON (query.hlsl:274) or ray.tmin (ORC_VARIANT_BOX_TMIN_RAY) */
     uint32_t oct_inv4;
 } prep_ray;
 
@@ -80,8 +82,10 @@ static inline void prepare_ray(const orc_ray* r, prep_ray* p) {
         p->o[a] = r->o[a];
         p->d[a] = (r->d[a] == 0.0f) ? F32_EPSILON : r->d[a];
         p->inv[a] = 1.0f / p->d[a];
+        p->dt[a] = (g_variant & ORC_VARIANT_ZERODIR_BOX_ONLY) ? r->d[a] : p->d[a];
     }
     p->tmin = r->tmin;
+    p->box_tmin = (g_variant & ORC_VARIANT_BOX_TMIN_RAY) ? r->tmin : BOX_EPSILON;
     p->oct_inv4 = (p->d[0] < 0.0f ? 0u : 0x04040404u) | (p->d[1] < 0.0f ? 0u : 0x02020202u) |
                   (p->d[2] < 0.0f ? 0u : 0x01010101u);
 }
@@ -120,7 +124,7 @@ static inline uint32_t node_intersect_scalar(const uint8_t* n, const prep_ray* r
                 tmin3[a] = (float)qn * adj_inv[a] + adj_org[a];        /* query.hlsl:285 (mul, add) */
                 tmax3[a] = (float)qf * adj_inv[a] + adj_org[a];        /* query.hlsl:286 */
             }
-            float tmin = fmaxf(fmaxf(fmaxf(tmin3[0], tmin3[1]), tmin3[2]), BOX_EPSILON);   /* :288 */
+            float tmin = fmaxf(fmaxf(fmaxf(tmin3[0], tmin3[1]), tmin3[2]), r->box_tmin);   /* :288 */
             float tmax = fminf(fminf(fminf(tmax3[0], tmax3[1]), tmax3[2]), max_distance);  /* :289 */
             if (tmin <= tmax) {                                                            /* :291 */
                 uint32_t child_bits = (child_bits4 >> (8 * j)) & 0xffu;
@@ -154,7 +158,7 @@ static uint32_t node_intersect_avx2(const uint8_t* n, const prep_ray* r, float m
         tn[a] = _mm256_add_ps(_mm256_mul_ps(neg ? qhi : qlo, ai), ao);
         tf[a] = _mm256_add_ps(_mm256_mul_ps(neg ? qlo : qhi, ai), ao);
     }
-    const __m256 tmin = _mm256_max_ps(_mm256_max_ps(_mm256_max_ps(tn[0], tn[1]), tn[2]), _mm256_set1_ps(BOX_EPSILON));
+    const __m256 tmin = _mm256_max_ps(_mm256_max_ps(_mm256_max_ps(tn[0], tn[1]), tn[2]), _mm256_set1_ps(r->box_tmin));
     const __m256 tmax = _mm256_min_ps(_mm256_min_ps(_mm256_min_ps(tf[0], tf[1]), tf[2]), _mm256_set1_ps(max_distance));
     unsigned hits = (unsigned)_mm256_movemask_ps(_mm256_cmp_ps(tmin, tmax, _CMP_LE_OQ));
     const uint32_t oct = r->oct_inv4 & 0xffu;
@@ -225,8 +229,8 @@ static inline float tri_intersect(const uint8_t* rec, uint32_t stride, const pre
     if (stride == 64) { ng[0] = load_f32(rec + 48); ng[1] = load_f32(rec + 52); ng[2] = load_f32(rec + 56); }
     else cross3(e1, e2, ng);                                           /* query.hlsl:93 */
     float c[3] = { v0[0] - r->o[0], v0[1] - r->o[1], v0[2] - r->o[2] };  /* :96 */
-    float rr[3]; cross3(r->d, c, rr);                                  /* :97 */
-    float inv_det = 1.0f / dot3(ng, r->d);                             /* :98 */
+    float rr[3]; cross3(r->dt, c, rr);                                 /* :97 */
+    float inv_det = 1.0f / dot3(ng, r->dt);                            /* :98 */
     float u = dot3(rr, e2) * inv_det;                                  /* :100 */
     float v = dot3(rr, e1) * inv_det;                                  /* :101 */
     float w = 1.0f - u - v;                                            /* :102 */

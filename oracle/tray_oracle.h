@@ -53,6 +53,9 @@ typedef struct orc_totals { uint64_t rays, nodes, tris, insts, hits; } orc_total
 #define ORC_VARIANT_DEFAULT     0u
 #define ORC_VARIANT_BOX_DIVIDE  0x1u  /* box test divides by dir (query.hlsl:237-242) instead of * inv_dir */
 #define ORC_VARIANT_TIE_LAST    0x2u  /* equal-t replaces (query.hlsl:120) instead of first-wins            */
+#define ORC_VARIANT_BOX_TMIN_RAY 0x4u /* slab test clamps at ray.tmin instead of EPSILON = 1e-4 (query.hlsl:274,288) */
+#define ORC_VARIANT_ZERODIR_BOX_ONLY 0x8u /* the zero-direction patch (query.hlsl:334) feeds the box test only; the triangle
+                                           * test sees the caller's direction (as if obvhs `Ray::new` only guarded 1/d)  */
 void orc_set_variant(uint32_t flags);
 
 unsigned orc_abi_version(void);

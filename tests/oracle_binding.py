@@ -18,6 +18,8 @@ COUNT_DTYPE = np.dtype([("nodes", "<u4"), ("tris", "<u4"), ("insts", "<u4")])
 INVALID_PRIM = 0xFFFFFFFF
 VARIANT_BOX_DIVIDE = 1
 VARIANT_TIE_LAST = 2
+VARIANT_BOX_TMIN_RAY = 4
+VARIANT_ZERODIR_BOX_ONLY = 8
 RENDER_BOUNCE = 1
 RENDER_RGBA = 2
 

@@ -25,7 +25,7 @@ def test_cuda_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/tray_cuda.h but not exported by libtray_cuda.so"
     assert sorted(cuda.EXPORTS) == names
-    assert L.tray_cuda_abi_version() == 2
+    assert L.tray_cuda_abi_version() == 3
 
 
 def test_rust_mirror_declares_every_entry_point():

@@ -15,23 +15,50 @@ def bits(a):
     return np.ascontiguousarray(a).view(np.uint32)
 
 
-def test_c3_hairball_full_frame_against_oracle():
-    m = host.Mesh.generate("hairball", 3, 1.0)
-    assert m.n_tris == 2880000
-    p = host.PackedScene(m)
-    w, h = 1920, 1080
-    view = host.view_from_camera(m.camera, w, h)
+def full_frame_against_oracle(name, seed, w, h, n_tris=None, tlas=False):
+    """Every pixel of a BASELINE-size frame, both frame paths (two launches, one-launch OVERLAP kernel), counters included."""
+    m = host.Mesh.generate(name, seed, 1.0)
+    if n_tris is not None:
+        assert m.n_tris == n_tris
+    p = host.PackedScene(m, use_tlas=tlas)
+    view = host.view_from_camera(m.camera, w, h, p.tlas_start)
+    ref = ob.Oracle.from_packed(p).render(view, w, h, 0)
     sc = cuda.TrayCudaScene.from_packed(p)
     try:
-        sc.render(view, w, h, 0, cuda.RENDER_BOUNCE | cuda.RENDER_COUNTERS)
-        out = sc.download(primary=True, bounce=True)
-        cp, cb = sc.counters()
+        for extra in (0, cuda.RENDER_OVERLAP):
+            sc.render(view, w, h, 0, cuda.RENDER_BOUNCE | cuda.RENDER_COUNTERS | extra)
+            sc.sync()
+            out = sc.download(primary=True, bounce=True)
+            cp, cb = sc.counters()
+            for k in ("primary", "bounce"):
+                assert (out[k]["prim"] == ref[k]["prim"]).all() and (bits(out[k]["t"]) == bits(ref[k]["t"])).all(), (name, k, extra)
+            for got, want in ((cp, ref["primary_totals"]), (cb, ref["bounce_totals"])):
+                assert got["rays"] == want["rays"] and got["hits"] == want["hits"]
+                assert got["nodes"] == want["nodes"] and got["tris"] == want["tris"] and got["instances"] == want["insts"]
     finally:
         sc.close()
-    ref = ob.Oracle.from_packed(p).render(view, w, h, 0)
-    for k in ("primary", "bounce"):
-        assert (out[k]["prim"] == ref[k]["prim"]).all() and (bits(out[k]["t"]) == bits(ref[k]["t"])).all()
-    assert cp["nodes"] == ref["primary_totals"]["nodes"] and cb["tris"] == ref["bounce_totals"]["tris"]
+    return ref
+
+
+def test_c3_hairball_full_frame_against_oracle():
+    ref = full_frame_against_oracle("hairball", 3, 1920, 1080, n_tris=2880000)
+    assert ref["primary_totals"]["hits"] > 800000
+
+
+def test_c1_kitchen_full_frame_against_oracle():
+    ref = full_frame_against_oracle("kitchen", 1, 1920, 1080, n_tris=56939)
+    assert ref["primary_totals"]["hits"] == 1920 * 1080               # an interior: every pixel hits
+
+
+def test_c2_demoscene_full_size_full_frame_against_oracle():
+    ref = full_frame_against_oracle("demoscene", 2, 1920, 1080)
+    assert ref["primary_totals"]["hits"] > 500000
+
+
+def test_c4_sanmiguel_full_4k_frame_against_oracle():
+    """All 8.3 M primary rays and their bounce rays of the 5.08 M-triangle scene at 3840x2160 — not a sample."""
+    ref = full_frame_against_oracle("sanmiguel", 4, 3840, 2160, n_tris=5075977)
+    assert ref["primary_totals"]["rays"] == 3840 * 2160
 
 
 @pytest.mark.parametrize("name,seed,w,h", [("sanmiguel", 4, 3840, 2160), ("caldera", 5, 3840, 2160)])

@@ -399,3 +399,34 @@ def test_oracle_matches_a_line_by_line_transliteration_of_the_shader(cornell, bo
                 assert cnt["nodes"][i] == nn and cnt["tris"][i] == nt and cnt["insts"][i] == ni, (i, cnt[i], nn, nt, ni)
     finally:
         ob.set_variant(0)
+
+
+def test_new_variant_switches_touch_only_what_they_name(cornell):
+    """ORC_VARIANT_BOX_TMIN_RAY: with the slab test clamped at ray.tmin = 0 instead of 1e-4 a superset of the boxes is entered;
+    (prim, t) can only change for rays that start closer than 1e-4 to a surface — the default never enters a box that ends before
+    t = 1e-4, so it cannot see a hit that close (the bounce rays of rt_cpu.rs:67 start 0.01 off the surface for that reason).
+    ORC_VARIANT_ZERODIR_BOX_ONLY: only rays with an exact-zero direction component can change; those that do keep their
+    primitive, with t moved by the 1.19e-7 tilt of the patched component — up to ~1e-5 relative on a surface the ray grazes,
+    i.e. AT the north_star tolerance, which is why this switch is the one the census (scripts/variant_census.py) watches."""
+    p = host.PackedScene(cornell)
+    o = ob.Oracle.from_packed(p)
+    rays = random_rays(60000, 77, axis_fraction=0.2, bounded_fraction=0.0)
+    a, ca, _ = o.trace(rays, counts=True)
+    try:
+        ob.set_variant(ob.VARIANT_BOX_TMIN_RAY)
+        b, cb, _ = o.trace(rays, counts=True)
+        diff = (a["prim"] != b["prim"]) | (a["t"].view(np.uint32) != b["t"].view(np.uint32))
+        assert diff.sum() <= 5 and (b["t"][diff] < 1.0001e-4).all()        # only hits the default cannot see: t < 1e-4
+        assert int(cb["nodes"].sum()) >= int(ca["nodes"].sum())            # clamp at 0 <= 1e-4: a superset of the boxes
+        ob.set_variant(ob.VARIANT_ZERODIR_BOX_ONLY)
+        c = o.trace(rays)
+    finally:
+        ob.set_variant(0)
+    zero = (rays["d"] == 0).any(axis=1)
+    changed = (a["prim"] != c["prim"]) | (a["t"].view(np.uint32) != c["t"].view(np.uint32))
+    assert zero.sum() >= 10000 and not changed[~zero].any()
+    assert changed.any()                                                   # the switch is not a no-op
+    both = changed & (a["prim"] != ob.INVALID_PRIM) & (c["prim"] != ob.INVALID_PRIM)
+    rel = np.abs(a["t"][both] - c["t"][both]) / np.abs(a["t"][both])
+    assert (rel <= 1e-4).all() and (rel <= 1e-5).mean() > 0.9
+    assert (a["prim"][both] == c["prim"][both]).mean() > 0.99

@@ -25,6 +25,7 @@ pub struct TrayView {
 pub struct TrayTri48 { pub v0: [f32; 3], pub p0: f32, pub e1: [f32; 3], pub p1: f32, pub e2: [f32; 3], pub p2: f32 }
 
 #[repr(C)] pub struct TrayScene { _private: [u8; 0] }
+#[repr(C)] pub struct TrayGroup { _private: [u8; 0] }
 
 /// `tray_build_stats` of include/tray_cuda.h
 #[repr(C)]
@@ -53,6 +54,11 @@ pub const RENDER_COUNTERS: u32 = 0x4;
 pub const RENDER_KEEP_RAYS: u32 = 0x8;
 pub const RENDER_ANYHIT_AO: u32 = 0x10;
 pub const RENDER_OVERLAP: u32 = 0x20;
+/// semantic switches of `tray_cuda_scene_set_variant` (include/tray_cuda.h TRAY_VARIANT_*)
+pub const VARIANT_BOX_DIVIDE: u32 = 0x1;
+pub const VARIANT_TIE_LAST: u32 = 0x2;
+pub const VARIANT_BOX_TMIN_RAY: u32 = 0x4;
+pub const VARIANT_ZERODIR_BOX_ONLY: u32 = 0x8;
 
 extern "C" {
     pub fn tray_cuda_abi_version() -> u32;
@@ -100,6 +106,33 @@ extern "C" {
     pub fn tray_cuda_scene_download(scene: *mut TrayScene, nodes: *mut c_void, tris: *mut c_void, prim_indices: *mut u32) -> c_int;
     pub fn tray_cuda_frame_download(scene: *mut TrayScene, primary: *mut TrayHit, bounce: *mut TrayHit,
         bounce_rays: *mut TrayRay, rgba: *mut u8) -> c_int;
+    pub fn tray_cuda_scene_set_variant(scene: *mut TrayScene, variant_flags: u32) -> c_int;
+    pub fn tray_cuda_shard_items(width: u32, height: u32, shard_index: u32, shard_count: u32) -> u64;
+    pub fn tray_cuda_scene_set_frames_in_flight(scene: *mut TrayScene, n: u32) -> c_int;
+    pub fn tray_cuda_scene_fence(scene: *mut TrayScene, stream: *mut c_void) -> c_int;
+    pub fn tray_cuda_scene_after(scene: *mut TrayScene, stream: *mut c_void) -> c_int;
+    pub fn tray_cuda_scene_set_geometry_offsets(scene: *mut TrayScene, tri_offsets: *const u32, n_geometries: u32) -> c_int;
+    pub fn tray_cuda_hits_to_geometry(scene: *mut TrayScene, hits: *const TrayHit, n: u64, geometry_id: *mut u32,
+        primitive_id: *mut u32) -> c_int;
+    pub fn tray_cuda_group_create(nodes: *const c_void, n_nodes: u64, tris: *const c_void, n_tris: u64, tri_stride: u32,
+        blas_offsets: *const u32, n_instances: u32, tlas_start: u32, devices: *const c_int, n_devices: c_int,
+        out: *mut *mut TrayGroup) -> c_int;
+    pub fn tray_cuda_group_destroy(group: *mut TrayGroup);
+    pub fn tray_cuda_group_size(group: *const TrayGroup) -> c_int;
+    pub fn tray_cuda_group_scene(group: *mut TrayGroup, i: c_int, out_scene: *mut *mut TrayScene) -> c_int;
+    pub fn tray_cuda_group_set_frames_in_flight(group: *mut TrayGroup, n: u32) -> c_int;
+    pub fn tray_cuda_group_render(group: *mut TrayGroup, view: *const TrayView, width: u32, height: u32, frame_count: u32,
+        flags: u32) -> c_int;
+    pub fn tray_cuda_group_render_timed(group: *mut TrayGroup, view: *const TrayView, width: u32, height: u32, frame_count: u32,
+        flags: u32, ms_frame: *mut f32) -> c_int;
+    pub fn tray_cuda_group_readback_begin(group: *mut TrayGroup, rgba_host: *mut u8, slot: u32) -> c_int;
+    pub fn tray_cuda_group_readback_wait(group: *mut TrayGroup, slot: u32) -> c_int;
+    pub fn tray_cuda_group_frame_ptr(group: *mut TrayGroup, d_frame: *mut *mut c_void) -> c_int;
+    pub fn tray_cuda_group_sync(group: *mut TrayGroup) -> c_int;
+    pub fn tray_cuda_start_multi(devices: *const c_int, n_devices: c_int, bvh: *const c_void, bvh_len: u64, inst: *const c_void,
+        inst_len: u64, tris: *const c_void, tri_len: u64, tri_stride: u32, tlas_start: u32, use_tlas: c_int,
+        view: *const TrayView, width: u32, height: u32, render_time_s: f32, benchmark: c_int, animate: c_int,
+        out_min_ms: *mut f32, out_mean_ms: *mut f32, out_frames: *mut u32) -> c_int;
     pub fn tray_cuda_start(bvh: *const c_void, bvh_len: u64, inst: *const c_void, inst_len: u64, tris: *const c_void,
         tri_len: u64, tri_stride: u32, tlas_start: u32, use_tlas: c_int, view: *const TrayView, width: u32, height: u32,
         render_time_s: f32, benchmark: c_int, animate: c_int, device: c_int,
@@ -117,16 +150,28 @@ fn check(rc: c_int) {
 pub struct StartArgs<'a> {
     pub bvh_bytes: &'a [u8], pub instance_bytes: &'a [u8], pub tri_bytes: &'a [u8], pub tlas_start: u32, pub use_tlas: bool,
     pub view: TrayView, pub width: u32, pub height: u32, pub render_time: f32, pub benchmark: bool, pub animate: bool,
+    /// bytes per triangle record in `tri_bytes`: 48 / 64 (f32 `RtTriangle`, the parity path) or 24 (`RtCompressedTriangle`)
+    pub tri_stride: u32,
+    /// CUDA devices to render on; one entry = `tray_cuda_start`, several = `tray_cuda_start_multi` (tiles dealt round-robin)
+    pub devices: &'a [i32],
 }
 
 /// Drop-in for `rt_gpu_software::start`: returns the min frame time in ms.
 pub fn start(a: StartArgs) -> f32 {
     let (mut min_ms, mut mean_ms, mut frames) = (0f32, 0f32, 0u32);
+    let devices: &[i32] = if a.devices.is_empty() { &[0] } else { a.devices };
     check(unsafe {
-        tray_cuda_start(a.bvh_bytes.as_ptr().cast(), a.bvh_bytes.len() as u64, a.instance_bytes.as_ptr().cast(),
-            a.instance_bytes.len() as u64, a.tri_bytes.as_ptr().cast(), a.tri_bytes.len() as u64, 48, a.tlas_start,
-            a.use_tlas as c_int, &a.view, a.width, a.height, a.render_time, a.benchmark as c_int, a.animate as c_int, 0,
-            &mut min_ms, &mut mean_ms, &mut frames)
+        if devices.len() == 1 {
+            tray_cuda_start(a.bvh_bytes.as_ptr().cast(), a.bvh_bytes.len() as u64, a.instance_bytes.as_ptr().cast(),
+                a.instance_bytes.len() as u64, a.tri_bytes.as_ptr().cast(), a.tri_bytes.len() as u64, a.tri_stride, a.tlas_start,
+                a.use_tlas as c_int, &a.view, a.width, a.height, a.render_time, a.benchmark as c_int, a.animate as c_int,
+                devices[0], &mut min_ms, &mut mean_ms, &mut frames)
+        } else {
+            tray_cuda_start_multi(devices.as_ptr(), devices.len() as c_int, a.bvh_bytes.as_ptr().cast(), a.bvh_bytes.len() as u64,
+                a.instance_bytes.as_ptr().cast(), a.instance_bytes.len() as u64, a.tri_bytes.as_ptr().cast(),
+                a.tri_bytes.len() as u64, a.tri_stride, a.tlas_start, a.use_tlas as c_int, &a.view, a.width, a.height,
+                a.render_time, a.benchmark as c_int, a.animate as c_int, &mut min_ms, &mut mean_ms, &mut frames)
+        }
     });
     min_ms
 }
@@ -191,6 +236,17 @@ impl Scene {
         let mut px = vec![0u8; width as usize * height as usize * 4];
         check(unsafe { tray_cuda_frame_download(self.raw, std::ptr::null_mut(), std::ptr::null_mut(), std::ptr::null_mut(), px.as_mut_ptr()) });
         px
+    }
+
+    /// CPU-style hit records of a `--tlas` scene (`CwBvhTlasScene::traverse`, src/cwbvh.rs:144-166): `tri_offsets` is the runner's
+    /// running `tri_offset` per object (src/rt_gpu/mod.rs:45-47) plus the total; returns (geometry_id, primitive_id) per hit.
+    pub fn set_geometry_offsets(&mut self, tri_offsets: &[u32]) {
+        check(unsafe { tray_cuda_scene_set_geometry_offsets(self.raw, tri_offsets.as_ptr(), (tri_offsets.len().max(1) - 1) as u32) });
+    }
+    pub fn hits_to_geometry(&mut self, hits: &[TrayHit]) -> (Vec<u32>, Vec<u32>) {
+        let (mut g, mut p) = (vec![u32::MAX; hits.len()], vec![u32::MAX; hits.len()]);
+        check(unsafe { tray_cuda_hits_to_geometry(self.raw, hits.as_ptr(), hits.len() as u64, g.as_mut_ptr(), p.as_mut_ptr()) });
+        (g, p)
     }
 
     pub fn counters(&mut self) -> (TrayCounters, TrayCounters) {

@@ -82,6 +82,7 @@ struct TraceParams {
     float zero;                               // 0.0f, passed at run time (see child_test_fast)
     uint32_t refill_min;                      // idle lanes needed before a partial warp refills
     uint32_t tri_weight;                      // vote: triangle phase when n_tri * tri_weight >= n_node
+    uint32_t variant;                         // MODE 1 kernels only: TRAY_VARIANT_* switches (tray_cuda_scene_set_variant)
     // FRAME kernel only (one launch per frame: bounce rays of finished 32-item groups start while the primary pass drains)
     FrameParams frame;                        // camera, frame geometry, frame_count (rays = the primary rays in item order)
     tray_hit* __restrict__ bounce_out;        // bounce hits by item
@@ -146,13 +147,20 @@ struct RayConst {
     float ox, oy, oz, dx, dy, dz, ix, iy, iz, tmin;
     uint32_t oct_inv4;
     bool wide;      // |1/d| >= 2^64 on some axis: 2^23 * adj_inv could overflow, use the unfused node test
+    // MODE 1 (semantic variants, tray_cuda_scene_set_variant) only — dead registers in every other kernel:
+    float tdx, tdy, tdz;    // the direction the TRIANGLE test sees (the caller's, when the zero patch feeds the box test only)
+    float box_tmin;         // lower clamp of the slab test: 1e-4 (query.hlsl:274) or ray.tmin
 };
 
-__device__ __forceinline__ void prepare_ray(RayConst& r, float ox, float oy, float oz, float dx, float dy, float dz, float tmin) {
+__device__ __forceinline__ void prepare_ray(RayConst& r, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
+                                            uint32_t variant = 0u) {
     r.ox = ox; r.oy = oy; r.oz = oz; r.tmin = tmin;
     r.dx = dx == 0.0f ? F32_EPS_ : dx;           // query.hlsl:334
     r.dy = dy == 0.0f ? F32_EPS_ : dy;
     r.dz = dz == 0.0f ? F32_EPS_ : dz;
+    const bool raw = (variant & TRAY_VARIANT_ZERODIR_BOX_ONLY) != 0u;
+    r.tdx = raw ? dx : r.dx; r.tdy = raw ? dy : r.dy; r.tdz = raw ? dz : r.dz;
+    r.box_tmin = (variant & TRAY_VARIANT_BOX_TMIN_RAY) ? tmin : BOX_EPS_;
     r.ix = __fdiv_rn(1.0f, r.dx); r.iy = __fdiv_rn(1.0f, r.dy); r.iz = __fdiv_rn(1.0f, r.dz);   // Ray::inv_direction
     r.oct_inv4 = (r.dx < 0.0f ? 0u : 0x04040404u) | (r.dy < 0.0f ? 0u : 0x02020202u) |
                  (r.dz < 0.0f ? 0u : 0x01010101u);                                              // query.hlsl:314-326
@@ -163,28 +171,32 @@ __device__ __forceinline__ void prepare_ray(RayConst& r, float ox, float oy, flo
 template <int J>
 __device__ __forceinline__ uint32_t child_test(uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz,
                                                float ax, float ay, float az, float bx, float by, float bz, float tmax,
-                                               uint32_t child_bits4, uint32_t bit_index4, uint32_t k4b) {
+                                               uint32_t child_bits4, uint32_t bit_index4, uint32_t k4b, float box_tmin) {
     // tmin3 = q_near * adj_inv + adj_org, tmax3 = q_far * adj_inv + adj_org: mul, then add (query.hlsl:285-286)
     const float tnx = add(mul(byte_f32<J>(nx, k4b), ax), bx), tfx = add(mul(byte_f32<J>(fx, k4b), ax), bx);
     const float tny = add(mul(byte_f32<J>(ny, k4b), ay), by), tfy = add(mul(byte_f32<J>(fy, k4b), ay), by);
     const float tnz = add(mul(byte_f32<J>(nz, k4b), az), bz), tfz = add(mul(byte_f32<J>(fz, k4b), az), bz);
-    const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), BOX_EPS_);      // query.hlsl:288
+    const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), box_tmin);      // query.hlsl:288
     const float tfar = fminf(fminf(fminf(tfx, tfy), tfz), tmax);          // query.hlsl:289
     // child_bits << bit_index (query.hlsl:291-298); bit_index bytes are < 32, so the shifter's wrap is harmless
     const uint32_t contrib = byte_u32<J>(child_bits4) << ((bit_index4 >> (8 * J)) & 31u);
     return tmin <= tfar ? contrib : 0u;
 }
 
+// `box_tmin` / `divide`: the slab test's lower clamp and the HLSL's divide-by-direction form (query.hlsl:237-242) — MODE 1 only
 __device__ __forceinline__ uint32_t node_test(const RayConst& r, float tmax, const uint4& n0, const uint4& n1,
-                                              const uint4& n2, const uint4& n3, const uint4& n4, uint32_t k4b) {
+                                              const uint4& n2, const uint4& n3, const uint4& n4, uint32_t k4b,
+                                              float box_tmin = BOX_EPS_, bool divide = false) {
     const uint32_t e = n0.w;
     // adj_inv = 2^(e-127) * inv_dir ; adj_org = (p - origin) * inv_dir  (CPU path: cached reciprocal; SURVEY §8c vi)
-    const float ax = mul(__uint_as_float((e & 0xffu) << 23), r.ix);
-    const float ay = mul(__uint_as_float(((e >> 8) & 0xffu) << 23), r.iy);
-    const float az = mul(__uint_as_float(((e >> 16) & 0xffu) << 23), r.iz);
-    const float bx = mul(sub(__uint_as_float(n0.x), r.ox), r.ix);
-    const float by = mul(sub(__uint_as_float(n0.y), r.oy), r.iy);
-    const float bz = mul(sub(__uint_as_float(n0.z), r.oz), r.iz);
+    const float sx_ = __uint_as_float((e & 0xffu) << 23), sy_ = __uint_as_float(((e >> 8) & 0xffu) << 23), sz_ = __uint_as_float(((e >> 16) & 0xffu) << 23);
+    const float px_ = sub(__uint_as_float(n0.x), r.ox), py_ = sub(__uint_as_float(n0.y), r.oy), pz_ = sub(__uint_as_float(n0.z), r.oz);
+    const float ax = divide ? __fdiv_rn(sx_, r.dx) : mul(sx_, r.ix);
+    const float ay = divide ? __fdiv_rn(sy_, r.dy) : mul(sy_, r.iy);
+    const float az = divide ? __fdiv_rn(sz_, r.dz) : mul(sz_, r.iz);
+    const float bx = divide ? __fdiv_rn(px_, r.dx) : mul(px_, r.ix);
+    const float by = divide ? __fdiv_rn(py_, r.dy) : mul(py_, r.iy);
+    const float bz = divide ? __fdiv_rn(pz_, r.dz) : mul(pz_, r.iz);
     const bool sx = r.dx < 0.0f, sy = r.dy < 0.0f, sz = r.dz < 0.0f;
     uint32_t mask = 0;
 #pragma unroll
@@ -200,10 +212,10 @@ __device__ __forceinline__ uint32_t node_test(const RayConst& r, float tmax, con
         const uint32_t nx = sx ? hix : lox, fx = sx ? lox : hix;                   // query.hlsl:266-273
         const uint32_t ny = sy ? hiy : loy, fy = sy ? loy : hiy;
         const uint32_t nz = sz ? hiz : loz, fz = sz ? loz : hiz;
-        mask |= child_test<0>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b);
-        mask |= child_test<1>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b);
-        mask |= child_test<2>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b);
-        mask |= child_test<3>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b);
+        mask |= child_test<0>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b, box_tmin);
+        mask |= child_test<1>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b, box_tmin);
+        mask |= child_test<2>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b, box_tmin);
+        mask |= child_test<3>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, bit_index4, k4b, box_tmin);
     }
     return mask;
 }
@@ -329,8 +341,10 @@ __device__ __forceinline__ void tri_load(const uint4* __restrict__ tris, uint32_
 }
 
 // ---- triangle test: RtTriangle::intersect, twin query.hlsl:89-129; returns t or +inf -------------
-template <int TRI_STRIDE>
+// VARIANT_DIR: the test reads its direction from r.tdx/tdy/tdz (MODE 1) instead of the box test's r.dx/dy/dz
+template <int TRI_STRIDE, bool VARIANT_DIR = false>
 __device__ __forceinline__ float tri_test(const RayConst& r, float tmax, const uint4* __restrict__ tris, uint32_t prim) {
+    const float ddx = VARIANT_DIR ? r.tdx : r.dx, ddy = VARIANT_DIR ? r.tdy : r.dy, ddz = VARIANT_DIR ? r.tdz : r.dz;
     float v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z;
     tri_load<TRI_STRIDE>(tris, prim, v0x, v0y, v0z, e1x, e1y, e1z, e2x, e2y, e2z);
     float ngx, ngy, ngz;
@@ -341,8 +355,8 @@ __device__ __forceinline__ float tri_test(const RayConst& r, float tmax, const u
         cross3(e1x, e1y, e1z, e2x, e2y, e2z, ngx, ngy, ngz);                       // :93
     }
     const float cx = sub(v0x, r.ox), cy = sub(v0y, r.oy), cz = sub(v0z, r.oz);     // :96
-    float rx, ry, rz; cross3(r.dx, r.dy, r.dz, cx, cy, cz, rx, ry, rz);            // :97
-    const float inv_det = __fdiv_rn(1.0f, dot3(ngx, ngy, ngz, r.dx, r.dy, r.dz));  // :98
+    float rx, ry, rz; cross3(ddx, ddy, ddz, cx, cy, cz, rx, ry, rz);               // :97
+    const float inv_det = __fdiv_rn(1.0f, dot3(ngx, ngy, ngz, ddx, ddy, ddz));     // :98
     const float u = mul(dot3(rx, ry, rz, e2x, e2y, e2z), inv_det);                 // :100
     const float v = mul(dot3(rx, ry, rz, e1x, e1y, e1z), inv_det);                 // :101
     const float w = sub(sub(1.0f, u), v);                                          // :102
@@ -561,6 +575,19 @@ __global__ void __launch_bounds__(BOUNCE_BLOCK) raygen_bounce_kernel(const __gri
     }
 }
 
+// FRAME kernel hand-shake: a primary hit record is published and polled as ONE 64-bit scalar access ({t, prim} packed),
+// which the PTX memory model makes single-copy atomic (a .v2.u32 pair is two accesses in unspecified order).
+__device__ __forceinline__ void publish_hit(tray_hit* dst, const tray_hit& h) {
+    const unsigned long long v = (unsigned long long)__float_as_uint(h.t) | ((unsigned long long)h.prim << 32);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" :: "l"(dst), "l"(v) : "memory");
+}
+__device__ __forceinline__ bool poll_hit(const tray_hit* src, float2& ph) {       // false: still the host's 0xFF fill pattern
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(src) : "memory");
+    ph.x = __uint_as_float((uint32_t)v); ph.y = __uint_as_float((uint32_t)(v >> 32));
+    return v != 0xffffffffffffffffull;
+}
+
 // ---- the traversal kernel ---------------------------------------------------------------------------
 // Per-lane state is kept NORMALISED between steps: a lane is exactly one of
 //   TRI   tri_y != 0                         next action: test one triangle (or enter one TLAS instance)
@@ -579,7 +606,11 @@ __global__ void __launch_bounds__(BOUNCE_BLOCK) raygen_bounce_kernel(const __gri
 // a reader that sees something else than the fill pattern sees the whole record.  A warp with nothing else in hand polls with
 // __nanosleep and a watchdog (the device is never hung: after ~2 s it raises the overflow flag and leaves).
 // Per ray nothing changes: same node order, same triangle order, same (prim, t).
-template <bool TLAS, bool COUNT, int TRI_STRIDE, bool ANYHIT = false, bool FRAME = false>
+// MODE 1: the three semantics of the reference's CPU path that are sourced from memory of the un-vendored obvhs crate (tie
+// rule, slab-test lower clamp, reach of the zero-direction patch) and the HLSL's divide-form box test become RUN-TIME switches
+// (P.variant, TRAY_VARIANT_*), so that the day a real obvhs dump arrives the answer is a flag.  Slower (unfused node test);
+// MODE 0, the default, compiles them away.
+template <bool TLAS, bool COUNT, int TRI_STRIDE, bool ANYHIT = false, bool FRAME = false, int MODE = 0>
 __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
     uint2 spill[STACK_SPILL];
@@ -619,8 +650,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
             if (FRAME) {
                 const uint32_t it = ray_idx & 0x7fffffffu;
                 if (COUNT && best_prim != INVALID) TRAY_CNT(hits);
-                if (!(ray_idx >> 31))      // ONE aligned 8-byte store (never two halves): the record itself tells a reader that it is there
-                    *reinterpret_cast<uint2*>(P.hits_out + it) = make_uint2(__float_as_uint(h.t), h.prim);
+                if (!(ray_idx >> 31))      // ONE 64-bit scalar store (single-copy atomic, unlike a .v2 pair): the record itself tells a reader that it is there
+                    publish_hit(P.hits_out + it, h);
                 else {
                     P.bounce_out[it] = h;
                     if (P.rgba_out) {
@@ -682,7 +713,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                     if (base < n_work && ray_idx < n_work) {
                         const float4* rp = reinterpret_cast<const float4*>(P.rays + ray_idx);
                         const float4 a = __ldg(rp), b = __ldg(rp + 1);
-                        prepare_ray(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w);
+                        prepare_ray(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w, MODE == 1 ? P.variant : 0u);
                         best_t = b.w; best_prim = INVALID;
                         cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp = 0;   // root group, query.hlsl:343
                         tlas_sp = INVALID; bvh_off = TLAS ? P.tlas_start : 0u;
@@ -731,8 +762,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                         // with the pattern 0xFFFFFFFF'FFFFFFFF before the launch, no hit record looks like that (t would be a NaN),
                         // and a record is one aligned 8-byte store — no counters, no fences in the primary pass
                         const uint32_t item = cand_unit * 32u + lane;
-                        const float2 ph = __ldcv(reinterpret_cast<const float2*>(P.hits_out + item));
-                        const bool there = !(__float_as_uint(ph.x) == 0xffffffffu && __float_as_uint(ph.y) == 0xffffffffu);
+                        float2 ph;
+                        const bool there = poll_hit(P.hits_out + item, ph);
                         if (__ballot_sync(FULL, there) == FULL) {
                             cur_unit = cand_unit; cand_unit = INVALID; sleeps = 0;
                             // the group's 32 pixels: who shoots?  Missed pixels get their final results here (rt_cpu.rs:59)
@@ -807,7 +838,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                 const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                 SC(const long long sc_b = clk_after(n0.x ^ n1.x ^ n2.x ^ n3.x ^ n4.x); sc_acc[2] += sc_b - sc_a;)
                 TRAY_CNT(nodes);
-                const uint32_t hitmask = (r.wide || P.force_exact) ? node_test(r, best_t, n0, n1, n2, n3, n4, k4b)
+                uint32_t hitmask;
+                if (MODE == 1) hitmask = node_test(r, best_t, n0, n1, n2, n3, n4, k4b, r.box_tmin, (P.variant & TRAY_VARIANT_BOX_DIVIDE) != 0u);
+                else hitmask = (r.wide || P.force_exact) ? node_test(r, best_t, n0, n1, n2, n3, n4, k4b)
                                                 : node_test_fast(r, best_t, n0, n1, n2, n3, n4, k4b, P.zero);   // :380
                 SC(const long long sc_c = clk_after(hitmask); sc_acc[3] += sc_c - sc_b; sc_n[0]++;)
                 cur_x = n1.x; tri_x = n1.y;                                                    // :383-384
@@ -846,8 +879,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                     SC({ const uint4 q0 = __ldg(P.tris + (size_t)g * (TRI_STRIDE / 16)), q2 = __ldg(P.tris + (size_t)g * (TRI_STRIDE / 16) + 2);
                          sc_acc[6] -= sc_a; sc_acc[6] += clk_after(q0.x ^ q2.x); })
                     SC(const long long sc_b = clk();)
-                    const float t = tri_test<TRI_STRIDE>(r, best_t, P.tris, g);
-                    if (t < best_t) { best_t = t; best_prim = g; }          // CPU tie rule: first of equal t wins (§8a a11)
+                    const float t = tri_test<TRI_STRIDE, MODE == 1>(r, best_t, P.tris, g);
+                    // CPU tie rule: first of equal t wins (§8a a11); TRAY_VARIANT_TIE_LAST: the HLSL's `tt <= t` (query.hlsl:120)
+                    const bool closer = (MODE == 1 && (P.variant & TRAY_VARIANT_TIE_LAST)) ? (t <= best_t && t < __int_as_float(0x7f800000)) : (t < best_t);
+                    if (closer) { best_t = t; best_prim = g; }
                     if (ANYHIT && best_prim != INVALID) { sp = 0; tri_y = 0u; cur_y = 0u; }   // drop the rest of the traversal
                     if (tri_y == 0u && cur_y < 0x01000000u) pop_or_retire();
                     SC(sc_acc[7] += clk_after(cur_y ^ tri_y ^ __float_as_uint(best_t)) - sc_b; sc_n[1]++;)

@@ -45,6 +45,27 @@ int env_int(const char* name, int dflt) {
 
 }  // namespace
 
+// Everything one frame in flight owns: its compact (tile-ordered) buffers, its work cursors and its stream.  Slot 0 runs on
+// tray_scene::stream (the scene's own, or the caller's: tray_cuda_scene_set_stream), slot 1 on a stream of its own, so that
+// the kernels of frame k+1 fill the SM slots the drain phase of frame k leaves empty.
+struct FrameSlot {
+    cudaStream_t own_stream = nullptr;       // slot 1 only
+    unsigned long long* d_cursor = nullptr;  // [0] cursor (u32), [1..10] 2 x 5 counters, [11] bounce-ray count (u32)
+    uint32_t* d_units = nullptr;             // FRAME kernel: cursor over the 32-item groups of bounce work
+    cudaEvent_t ev[4] = { nullptr, nullptr, nullptr, nullptr };
+    cudaEvent_t done = nullptr;              // recorded behind the frame's last launch (fences, group completion)
+    uint32_t fw = 0, fh = 0, fshard = 0, fshards = 1;
+    uint64_t f_items = 0, f_cap = 0;
+    bool f_has_bounce = false, f_has_rgba = false, f_has_rays = false;
+    uchar4* f_target = nullptr;              // the frame target the last frame was rendered into (NULL: compact d_rgba)
+    tray_hit* d_primary = nullptr; tray_hit* d_bounce = nullptr; uchar4* d_rgba = nullptr;
+    tray_ray* d_prays = nullptr;             // generated primary rays, local order
+    tray_ray* d_brays = nullptr;             // generated bounce rays, COMPACT (hit pixels only)
+    uint32_t* d_bitem = nullptr;             // local item of compact bounce ray i
+    tray_ray* d_brays_item = nullptr;        // optional: bounce rays by local item (TRAY_RENDER_KEEP_RAYS)
+    tray::FrameParams last_frame;
+};
+
 struct tray_scene {
     int device = 0;
     int sm_count = 0;
@@ -56,6 +77,7 @@ struct tray_scene {
     uint4* d_tris = nullptr;
     uint32_t* d_blas = nullptr;
     uint32_t* d_prim_indices = nullptr;      // BVH slot -> input triangle (scenes made by tray_cuda_scene_build)
+    uint32_t* d_geom_offsets = nullptr; uint32_t n_geometries = 0;   // first global triangle of BLAS / object g (tray_cuda_scene_set_geometry_offsets)
     unsigned long long* d_cursor = nullptr;     // [0] cursor (u32), [1..10] 2 x 5 counters, [11] bounce-ray count (u32)
     uint32_t* d_overflow = nullptr;
     cudaStream_t stream = nullptr;          // the stream work is enqueued on
@@ -65,42 +87,53 @@ struct tray_scene {
     cudaAccessPolicyWindow window{};
     uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
     bool counting = false;
+    uint32_t variant = 0;                    // TRAY_VARIANT_* (tray_cuda_scene_set_variant): the MODE 1 kernels
     uint32_t refill_min = 4, tri_weight = 4, gen_min = 4;
     bool overlap_default = false;            // TRAY_CUDA_OVERLAP=1: tray_cuda_render always takes the one-launch frame kernel
-    uint32_t* d_units = nullptr;             // FRAME kernel: cursor over the 32-item groups of bounce work
     bool pool = false;                       // pooled kernel (traverse_pool.cuh) or one-ray-per-lane kernel (traverse.cuh)
     uint32_t pool_refill_min = 8, pool_tri_weight = 1;
     uint2* d_spill = nullptr; uint64_t spill_cap = 0;
-    int blocks_per_sm[2] = { 0, 0 };         // resident CTAs per SM of the lane kernel [0] and the pooled kernel [1]
+    int blocks_per_sm[3] = { 0, 0, 0 };      // resident CTAs per SM of the lane kernel [0], the pooled kernel [1], the MODE 1 kernel [2]
     // ray-batch staging
     tray_ray* d_rays = nullptr; tray_hit* d_hits = nullptr; uint64_t batch_cap = 0;
     // host <-> device pipeline of tray_cuda_trace: two pinned staging slots per direction, copy streams, events
     tray_ray* h_rays[2] = { nullptr, nullptr }; tray_hit* h_hits[2] = { nullptr, nullptr };
-    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr; bool pipeline_ready = false;
     cudaEvent_t e_in[2] = { nullptr, nullptr }, e_k[2] = { nullptr, nullptr }, e_out[2] = { nullptr, nullptr };
-    // frame state (compact local order)
-    uint32_t fw = 0, fh = 0, fshard = 0, fshards = 1;
-    uint64_t f_items = 0, f_cap = 0;
-    bool f_has_bounce = false, f_has_rgba = false, f_has_rays = false;
-    uchar4* f_target = nullptr;              // the frame target the last frame was rendered into (NULL: compact d_rgba)
-    tray_hit* d_primary = nullptr; tray_hit* d_bounce = nullptr; uchar4* d_rgba = nullptr;
-    tray_ray* d_prays = nullptr;             // generated primary rays, local order
-    tray_ray* d_brays = nullptr;             // generated bounce rays, COMPACT (hit pixels only)
-    uint32_t* d_bitem = nullptr;             // local item of compact bounce ray i
-    tray_ray* d_brays_item = nullptr;        // optional: bounce rays by local item (TRAY_RENDER_KEEP_RAYS)
+    // frame state: one FrameSlot per frame in flight (tray_cuda_scene_set_frames_in_flight); `cur` = the slot of the last frame
+    FrameSlot slot[2];
+    int n_slots = 1, cur = 0;
     void* d_untiled = nullptr; uint64_t untiled_cap = 0;
     // asynchronous RGBA readback: double-buffered row-major staging, copies on their own stream
     cudaStream_t copy_stream = nullptr;
     uchar4* d_stage[2] = { nullptr, nullptr }; uint64_t stage_cap[2] = { 0, 0 }; bool stage_busy[2] = { false, false };
     cudaEvent_t ev_untiled[2] = { nullptr, nullptr }, ev_copied[2] = { nullptr, nullptr };
+    cudaEvent_t ev_after = nullptr;          // tray_cuda_scene_after
+    uint32_t bounce_sort = 1;                // raygen_bounce_kernel: 0 append in pixel order, 1 group by direction octant, 2 octant x major axis
+    uint32_t* h_flag = nullptr;              // pinned, 2 words: the device error flag as it was when staging slot i was filled
     uchar4* frame_target = nullptr;          // borrowed: row-major RGBA8 frame (this or a peer device), see tray_cuda_scene_set_frame_target
-    tray::FrameParams last_frame;
     tray_counters cnt_primary{}, cnt_bounce{};
 };
 
 namespace {
 
 using namespace tray;
+
+void free_pipeline(tray_scene* s) {
+    for (int i = 0; i < 2; i++) {
+        if (s->h_rays[i]) cudaFreeHost(s->h_rays[i]);
+        if (s->h_hits[i]) cudaFreeHost(s->h_hits[i]);
+        if (s->e_in[i]) cudaEventDestroy(s->e_in[i]);
+        if (s->e_k[i]) cudaEventDestroy(s->e_k[i]);
+        if (s->e_out[i]) cudaEventDestroy(s->e_out[i]);
+        s->h_rays[i] = nullptr; s->h_hits[i] = nullptr; s->e_in[i] = s->e_k[i] = s->e_out[i] = nullptr;
+    }
+    if (s->s_in) cudaStreamDestroy(s->s_in);
+    if (s->s_out) cudaStreamDestroy(s->s_out);
+    s->s_in = s->s_out = nullptr;
+    s->pipeline_ready = false;
+}
+
 
 typedef void (*kernel_fn)(const TraceParams);
 
@@ -118,6 +151,12 @@ kernel_fn pick_frame_kernel(bool tlas, bool count, uint32_t stride) {
     if (tlas) return count ? pick_frame_stride<true, true>(stride) : pick_frame_stride<true, false>(stride);
     return count ? pick_frame_stride<false, true>(stride) : pick_frame_stride<false, false>(stride);
 }
+template <bool TLAS>
+kernel_fn pick_variant_stride(uint32_t stride) {
+    return stride == 64 ? (kernel_fn)trace_kernel<TLAS, false, 64, false, false, 1>
+         : stride == 24 ? (kernel_fn)trace_kernel<TLAS, false, 24, false, false, 1> : (kernel_fn)trace_kernel<TLAS, false, 48, false, false, 1>;
+}
+kernel_fn pick_variant_kernel(bool tlas, uint32_t stride) { return tlas ? pick_variant_stride<true>(stride) : pick_variant_stride<false>(stride); }
 kernel_fn pick_kernel(bool tlas, bool count, uint32_t stride, bool anyhit) {
     if (anyhit) {
         if (tlas) return count ? pick_stride<true, true, true>(stride) : pick_stride<true, false, true>(stride);
@@ -146,16 +185,21 @@ void base_params(const tray_scene* s, TraceParams& P) {
     P.nodes = s->d_nodes; P.tris = s->d_tris; P.blas_offsets = s->d_blas; P.tlas_start = s->tlas_start;
     P.cursor = (uint32_t*)s->d_cursor; P.overflow = s->d_overflow;
     P.refill_min = s->refill_min; P.tri_weight = s->tri_weight; P.k4b = 0x4B000000u; P.force_exact = s->force_exact ? 1u : 0u;
+    P.variant = s->variant;
 }
 
 // one launch: reset the cursor, run the persistent grid (sized to the chip, or to the work if that is smaller)
-int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, bool anyhit = false, bool keep_counters = false, bool frame = false) {
-    const bool pool = s->pool && !anyhit && !frame && s->tri_stride != 24;      // the pooled kernel covers closest hit on f32 records
-    kernel_fn k = pool ? pick_pool_kernel(s->tlas, s->counting, s->tri_stride)
+// `cur` = the cursor block the launch works on: [0] cursor, [1..10] counters ([1 + 5 * counter_slot ..])
+int launch(tray_scene* s, TraceParams& P, cudaStream_t st, unsigned long long* cur, int counter_slot, bool anyhit = false, bool keep_counters = false, bool frame = false) {
+    if (s->variant && (anyhit || frame || s->counting))
+        return fail(TRAY_ERR_ARG, "semantic variants (tray_cuda_scene_set_variant) cover the closest-hit kernels without counters only");
+    const bool pool = s->pool && !anyhit && !frame && s->tri_stride != 24 && !s->variant;      // the pooled kernel covers closest hit on f32 records
+    kernel_fn k = s->variant ? pick_variant_kernel(s->tlas, s->tri_stride)
+                : pool ? pick_pool_kernel(s->tlas, s->counting, s->tri_stride)
                 : frame ? pick_frame_kernel(s->tlas, s->counting, s->tri_stride) : pick_kernel(s->tlas, s->counting, s->tri_stride, anyhit);
     const int threads = pool ? POOL_WARPS * 32 : BLOCK_THREADS;
     const uint64_t rays_per_block = pool ? (uint64_t)POOL_WARPS * POOL_SLOTS : (uint64_t)BLOCK_THREADS;
-    int& bps = s->blocks_per_sm[pool ? 1 : 0];
+    int& bps = s->blocks_per_sm[s->variant ? 2 : pool ? 1 : 0];
     if (bps == 0) {
         int nb = 0;
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k, threads, 0));
@@ -163,8 +207,9 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, boo
         int cap = env_int("TRAY_CUDA_BLOCKS_PER_SM", 0);
         if (cap > 0 && cap < bps) bps = cap;
     }
-    P.counters = s->d_cursor + 1 + 5 * counter_slot;
-    CU(cudaMemsetAsync(s->d_cursor, 0, sizeof(unsigned long long), st));
+    P.cursor = (uint32_t*)cur;
+    P.counters = cur + 1 + 5 * counter_slot;
+    CU(cudaMemsetAsync(cur, 0, sizeof(unsigned long long), st));
     if (s->counting && !keep_counters) CU(cudaMemsetAsync(P.counters, 0, (frame ? 10 : 5) * sizeof(unsigned long long), st));
     const uint64_t blocks_needed = ((uint64_t)P.n_work + rays_per_block - 1) / rays_per_block;
     uint64_t grid = (uint64_t)s->sm_count * bps;
@@ -220,6 +265,8 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, int counter_slot, boo
     return TRAY_OK;
 }
 
+cudaStream_t slot_stream(const tray_scene* s, int k) { return k == 0 ? s->stream : s->slot[1].own_stream; }
+
 void frame_params(FrameParams& F, const tray_view* view, uint32_t w, uint32_t h, uint32_t frame_count, uint32_t shard, uint32_t shards) {
     memset(&F, 0, sizeof F);
     if (view) F.view = *view;
@@ -228,18 +275,19 @@ void frame_params(FrameParams& F, const tray_view* view, uint32_t w, uint32_t h,
     F.n_items = (uint32_t)local_items(w, h, shard, shards);
 }
 
-int read_counters(tray_scene* s, int slot, tray_counters* out) {
+int read_counters(tray_scene* s, const unsigned long long* cur, cudaStream_t st, int slot, tray_counters* out) {
     unsigned long long c[5];
-    CU(cudaMemcpyAsync(c, s->d_cursor + 1 + 5 * slot, sizeof c, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpyAsync(c, cur + 1 + 5 * slot, sizeof c, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     out->rays = c[0]; out->nodes = c[1]; out->tris = c[2]; out->instances = c[3]; out->hits = c[4];
     return TRAY_OK;
 }
 
-int check_overflow(tray_scene* s) {
+int check_overflow(tray_scene* s, cudaStream_t st = nullptr) {
+    if (!st) st = s->stream;
     uint32_t f = 0;
-    CU(cudaMemcpyAsync(&f, s->d_overflow, 4, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpyAsync(&f, s->d_overflow, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     if (f & 4u) {
         cudaMemsetAsync(s->d_overflow, 0, 4, s->stream);
         return fail(TRAY_ERR_CUDA, "frame kernel watchdog: a group of primary hits never arrived (the frame is incomplete)");
@@ -304,18 +352,17 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     cudaFree(s->d_nodes); cudaFree(s->d_tris); cudaFree(s->d_blas); cudaFree(s->d_prim_indices); cudaFree(s->d_cursor); cudaFree(s->d_overflow);
-    cudaFree(s->d_rays); cudaFree(s->d_hits); cudaFree(s->d_spill); cudaFree(s->d_units);
-    for (int i = 0; i < 2; i++) {
-        if (s->h_rays[i]) cudaFreeHost(s->h_rays[i]);
-        if (s->h_hits[i]) cudaFreeHost(s->h_hits[i]);
-        if (s->e_in[i]) cudaEventDestroy(s->e_in[i]);
-        if (s->e_k[i]) cudaEventDestroy(s->e_k[i]);
-        if (s->e_out[i]) cudaEventDestroy(s->e_out[i]);
+    cudaFree(s->d_rays); cudaFree(s->d_hits); cudaFree(s->d_spill); cudaFree(s->d_geom_offsets);
+    free_pipeline(s);
+    cudaFree(s->d_untiled);
+    for (auto& f : s->slot) {
+        if (f.own_stream) cudaStreamSynchronize(f.own_stream);
+        cudaFree(f.d_primary); cudaFree(f.d_bounce); cudaFree(f.d_brays); cudaFree(f.d_rgba);
+        cudaFree(f.d_prays); cudaFree(f.d_bitem); cudaFree(f.d_brays_item); cudaFree(f.d_cursor); cudaFree(f.d_units);
+        for (auto& e : f.ev) if (e) cudaEventDestroy(e);
+        if (f.done) cudaEventDestroy(f.done);
+        if (f.own_stream) cudaStreamDestroy(f.own_stream);
     }
-    if (s->s_in) cudaStreamDestroy(s->s_in);
-    if (s->s_out) cudaStreamDestroy(s->s_out);
-    cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba); cudaFree(s->d_untiled);
-    cudaFree(s->d_prays); cudaFree(s->d_bitem); cudaFree(s->d_brays_item);
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
     for (int i = 0; i < 2; i++) {
         if (s->stage_busy[i]) cudaEventSynchronize(s->ev_copied[i]);
@@ -325,6 +372,8 @@ void tray_cuda_scene_destroy(tray_scene* s) {
     }
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->h_flag) cudaFreeHost(s->h_flag);
+    if (s->ev_after) cudaEventDestroy(s->ev_after);
     delete s;
 }
 
@@ -334,7 +383,7 @@ namespace {
 // `built` != NULL: adopt the device buffers of the device-side builder instead of uploading host arrays
 int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uint64_t n_tris, uint32_t tri_stride,
                       const uint32_t* blas_offsets, uint32_t n_instances, uint32_t tlas_start,
-                      int device, const tray_build::Result* built, tray_scene** out) {
+                      int device, tray_build::Result* built, tray_scene** out) {
     if (!out) return fail(TRAY_ERR_ARG, "out_scene is NULL");
     *out = nullptr;
     if (!built && ((n_nodes && !nodes) || (n_tris && !tris))) return fail(TRAY_ERR_ARG, "NULL node / triangle buffer");
@@ -365,6 +414,7 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
     if (s->pool_refill_min < 1) s->pool_refill_min = 1;
     if (s->pool_refill_min > POOL_SLOTS) s->pool_refill_min = POOL_SLOTS;
     int rc = TRAY_OK;
+    bool adopted = false;
     auto body = [&]() -> int {
         cudaDeviceProp prop;
         CU(cudaGetDeviceProperties(&prop, device));
@@ -374,6 +424,10 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         s->stream = s->own_stream;
         for (auto& e : s->ev) CU(cudaEventCreate(&e));
         CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->ev_after, cudaEventDisableTiming));
+        s->bounce_sort = (uint32_t)env_int("TRAY_CUDA_BOUNCE_SORT", 1);
+        CU(cudaMallocHost(&s->h_flag, 2 * sizeof(uint32_t)));
+        s->h_flag[0] = s->h_flag[1] = 0u;
         for (int i = 0; i < 2; i++) {
             CU(cudaEventCreateWithFlags(&s->ev_untiled[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
@@ -382,6 +436,9 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         if (built && built->d_nodes) {
             s->d_nodes = (uint4*)built->d_nodes; s->d_tris = (uint4*)built->d_tris; s->d_prim_indices = built->d_prim_indices;
             s->d_blas = built->d_blas_offsets;
+            // ownership moves to the scene HERE: from now on tray_cuda_scene_destroy is the one place that frees them
+            built->d_nodes = nullptr; built->d_tris = nullptr; built->d_prim_indices = nullptr; built->d_blas_offsets = nullptr;
+            adopted = true;
         } else {
             CU(cudaMalloc(&s->d_nodes, nb));
             CU(cudaMalloc(&s->d_tris, tb));
@@ -390,12 +447,21 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         CU(cudaMalloc(&s->d_cursor, 16 * sizeof(unsigned long long)));
         CU(cudaMalloc(&s->d_overflow, 4));
         CU(cudaMemsetAsync(s->d_cursor, 0, 16 * sizeof(unsigned long long), s->stream));
+        for (int k = 0; k < 2; k++) {
+            FrameSlot& f = s->slot[k];
+            if (k == 1) CU(cudaStreamCreateWithFlags(&f.own_stream, cudaStreamNonBlocking));
+            CU(cudaMalloc(&f.d_cursor, 16 * sizeof(unsigned long long)));
+            CU(cudaMalloc(&f.d_units, sizeof(uint32_t)));
+            CU(cudaMemsetAsync(f.d_cursor, 0, 16 * sizeof(unsigned long long), s->stream));
+            for (auto& e : f.ev) CU(cudaEventCreate(&e));
+            CU(cudaEventCreateWithFlags(&f.done, cudaEventDisableTiming));
+        }
         CU(cudaMemsetAsync(s->d_overflow, 0, 4, s->stream));
         s->device_bytes = nb + tb + (size_t)n_instances * 4;
-        if (built && built->d_nodes) {}
+        if (adopted) {}
         else if (n_nodes) CU(tray::upload_pipelined(s->d_nodes, nodes, (size_t)n_nodes * 80, s->stream));
         else CU(cudaMemsetAsync(s->d_nodes, 0, 80, s->stream));   // empty scene: a root with no children, every ray misses
-        if (!(built && built->d_nodes) && n_tris) CU(tray::upload_pipelined(s->d_tris, tris, (size_t)n_tris * tri_stride, s->stream));
+        if (!adopted && n_tris) CU(tray::upload_pipelined(s->d_tris, tris, (size_t)n_tris * tri_stride, s->stream));
         if (n_instances && blas_offsets) CU(cudaMemcpyAsync(s->d_blas, blas_offsets, (size_t)n_instances * 4, cudaMemcpyHostToDevice, s->stream));
         // keep the node array hot in the 126 MB L2: persisting access-policy window, attached to every traversal launch
         if (env_int("TRAY_CUDA_L2_PERSIST", 1) && prop.persistingL2CacheMaxSize > 0 && n_nodes) {
@@ -454,7 +520,8 @@ int scene_build_impl(const float* tris9, uint64_t n_tris, const uint64_t* object
                                            search_radius ? search_radius : 14u, nullptr, &r, msg, sizeof msg);
     if (brc) return fail(brc == -1 ? TRAY_ERR_ARG : TRAY_ERR_CUDA, "device build failed: %s", msg);
     const int rc = scene_create_impl(nullptr, r.n_nodes, nullptr, n_tris, tri_stride, nullptr, r.n_instances, r.tlas_start, device, &r, out);
-    if (rc) { if (!*out) { cudaFree(r.d_nodes); cudaFree(r.d_tris); cudaFree(r.d_prim_indices); cudaFree(r.d_blas_offsets); } return rc; }
+    // whatever scene_create_impl did not adopt is still ours (adopted pointers are nulled in `r`): freed exactly once
+    if (rc) { cudaFree(r.d_nodes); cudaFree(r.d_tris); cudaFree(r.d_prim_indices); cudaFree(r.d_blas_offsets); return rc; }
     if (out_stats) *out_stats = r.stats;
     return TRAY_OK;
 }
@@ -507,10 +574,18 @@ int tray_cuda_set_counting(tray_scene* s, int enabled) {
     return TRAY_OK;
 }
 
+int tray_cuda_scene_set_variant(tray_scene* s, uint32_t flags) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    if (flags & ~0xfu) return fail(TRAY_ERR_ARG, "unknown variant flags 0x%x", flags);
+    s->variant = flags;
+    return TRAY_OK;
+}
+
 int tray_cuda_scene_set_stream(tray_scene* s, void* stream) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
+    CU(cudaStreamSynchronize(s->slot[1].own_stream));
     s->stream = stream ? (cudaStream_t)stream : s->own_stream;
     return TRAY_OK;
 }
@@ -579,6 +654,7 @@ int tray_cuda_scene_set_frame_target(tray_scene* s, void* d_frame) {
 int tray_cuda_sync(tray_scene* s) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
     CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->slot[1].own_stream));
     CU(cudaStreamSynchronize(s->stream));
     return check_overflow(s);
 }
@@ -595,7 +671,7 @@ int trace_device_impl(tray_scene* s, const tray_ray* d_rays, uint64_t n, tray_hi
     for (uint64_t off = 0; off < n; off += chunk) {
         TraceParams P; base_params(s, P);
         P.rays = d_rays + off; P.n_work = (uint32_t)(n - off < chunk ? n - off : chunk); P.hits_out = d_hits + off;
-        int rc = launch(s, P, st, 0, anyhit, /*keep_counters=*/off > 0);      // counters accumulate over the chunks of one batch
+        int rc = launch(s, P, st, s->d_cursor, 0, anyhit, /*keep_counters=*/off > 0);      // counters accumulate over the chunks of one batch
         if (rc) return rc;
     }
     if (ms_kernel) {
@@ -610,16 +686,22 @@ constexpr uint64_t PIPE_CHUNK = 1ull << 20;       // rays per pipeline stage (32
 constexpr uint64_t PIPE_MIN = 1ull << 18;         // smaller batches take the plain copy-launch-copy path
 
 int ensure_pipeline(tray_scene* s) {
-    if (s->s_in) return TRAY_OK;
-    CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        CU(cudaMallocHost(&s->h_rays[i], PIPE_CHUNK * sizeof(tray_ray)));
-        CU(cudaMallocHost(&s->h_hits[i], PIPE_CHUNK * sizeof(tray_hit)));
-        CU(cudaEventCreateWithFlags(&s->e_in[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&s->e_k[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&s->e_out[i], cudaEventDisableTiming));
-    }
+    if (s->pipeline_ready) return TRAY_OK;
+    auto body = [&]() -> int {
+        CU(cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaMallocHost(&s->h_rays[i], PIPE_CHUNK * sizeof(tray_ray)));
+            CU(cudaMallocHost(&s->h_hits[i], PIPE_CHUNK * sizeof(tray_hit)));
+            CU(cudaEventCreateWithFlags(&s->e_in[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->e_k[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->e_out[i], cudaEventDisableTiming));
+        }
+        return TRAY_OK;
+    };
+    const int rc = body();
+    if (rc) { free_pipeline(s); return rc; }      // a half-built pipeline must not look ready to the next call
+    s->pipeline_ready = true;
     return TRAY_OK;
 }
 
@@ -668,7 +750,7 @@ int trace_impl(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, 
                 CU(cudaStreamWaitEvent(s->stream, s->e_in[slot], 0));
                 TraceParams P; base_params(s, P);
                 P.rays = s->d_rays + off; P.n_work = (uint32_t)len; P.hits_out = s->d_hits + off;
-                rc = launch(s, P, s->stream, 0, anyhit, /*keep_counters=*/true);
+                rc = launch(s, P, s->stream, s->d_cursor, 0, anyhit, /*keep_counters=*/true);
                 if (rc) return rc;
                 CU(cudaEventRecord(s->e_k[slot], s->stream));
             }
@@ -688,7 +770,7 @@ int trace_impl(tray_scene* s, const tray_ray* rays, uint64_t n, tray_hit* hits, 
         CU(cudaStreamSynchronize(s->stream));
         CU(cudaEventElapsedTime(&k, s->ev[0], s->ev[1]));       // span of the GPU work, uploads it waited for included
     }
-    if (s->counting) { rc = read_counters(s, 0, &s->cnt_primary); if (rc) return rc; memset(&s->cnt_bounce, 0, sizeof s->cnt_bounce); }
+    if (s->counting) { rc = read_counters(s, s->d_cursor, s->stream, 0, &s->cnt_primary); if (rc) return rc; memset(&s->cnt_bounce, 0, sizeof s->cnt_bounce); }
     rc = check_overflow(s);
     if (rc) return rc;
     if (ms_kernel) *ms_kernel = k;
@@ -724,6 +806,41 @@ uint64_t tray_cuda_shard_pixels(uint32_t w, uint32_t h, uint32_t shard, uint32_t
     return n;
 }
 
+uint64_t tray_cuda_shard_items(uint32_t w, uint32_t h, uint32_t shard, uint32_t shards) {
+    return local_items(w, h, shard, shards ? shards : 1);
+}
+
+int tray_cuda_scene_set_frames_in_flight(tray_scene* s, uint32_t n) {
+    if (!s || n < 1 || n > 2) return fail(TRAY_ERR_ARG, "frames in flight must be 1 or 2");
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->slot[1].own_stream));
+    CU(cudaStreamSynchronize(s->stream));
+    if ((int)n != s->n_slots) { s->n_slots = (int)n; s->cur = 0; }
+    return TRAY_OK;
+}
+
+int tray_cuda_scene_fence(tray_scene* s, void* stream) {
+    if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
+    CU(cudaSetDevice(s->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    for (int k = 0; k < s->n_slots; k++) {
+        cudaStream_t fs = slot_stream(s, k);
+        if (fs == st) continue;
+        CU(cudaEventRecord(s->slot[k].done, fs));
+        CU(cudaStreamWaitEvent(st, s->slot[k].done, 0));
+    }
+    return TRAY_OK;
+}
+
+int tray_cuda_scene_after(tray_scene* s, void* stream) {
+    if (!s || !stream) return fail(TRAY_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventRecord(s->ev_after, (cudaStream_t)stream));
+    for (int k = 0; k < 2; k++)
+        if (slot_stream(s, k) != (cudaStream_t)stream) CU(cudaStreamWaitEvent(slot_stream(s, k), s->ev_after, 0));
+    return TRAY_OK;
+}
+
 int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t h, uint32_t frame_count, uint32_t flags,
                      uint32_t shard, uint32_t shards, float* ms_primary, float* ms_bounce) {
     if (!s || !view) return fail(TRAY_ERR_ARG, "NULL argument");
@@ -733,47 +850,51 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     CU(cudaSetDevice(s->device));
     const bool want_count = (flags & TRAY_RENDER_COUNTERS) != 0;
     if (want_count != s->counting) tray_cuda_set_counting(s, want_count);
+    s->cur = s->n_slots > 1 ? (s->cur + 1) % s->n_slots : 0;           // the next frame goes to the other slot
+    FrameSlot& f = s->slot[s->cur];
+    cudaStream_t st = slot_stream(s, s->cur);
     const uint64_t items_cap = local_items(w, h, 0, shards);   // every shard's buffers have the size of the largest (gather)
     const bool bounce = (flags & TRAY_RENDER_BOUNCE) != 0, rgba = (flags & TRAY_RENDER_RGBA) != 0;
     const bool keep_rays = (flags & TRAY_RENDER_KEEP_RAYS) != 0;
     const bool any_ao = (flags & TRAY_RENDER_ANYHIT_AO) != 0;
-    const bool overlap = bounce && !any_ao && ((flags & TRAY_RENDER_OVERLAP) != 0 || s->overlap_default);
-    if (items_cap > s->f_cap || (keep_rays && !s->d_brays_item)) {
-        const uint64_t cap = items_cap > s->f_cap ? items_cap : s->f_cap;
-        cudaFree(s->d_primary); cudaFree(s->d_bounce); cudaFree(s->d_brays); cudaFree(s->d_rgba);
-        cudaFree(s->d_prays); cudaFree(s->d_bitem); cudaFree(s->d_brays_item);
-        s->d_primary = nullptr; s->d_bounce = nullptr; s->d_brays = nullptr; s->d_rgba = nullptr;
-        s->d_prays = nullptr; s->d_bitem = nullptr; s->d_brays_item = nullptr; s->f_cap = 0;
+    const bool overlap = bounce && !any_ao && !s->variant && ((flags & TRAY_RENDER_OVERLAP) != 0 || s->overlap_default);
+    if (items_cap > f.f_cap || (keep_rays && !f.d_brays_item)) {
+        const uint64_t cap = items_cap > f.f_cap ? items_cap : f.f_cap;
+        CU(cudaStreamSynchronize(st));
+        cudaFree(f.d_primary); cudaFree(f.d_bounce); cudaFree(f.d_brays); cudaFree(f.d_rgba);
+        cudaFree(f.d_prays); cudaFree(f.d_bitem); cudaFree(f.d_brays_item);
+        f.d_primary = nullptr; f.d_bounce = nullptr; f.d_brays = nullptr; f.d_rgba = nullptr;
+        f.d_prays = nullptr; f.d_bitem = nullptr; f.d_brays_item = nullptr; f.f_cap = 0;
         const uint64_t c1 = cap ? cap : 1;
-        CU(cudaMalloc(&s->d_primary, c1 * sizeof(tray_hit)));
-        CU(cudaMalloc(&s->d_bounce, c1 * sizeof(tray_hit)));
-        CU(cudaMalloc(&s->d_rgba, c1 * sizeof(uchar4)));
-        CU(cudaMalloc(&s->d_prays, c1 * sizeof(tray_ray)));
-        CU(cudaMalloc(&s->d_brays, c1 * sizeof(tray_ray)));
-        CU(cudaMalloc(&s->d_bitem, c1 * sizeof(uint32_t)));
-        if (keep_rays) CU(cudaMalloc(&s->d_brays_item, c1 * sizeof(tray_ray)));
-        CU(cudaMemsetAsync(s->d_primary, 0xff, c1 * sizeof(tray_hit), s->stream));
-        CU(cudaMemsetAsync(s->d_bounce, 0xff, c1 * sizeof(tray_hit), s->stream));
-        CU(cudaMemsetAsync(s->d_rgba, 0, c1 * sizeof(uchar4), s->stream));
-        s->f_cap = cap;
+        CU(cudaMalloc(&f.d_primary, c1 * sizeof(tray_hit)));
+        CU(cudaMalloc(&f.d_bounce, c1 * sizeof(tray_hit)));
+        CU(cudaMalloc(&f.d_rgba, c1 * sizeof(uchar4)));
+        CU(cudaMalloc(&f.d_prays, c1 * sizeof(tray_ray)));
+        CU(cudaMalloc(&f.d_brays, c1 * sizeof(tray_ray)));
+        CU(cudaMalloc(&f.d_bitem, c1 * sizeof(uint32_t)));
+        if (keep_rays) CU(cudaMalloc(&f.d_brays_item, c1 * sizeof(tray_ray)));
+        CU(cudaMemsetAsync(f.d_primary, 0xff, c1 * sizeof(tray_hit), st));
+        CU(cudaMemsetAsync(f.d_bounce, 0xff, c1 * sizeof(tray_hit), st));
+        CU(cudaMemsetAsync(f.d_rgba, 0, c1 * sizeof(uchar4), st));
+        f.f_cap = cap;
     }
     FrameParams F; frame_params(F, view, w, h, frame_count, shard, shards);
-    s->fw = w; s->fh = h; s->fshard = shard; s->fshards = shards; s->f_items = F.n_items;
-    s->f_has_bounce = bounce; s->f_has_rgba = rgba && !s->frame_target; s->f_has_rays = keep_rays && bounce;
-    s->f_target = rgba ? s->frame_target : nullptr;
-    s->last_frame = F;
+    f.fw = w; f.fh = h; f.fshard = shard; f.fshards = shards; f.f_items = F.n_items;
+    f.f_has_bounce = bounce; f.f_has_rgba = rgba && !s->frame_target; f.f_has_rays = keep_rays && bounce;
+    f.f_target = rgba ? s->frame_target : nullptr;
+    f.last_frame = F;
     if (F.n_items == 0) { if (ms_primary) *ms_primary = 0.f; if (ms_bounce) *ms_bounce = 0.f; return TRAY_OK; }
     const unsigned gen_grid = (F.n_items + 255) / 256;
-    uint32_t* d_nbrays = (uint32_t*)(s->d_cursor + 11);
+    uint32_t* d_nbrays = (uint32_t*)(f.d_cursor + 11);
     const bool timed = ms_primary || ms_bounce;
 
     // ---- primary: generate rays, trace ----
-    if (timed) CU(cudaEventRecord(s->ev[0], s->stream));
-    tray::raygen_primary_kernel<<<gen_grid, 256, 0, s->stream>>>(F, s->d_prays);
+    if (timed) CU(cudaEventRecord(f.ev[0], st));
+    tray::raygen_primary_kernel<<<gen_grid, 256, 0, st>>>(F, f.d_prays);
     CU(cudaGetLastError());
     TraceParams P; base_params(s, P);
-    P.rays = s->d_prays; P.n_work = F.n_items; P.hits_out = s->d_primary;
-    uchar4* const rgba_dst = s->frame_target ? s->frame_target : s->d_rgba;
+    P.rays = f.d_prays; P.n_work = F.n_items; P.hits_out = f.d_primary;
+    uchar4* const rgba_dst = s->frame_target ? s->frame_target : f.d_rgba;
     auto set_frame = [&](TraceParams& T) {
         if (!s->frame_target) return;
         T.frame_w = w; T.frame_h = h; T.frame_tiles_x = F.tiles_x; T.frame_shard = shard; T.frame_shards = shards;
@@ -781,47 +902,47 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     P.rgba_out = (rgba && !bounce) ? rgba_dst : nullptr; P.shade_mode = SHADE_PRIMARY;
     if (overlap) {
         // one launch for the whole frame (trace_kernel<FRAME>): the bounce rays of finished tiles fill the primary pass's drain
-        if (!s->d_units) CU(cudaMalloc(&s->d_units, sizeof(uint32_t)));
-        CU(cudaMemsetAsync(s->d_units, 0, sizeof(uint32_t), s->stream));
-        CU(cudaMemsetAsync(s->d_primary, 0xff, (size_t)F.n_items * sizeof(tray_hit), s->stream));     // "not there yet" for every primary hit
+        CU(cudaMemsetAsync(f.d_units, 0, sizeof(uint32_t), st));
+        CU(cudaMemsetAsync(f.d_primary, 0xff, (size_t)F.n_items * sizeof(tray_hit), st));     // "not there yet" for every primary hit
         P.rgba_out = rgba ? rgba_dst : nullptr;
-        P.frame = F; P.bounce_out = s->d_bounce; P.rays_by_item = keep_rays ? s->d_brays_item : nullptr; P.gen_min = s->gen_min;
-        P.gen_rays = s->d_brays;
-        P.unit_cursor = s->d_units; P.n_units = (uint32_t)(F.n_items / 32);
+        P.frame = F; P.bounce_out = f.d_bounce; P.rays_by_item = keep_rays ? f.d_brays_item : nullptr; P.gen_min = s->gen_min;
+        P.gen_rays = f.d_brays;
+        P.unit_cursor = f.d_units; P.n_units = (uint32_t)(F.n_items / 32);
     }
     if (P.rgba_out) set_frame(P);
-    int rc = launch(s, P, s->stream, 0, false, false, overlap);
+    int rc = launch(s, P, st, f.d_cursor, 0, false, false, overlap);
     if (rc) return rc;
-    if (timed) CU(cudaEventRecord(s->ev[1], s->stream));
-    if (overlap && timed) CU(cudaEventRecord(s->ev[2], s->stream));
+    if (timed) CU(cudaEventRecord(f.ev[1], st));
+    if (overlap && timed) CU(cudaEventRecord(f.ev[2], st));
 
     // ---- bounce: generate + compact rays of hit pixels, trace ----
     if (bounce && !overlap) {
-        CU(cudaMemsetAsync(d_nbrays, 0, sizeof(uint32_t), s->stream));
+        CU(cudaMemsetAsync(d_nbrays, 0, sizeof(uint32_t), st));
         auto gen = s->tri_stride == 64 ? tray::raygen_bounce_kernel<64> : s->tri_stride == 24 ? tray::raygen_bounce_kernel<24> : tray::raygen_bounce_kernel<48>;
-        gen<<<(F.n_items + BOUNCE_BLOCK - 1) / BOUNCE_BLOCK, BOUNCE_BLOCK, 0, s->stream>>>(F, s->d_tris, s->d_primary, s->d_brays, s->d_bitem, d_nbrays, s->d_bounce,
-                                             rgba ? rgba_dst : nullptr, keep_rays ? s->d_brays_item : nullptr, s->frame_target ? 1u : 0u,
-                                             (uint32_t)env_int("TRAY_CUDA_BOUNCE_SORT", 1));
+        gen<<<(F.n_items + BOUNCE_BLOCK - 1) / BOUNCE_BLOCK, BOUNCE_BLOCK, 0, st>>>(F, s->d_tris, f.d_primary, f.d_brays, f.d_bitem, d_nbrays, f.d_bounce,
+                                             rgba ? rgba_dst : nullptr, keep_rays ? f.d_brays_item : nullptr, s->frame_target ? 1u : 0u,
+                                             s->bounce_sort);
         CU(cudaGetLastError());
         TraceParams B; base_params(s, B);
-        B.rays = s->d_brays; B.ray_item = s->d_bitem; B.n_work = F.n_items; B.n_work_dev = d_nbrays;   // count stays on the device
-        B.hits_out = s->d_bounce; B.rgba_out = rgba ? rgba_dst : nullptr; B.shade_mode = any_ao ? SHADE_OCCLUSION : SHADE_BOUNCE;
+        B.rays = f.d_brays; B.ray_item = f.d_bitem; B.n_work = F.n_items; B.n_work_dev = d_nbrays;   // count stays on the device
+        B.hits_out = f.d_bounce; B.rgba_out = rgba ? rgba_dst : nullptr; B.shade_mode = any_ao ? SHADE_OCCLUSION : SHADE_BOUNCE;
         if (B.rgba_out) set_frame(B);
-        rc = launch(s, B, s->stream, 1, any_ao);
+        rc = launch(s, B, st, f.d_cursor, 1, any_ao);
         if (rc) return rc;
-        if (timed) CU(cudaEventRecord(s->ev[2], s->stream));
+        if (timed) CU(cudaEventRecord(f.ev[2], st));
     }
     if (timed) {
-        CU(cudaStreamSynchronize(s->stream));
+        CU(cudaStreamSynchronize(st));
         float a = 0.f, b = 0.f;
-        CU(cudaEventElapsedTime(&a, s->ev[0], s->ev[1]));
-        if (bounce) CU(cudaEventElapsedTime(&b, s->ev[1], s->ev[2]));
+        CU(cudaEventElapsedTime(&a, f.ev[0], f.ev[1]));
+        if (bounce) CU(cudaEventElapsedTime(&b, f.ev[1], f.ev[2]));
         if (ms_primary) *ms_primary = a;
         if (ms_bounce) *ms_bounce = b;
+        rc = check_overflow(s, st); if (rc) return rc;
     }
     if (s->counting) {
-        rc = read_counters(s, 0, &s->cnt_primary); if (rc) return rc;
-        if (bounce) { rc = read_counters(s, 1, &s->cnt_bounce); if (rc) return rc; }
+        rc = read_counters(s, f.d_cursor, st, 0, &s->cnt_primary); if (rc) return rc;
+        if (bounce) { rc = read_counters(s, f.d_cursor, st, 1, &s->cnt_bounce); if (rc) return rc; }
         else memset(&s->cnt_bounce, 0, sizeof s->cnt_bounce);
         // rays generated for pixels outside the frame (tmax = 0) are not rays of the workload
         const uint64_t pad = (uint64_t)F.n_items - tray_cuda_shard_pixels(w, h, shard, shards);
@@ -834,13 +955,15 @@ int tray_cuda_render_timed(tray_scene* s, const tray_view* view, uint32_t w, uin
                            uint32_t shard, uint32_t shards, float* ms_frame) {
     if (!s || !view || !ms_frame) return fail(TRAY_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(s->device));
-    CU(cudaEventRecord(s->ev[0], s->stream));
+    const int k = s->n_slots > 1 ? (s->cur + 1) % s->n_slots : 0;          // the slot tray_cuda_render is about to take
+    cudaStream_t st = slot_stream(s, k);
+    CU(cudaEventRecord(s->slot[k].ev[0], st));
     int rc = tray_cuda_render(s, view, w, h, frame_count, flags, shard, shards, nullptr, nullptr);
     if (rc) return rc;
-    CU(cudaEventRecord(s->ev[3], s->stream));
-    CU(cudaEventSynchronize(s->ev[3]));
-    CU(cudaEventElapsedTime(ms_frame, s->ev[0], s->ev[3]));
-    return TRAY_OK;
+    CU(cudaEventRecord(s->slot[k].ev[3], st));
+    CU(cudaEventSynchronize(s->slot[k].ev[3]));
+    CU(cudaEventElapsedTime(ms_frame, s->slot[k].ev[0], s->slot[k].ev[3]));
+    return check_overflow(s, st);             // synchronising point: a stack overflow / watchdog flag must not pass as TRAY_OK
 }
 
 int tray_cuda_counters(tray_scene* s, tray_counters* primary, tray_counters* bounce) {
@@ -852,9 +975,10 @@ int tray_cuda_counters(tray_scene* s, tray_counters* primary, tray_counters* bou
 
 int tray_cuda_frame_device_ptrs(tray_scene* s, void** d_primary, void** d_bounce, void** d_rgba) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
-    if (d_primary) *d_primary = s->d_primary;
-    if (d_bounce) *d_bounce = s->d_bounce;
-    if (d_rgba) *d_rgba = s->d_rgba;
+    const FrameSlot& f = s->slot[s->cur];
+    if (d_primary) *d_primary = f.d_primary;
+    if (d_bounce) *d_bounce = f.d_bounce;
+    if (d_rgba) *d_rgba = f.d_rgba;
     return TRAY_OK;
 }
 
@@ -863,20 +987,22 @@ int tray_cuda_frame_device_ptrs(tray_scene* s, void** d_primary, void** d_bounce
 namespace {
 template <typename T>
 int download(tray_scene* s, const T* d_src, T* host_dst) {
-    const uint64_t n = (uint64_t)s->fw * s->fh, bytes = n * sizeof(T);
+    const FrameSlot& f = s->slot[s->cur];
+    cudaStream_t st = slot_stream(s, s->cur);
+    const uint64_t n = (uint64_t)f.fw * f.fh, bytes = n * sizeof(T);
     if (bytes > s->untiled_cap) {
         cudaFree(s->d_untiled); s->d_untiled = nullptr; s->untiled_cap = 0;
         CU(cudaMalloc(&s->d_untiled, bytes));
         s->untiled_cap = bytes;
     }
-    if (s->fshards > 1) CU(cudaMemsetAsync(s->d_untiled, 0, bytes, s->stream));   // pixels of other shards read as zero
-    if (s->f_items) {
-        const unsigned grid = (unsigned)((s->f_items + 255) / 256);
-        tray::untile_kernel<T><<<grid, 256, 0, s->stream>>>(s->last_frame, d_src, (T*)s->d_untiled);
+    if (f.fshards > 1) CU(cudaMemsetAsync(s->d_untiled, 0, bytes, st));   // pixels of other shards read as zero
+    if (f.f_items) {
+        const unsigned grid = (unsigned)((f.f_items + 255) / 256);
+        tray::untile_kernel<T><<<grid, 256, 0, st>>>(f.last_frame, d_src, (T*)s->d_untiled);
         CU(cudaGetLastError());
     }
-    CU(cudaMemcpyAsync(host_dst, s->d_untiled, bytes, cudaMemcpyDeviceToHost, s->stream));
-    CU(cudaStreamSynchronize(s->stream));
+    CU(cudaMemcpyAsync(host_dst, s->d_untiled, bytes, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
     return TRAY_OK;
 }
 }  // namespace
@@ -885,30 +1011,33 @@ extern "C" {
 
 int tray_cuda_frame_download(tray_scene* s, tray_hit* primary, tray_hit* bounce, tray_ray* bounce_rays, uint8_t* rgba) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
-    if (s->fw == 0) return fail(TRAY_ERR_ARG, "no frame has been rendered");
+    const FrameSlot& f = s->slot[s->cur];
+    if (f.fw == 0) return fail(TRAY_ERR_ARG, "no frame has been rendered");
     CU(cudaSetDevice(s->device));
     int rc;
-    if (primary) { rc = download<tray_hit>(s, s->d_primary, primary); if (rc) return rc; }
+    if (primary) { rc = download<tray_hit>(s, f.d_primary, primary); if (rc) return rc; }
     if (bounce) {
-        if (!s->f_has_bounce) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_BOUNCE");
-        rc = download<tray_hit>(s, s->d_bounce, bounce); if (rc) return rc;
+        if (!f.f_has_bounce) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_BOUNCE");
+        rc = download<tray_hit>(s, f.d_bounce, bounce); if (rc) return rc;
     }
     if (bounce_rays) {
-        if (!s->f_has_rays) return fail(TRAY_ERR_ARG, "last frame was rendered without the keep-bounce-rays flag (0x8)");
-        rc = download<tray_ray>(s, s->d_brays_item, bounce_rays); if (rc) return rc;
+        if (!f.f_has_rays) return fail(TRAY_ERR_ARG, "last frame was rendered without the keep-bounce-rays flag (0x8)");
+        rc = download<tray_ray>(s, f.d_brays_item, bounce_rays); if (rc) return rc;
     }
     if (rgba) {
-        if (!s->f_has_rgba) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA");
-        rc = download<uchar4>(s, s->d_rgba, (uchar4*)rgba); if (rc) return rc;
+        if (!f.f_has_rgba) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA");
+        rc = download<uchar4>(s, f.d_rgba, (uchar4*)rgba); if (rc) return rc;
     }
-    return check_overflow(s);
+    return check_overflow(s, slot_stream(s, s->cur));
 }
 
 int tray_cuda_frame_readback_begin(tray_scene* s, uint8_t* rgba, uint32_t slot) {
     if (!s || !rgba || slot > 1) return fail(TRAY_ERR_ARG, "bad argument");
-    if (s->fw == 0 || (!s->f_has_rgba && !s->f_target)) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA");
+    const FrameSlot& f = s->slot[s->cur];
+    cudaStream_t st = slot_stream(s, s->cur);
+    if (f.fw == 0 || (!f.f_has_rgba && !f.f_target)) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA");
     CU(cudaSetDevice(s->device));
-    const uint64_t bytes = (uint64_t)s->fw * s->fh * sizeof(uchar4);
+    const uint64_t bytes = (uint64_t)f.fw * f.fh * sizeof(uchar4);
     if (s->stage_busy[slot]) {                       // the previous copy out of this staging buffer must have landed
         CU(cudaEventSynchronize(s->ev_copied[slot]));
         s->stage_busy[slot] = false;
@@ -918,21 +1047,23 @@ int tray_cuda_frame_readback_begin(tray_scene* s, uint8_t* rgba, uint32_t slot) 
         CU(cudaMalloc(&s->d_stage[slot], bytes));
         s->stage_cap[slot] = bytes;
     }
-    if (s->f_target) {
+    if (f.f_target) {
         // the frame was rendered into a row-major frame target (all shards' pixels, once the caller's barrier has passed):
         // snapshot it, so that the next frame may overwrite the target while this one travels to the host
-        CU(cudaMemcpyAsync(s->d_stage[slot], s->f_target, bytes, cudaMemcpyDeviceToDevice, s->stream));
+        CU(cudaMemcpyAsync(s->d_stage[slot], f.f_target, bytes, cudaMemcpyDeviceToDevice, st));
     } else {
-        if (s->fshards > 1) CU(cudaMemsetAsync(s->d_stage[slot], 0, bytes, s->stream));
-        if (s->f_items) {
-            const unsigned grid = (unsigned)((s->f_items + 255) / 256);
-            tray::untile_kernel<uchar4><<<grid, 256, 0, s->stream>>>(s->last_frame, s->d_rgba, s->d_stage[slot]);
+        if (f.fshards > 1) CU(cudaMemsetAsync(s->d_stage[slot], 0, bytes, st));
+        if (f.f_items) {
+            const unsigned grid = (unsigned)((f.f_items + 255) / 256);
+            tray::untile_kernel<uchar4><<<grid, 256, 0, st>>>(f.last_frame, f.d_rgba, s->d_stage[slot]);
             CU(cudaGetLastError());
         }
     }
-    CU(cudaEventRecord(s->ev_untiled[slot], s->stream));
+    CU(cudaEventRecord(s->ev_untiled[slot], st));
     CU(cudaStreamWaitEvent(s->copy_stream, s->ev_untiled[slot], 0));
     CU(cudaMemcpyAsync(rgba, s->d_stage[slot], bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    // the error flag travels with the frame (a stream synchronise here would undo the overlap): checked in _wait
+    CU(cudaMemcpyAsync(s->h_flag + slot, s->d_overflow, sizeof(uint32_t), cudaMemcpyDeviceToHost, s->copy_stream));
     CU(cudaEventRecord(s->ev_copied[slot], s->copy_stream));
     s->stage_busy[slot] = true;
     return TRAY_OK;
@@ -944,6 +1075,13 @@ int tray_cuda_frame_readback_wait(tray_scene* s, uint32_t slot) {
     CU(cudaSetDevice(s->device));
     CU(cudaEventSynchronize(s->ev_copied[slot]));
     s->stage_busy[slot] = false;
+    const uint32_t fl = s->h_flag[slot];
+    if (fl) {
+        s->h_flag[slot] = 0u;
+        cudaMemsetAsync(s->d_overflow, 0, 4, s->stream);
+        if (fl & 4u) return fail(TRAY_ERR_CUDA, "frame kernel watchdog: a group of primary hits never arrived (the frame is incomplete)");
+        return fail(TRAY_ERR_OVERFLOW, "traversal stack overflow: BVH needs more than %d stack entries", STACK_SMEM + STACK_SPILL);
+    }
     return TRAY_OK;
 }
 
@@ -993,6 +1131,293 @@ int tray_cuda_start(const void* bvh_bytes, uint64_t bvh_len, const void* instanc
     }
     if (!rc) rc = tray_cuda_sync(s);
     tray_cuda_scene_destroy(s);
+    if (rc) return rc;
+    if (out_min_ms) *out_min_ms = min_ms;
+    if (out_mean_ms) *out_mean_ms = frames ? (float)(sum / frames) : 0.f;
+    if (out_frames) *out_frames = frames;
+    return TRAY_OK;
+}
+
+}  // extern "C"
+
+// ---- CPU-style hit records: (geometry_id, primitive_id) -----------------------------------------------------------------
+namespace {
+// global triangle index -> (object whose range holds it, index inside that object's BVH-ordered triangle array)
+__global__ void hits_to_geometry_kernel(const tray_hit* __restrict__ hits, uint64_t n, const uint32_t* __restrict__ offsets, uint32_t n_geom,
+                                        uint32_t* __restrict__ geometry_id, uint32_t* __restrict__ primitive_id) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t prim = hits[i].prim;
+    uint32_t g = 0xffffffffu, local = prim;                  // miss: RayHit::none()
+    if (prim != 0xffffffffu && n_geom) {
+        uint32_t lo = 0, hi = n_geom;                        // last g with offsets[g] <= prim
+        while (hi - lo > 1u) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(offsets + mid) <= prim) lo = mid; else hi = mid; }
+        g = lo; local = prim - __ldg(offsets + lo);
+    }
+    geometry_id[i] = g; primitive_id[i] = local;
+}
+}  // namespace
+
+extern "C" {
+
+int tray_cuda_scene_set_geometry_offsets(tray_scene* s, const uint32_t* tri_offsets, uint32_t n_geometries) {
+    if (!s || (n_geometries && !tri_offsets)) return fail(TRAY_ERR_ARG, "NULL argument");
+    if (n_geometries) {
+        if (tri_offsets[0] != 0u || tri_offsets[n_geometries] != (uint32_t)s->n_tris) return fail(TRAY_ERR_ARG, "tri_offsets must run from 0 to n_tris (%llu)", (unsigned long long)s->n_tris);
+        for (uint32_t g = 0; g < n_geometries; g++)
+            if (tri_offsets[g] > tri_offsets[g + 1]) return fail(TRAY_ERR_ARG, "tri_offsets must ascend (entry %u)", g);
+    }
+    CU(cudaSetDevice(s->device));
+    CU(cudaStreamSynchronize(s->stream));
+    cudaFree(s->d_geom_offsets); s->d_geom_offsets = nullptr; s->n_geometries = 0;
+    if (n_geometries) {
+        CU(cudaMalloc(&s->d_geom_offsets, (size_t)(n_geometries + 1) * 4));
+        CU(cudaMemcpy(s->d_geom_offsets, tri_offsets, (size_t)(n_geometries + 1) * 4, cudaMemcpyHostToDevice));
+        s->n_geometries = n_geometries;
+    }
+    return TRAY_OK;
+}
+
+int tray_cuda_hits_to_geometry(tray_scene* s, const tray_hit* hits, uint64_t n, uint32_t* geometry_id, uint32_t* primitive_id) {
+    if (!s || (n && (!hits || !geometry_id || !primitive_id))) return fail(TRAY_ERR_ARG, "NULL argument");
+    if (n == 0) return TRAY_OK;
+    CU(cudaSetDevice(s->device));
+    tray_hit* d_h = nullptr; uint32_t* d_o = nullptr;
+    CU(cudaMalloc(&d_h, n * sizeof(tray_hit)));
+    if (cudaMalloc(&d_o, n * 8) != cudaSuccess) { cudaFree(d_h); return fail(TRAY_ERR_CUDA, "cudaMalloc failed"); }
+    auto body = [&]() -> int {
+        CU(cudaMemcpyAsync(d_h, hits, n * sizeof(tray_hit), cudaMemcpyHostToDevice, s->stream));
+        hits_to_geometry_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s->stream>>>(d_h, n, s->d_geom_offsets, s->n_geometries, d_o, d_o + n);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(geometry_id, d_o, n * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaMemcpyAsync(primitive_id, d_o + n, n * 4, cudaMemcpyDeviceToHost, s->stream));
+        CU(cudaStreamSynchronize(s->stream));
+        return TRAY_OK;
+    };
+    const int rc = body();
+    cudaFree(d_h); cudaFree(d_o);
+    return rc;
+}
+
+}  // extern "C"
+
+// ---- one process, several GPUs -----------------------------------------------------------------------------------------
+// The reference's slot is ONE call from ONE host thread (rt_gpu_software.rs:24-32).  A tray_group keeps that shape on a box
+// with several GPUs: the BVH is replicated (one tray_scene per device), the frame's 32x8 tiles are dealt round-robin to the
+// devices, and every device's traversal kernels store their finished pixels straight into ONE row-major frame on devices[0]
+// through peer access (cudaDeviceEnablePeerAccess: no IPC, no NCCL, no torch).  "Frame complete" is a set of events: device
+// 0's stream waits for the event each other device records behind its last launch.
+struct tray_group {
+    std::vector<tray_scene*> scenes;
+    std::vector<int> devices;
+    uchar4* target[2] = { nullptr, nullptr };          // row-major frames on devices[0], one per frame in flight
+    uint64_t target_bytes = 0;
+    int in_flight = 1, cur = 0;
+    cudaEvent_t ev_snap[2] = { nullptr, nullptr };     // devices[0]: the frame in target[i] has been copied out (readback)
+    bool snap_pending[2] = { false, false };
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      // devices[0]: frame timing
+};
+
+namespace {
+int group_ensure_target(tray_group* g, uint32_t w, uint32_t h) {
+    const uint64_t bytes = (uint64_t)w * h * 4;
+    if (bytes <= g->target_bytes) return TRAY_OK;
+    CU(cudaSetDevice(g->devices[0]));
+    for (auto* sc : g->scenes) { int rc = tray_cuda_sync(sc); if (rc) return rc; }
+    CU(cudaSetDevice(g->devices[0]));
+    for (int i = 0; i < 2; i++) {
+        cudaFree(g->target[i]); g->target[i] = nullptr;
+        CU(cudaMalloc(&g->target[i], bytes));
+        CU(cudaMemset(g->target[i], 0, bytes));
+    }
+    g->target_bytes = bytes;
+    return TRAY_OK;
+}
+}  // namespace
+
+extern "C" {
+
+void tray_cuda_group_destroy(tray_group* g) {
+    if (!g) return;
+    for (auto* sc : g->scenes) tray_cuda_scene_destroy(sc);
+    if (!g->devices.empty()) {
+        cudaSetDevice(g->devices[0]);
+        for (int i = 0; i < 2; i++) { cudaFree(g->target[i]); if (g->ev_snap[i]) cudaEventDestroy(g->ev_snap[i]); }
+        if (g->ev_t0) cudaEventDestroy(g->ev_t0);
+        if (g->ev_t1) cudaEventDestroy(g->ev_t1);
+    }
+    delete g;
+}
+
+int tray_cuda_group_create(const void* nodes, uint64_t n_nodes, const void* tris, uint64_t n_tris, uint32_t tri_stride,
+                           const uint32_t* blas_offsets, uint32_t n_instances, uint32_t tlas_start,
+                           const int* devices, int n_devices, tray_group** out) {
+    if (!out) return fail(TRAY_ERR_ARG, "out_group is NULL");
+    *out = nullptr;
+    const int ndev = tray_cuda_device_count();
+    if (ndev == 0) return fail(TRAY_ERR_NO_DEVICE, "no CUDA device (tray_cuda has no CPU fallback)");
+    if (n_devices < 1 || n_devices > ndev) return fail(TRAY_ERR_ARG, "n_devices %d out of range (1..%d)", n_devices, ndev);
+    tray_group* g = new (std::nothrow) tray_group();
+    if (!g) return fail(TRAY_ERR_ARG, "out of host memory");
+    for (int i = 0; i < n_devices; i++) {
+        const int d = devices ? devices[i] : i;
+        for (int j = 0; j < i; j++)
+            if (g->devices[j] == d) { tray_cuda_group_destroy(g); return fail(TRAY_ERR_ARG, "device %d listed twice", d); }
+        g->devices.push_back(d);
+    }
+    auto body = [&]() -> int {
+        for (int i = 0; i < n_devices; i++) {
+            tray_scene* sc = nullptr;
+            int rc = tray_cuda_scene_create(nodes, n_nodes, tris, n_tris, tri_stride, blas_offsets, n_instances, tlas_start, g->devices[i], &sc);
+            if (rc) return rc;
+            g->scenes.push_back(sc);
+            if (i > 0) {        // device i stores pixels into device 0's frame
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, g->devices[i], g->devices[0]));
+                if (!can) return fail(TRAY_ERR_CUDA, "device %d has no peer access to device %d", g->devices[i], g->devices[0]);
+                CU(cudaSetDevice(g->devices[i]));
+                const cudaError_t e = cudaDeviceEnablePeerAccess(g->devices[0], 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else if (e != cudaSuccess) return fail(TRAY_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d) failed: %s", g->devices[i], g->devices[0], cudaGetErrorString(e));
+            }
+        }
+        CU(cudaSetDevice(g->devices[0]));
+        for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&g->ev_snap[i], cudaEventDisableTiming));
+        CU(cudaEventCreate(&g->ev_t0)); CU(cudaEventCreate(&g->ev_t1));
+        return TRAY_OK;
+    };
+    const int rc = body();
+    if (rc) { tray_cuda_group_destroy(g); return rc; }
+    *out = g;
+    return TRAY_OK;
+}
+
+int tray_cuda_group_size(const tray_group* g) { return g ? (int)g->scenes.size() : 0; }
+
+int tray_cuda_group_scene(tray_group* g, int i, tray_scene** out) {
+    if (!g || !out || i < 0 || i >= (int)g->scenes.size()) return fail(TRAY_ERR_ARG, "bad argument");
+    *out = g->scenes[i];
+    return TRAY_OK;
+}
+
+int tray_cuda_group_set_frames_in_flight(tray_group* g, uint32_t n) {
+    if (!g || n < 1 || n > 2) return fail(TRAY_ERR_ARG, "frames in flight must be 1 or 2");
+    for (auto* sc : g->scenes) { int rc = tray_cuda_scene_set_frames_in_flight(sc, n); if (rc) return rc; }
+    g->in_flight = (int)n; g->cur = 0;
+    return TRAY_OK;
+}
+
+int tray_cuda_group_render(tray_group* g, const tray_view* view, uint32_t w, uint32_t h, uint32_t frame_count, uint32_t flags) {
+    if (!g || !view) return fail(TRAY_ERR_ARG, "NULL argument");
+    int rc = group_ensure_target(g, w, h);
+    if (rc) return rc;
+    const int n = (int)g->scenes.size();
+    g->cur = g->in_flight > 1 ? (g->cur + 1) % 2 : 0;
+    uchar4* const target = g->target[g->cur];
+    for (int i = 0; i < n; i++) {
+        tray_scene* sc = g->scenes[i];
+        const int k = sc->n_slots > 1 ? (sc->cur + 1) % sc->n_slots : 0;          // the slot this frame will take on device i
+        if (i > 0 && g->snap_pending[g->cur]) {         // the previous frame in this target must have been copied out first
+            CU(cudaSetDevice(sc->device));
+            CU(cudaStreamWaitEvent(slot_stream(sc, k), g->ev_snap[g->cur], 0));
+        }
+        sc->frame_target = target;
+        rc = tray_cuda_render(sc, view, w, h, frame_count, flags | TRAY_RENDER_RGBA, (uint32_t)i, (uint32_t)n, nullptr, nullptr);
+        if (rc) return rc;
+        if (i > 0) CU(cudaEventRecord(sc->slot[sc->cur].done, slot_stream(sc, sc->cur)));
+    }
+    g->snap_pending[g->cur] = false;
+    // frame complete on devices[0]: its stream waits for every other device's last launch
+    tray_scene* s0 = g->scenes[0];
+    CU(cudaSetDevice(s0->device));
+    for (int i = 1; i < n; i++) CU(cudaStreamWaitEvent(slot_stream(s0, s0->cur), g->scenes[i]->slot[g->scenes[i]->cur].done, 0));
+    return TRAY_OK;
+}
+
+int tray_cuda_group_render_timed(tray_group* g, const tray_view* view, uint32_t w, uint32_t h, uint32_t frame_count, uint32_t flags, float* ms_frame) {
+    if (!g || !view || !ms_frame) return fail(TRAY_ERR_ARG, "NULL argument");
+    int rc = group_ensure_target(g, w, h);
+    if (rc) return rc;
+    tray_scene* s0 = g->scenes[0];
+    const int k0 = s0->n_slots > 1 ? (s0->cur + 1) % s0->n_slots : 0;
+    CU(cudaSetDevice(s0->device));
+    CU(cudaEventRecord(g->ev_t0, slot_stream(s0, k0)));
+    for (size_t i = 1; i < g->scenes.size(); i++) {      // nobody starts before the clock does
+        tray_scene* sc = g->scenes[i];
+        const int k = sc->n_slots > 1 ? (sc->cur + 1) % sc->n_slots : 0;
+        CU(cudaSetDevice(sc->device));
+        CU(cudaStreamWaitEvent(slot_stream(sc, k), g->ev_t0, 0));
+    }
+    rc = tray_cuda_group_render(g, view, w, h, frame_count, flags);
+    if (rc) return rc;
+    CU(cudaSetDevice(s0->device));
+    CU(cudaEventRecord(g->ev_t1, slot_stream(s0, s0->cur)));
+    CU(cudaEventSynchronize(g->ev_t1));
+    CU(cudaEventElapsedTime(ms_frame, g->ev_t0, g->ev_t1));
+    for (auto* sc : g->scenes) { CU(cudaSetDevice(sc->device)); rc = check_overflow(sc, slot_stream(sc, sc->cur)); if (rc) return rc; }
+    return TRAY_OK;
+}
+
+int tray_cuda_group_readback_begin(tray_group* g, uint8_t* rgba_host, uint32_t slot) {
+    if (!g || slot > 1) return fail(TRAY_ERR_ARG, "bad argument");
+    tray_scene* s0 = g->scenes[0];
+    int rc = tray_cuda_frame_readback_begin(s0, rgba_host, slot);       // snapshots the frame target on devices[0], D2H on the copy stream
+    if (rc) return rc;
+    CU(cudaEventRecord(g->ev_snap[g->cur], slot_stream(s0, s0->cur)));
+    g->snap_pending[g->cur] = true;
+    return TRAY_OK;
+}
+
+int tray_cuda_group_readback_wait(tray_group* g, uint32_t slot) {
+    if (!g) return fail(TRAY_ERR_ARG, "NULL group");
+    return tray_cuda_frame_readback_wait(g->scenes[0], slot);
+}
+
+int tray_cuda_group_frame_ptr(tray_group* g, void** d_frame) {
+    if (!g || !d_frame) return fail(TRAY_ERR_ARG, "NULL argument");
+    *d_frame = g->target[g->cur];
+    return TRAY_OK;
+}
+
+int tray_cuda_group_sync(tray_group* g) {
+    if (!g) return fail(TRAY_ERR_ARG, "NULL group");
+    for (auto* sc : g->scenes) { int rc = tray_cuda_sync(sc); if (rc) return rc; }
+    return TRAY_OK;
+}
+
+int tray_cuda_start_multi(const int* devices, int n_devices,
+                          const void* bvh_bytes, uint64_t bvh_len, const void* instance_bytes, uint64_t instance_len,
+                          const void* tri_bytes, uint64_t tri_len, uint32_t tri_stride, uint32_t tlas_start, int use_tlas,
+                          const tray_view* view, uint32_t width, uint32_t height, float render_time_s, int benchmark,
+                          int animate, float* out_min_ms, float* out_mean_ms, uint32_t* out_frames) {
+    if (!view) return fail(TRAY_ERR_ARG, "NULL view");
+    if (bvh_len % 80 != 0) return fail(TRAY_ERR_ARG, "bvh_bytes length %llu is not a multiple of 80", (unsigned long long)bvh_len);
+    if (tri_stride == 0 || tri_len % tri_stride != 0) return fail(TRAY_ERR_ARG, "tri_bytes length is not a multiple of tri_stride");
+    if (instance_len % 4 != 0) return fail(TRAY_ERR_ARG, "instance_bytes length is not a multiple of 4");
+    tray_group* g = nullptr;
+    int rc = tray_cuda_group_create(bvh_bytes, bvh_len / 80, tri_bytes, tri_len / tri_stride, tri_stride,
+                                    use_tlas ? (const uint32_t*)instance_bytes : nullptr, use_tlas ? (uint32_t)(instance_len / 4) : 0u,
+                                    tlas_start, devices, n_devices, &g);
+    if (rc) return rc;
+    const uint32_t flags = TRAY_RENDER_BOUNCE | TRAY_RENDER_RGBA;
+    float min_ms = 3.402823466e+38f; double sum = 0; uint32_t frames = 0, frame_count = 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        if (benchmark) {   // untimed warm-up dispatch right before the timed one (rt_gpu_software.rs:289-295)
+            rc = tray_cuda_group_render(g, view, width, height, frame_count, flags);
+            if (rc) break;
+        }
+        float ms = 0.f;
+        rc = tray_cuda_group_render_timed(g, view, width, height, frame_count, flags, &ms);
+        if (rc) break;
+        if (ms < min_ms) min_ms = ms;
+        sum += ms; frames++;
+        if (animate) frame_count = frames;
+        const float el = std::chrono::duration<float>(std::chrono::steady_clock::now() - t0).count();
+        if (el > render_time_s) break;
+    }
+    if (!rc) rc = tray_cuda_group_sync(g);
+    tray_cuda_group_destroy(g);
     if (rc) return rc;
     if (out_min_ms) *out_min_ms = min_ms;
     if (out_mean_ms) *out_mean_ms = frames ? (float)(sum / frames) : 0.f;

@@ -26,7 +26,15 @@ EXPORTS = (
     "tray_cuda_scene_set_frame_target", "tray_cuda_render_timed", "tray_cuda_trace_any", "tray_cuda_trace_any_device",
     "tray_cuda_scene_build", "tray_cuda_scene_download", "tray_cuda_frame_readback_begin", "tray_cuda_frame_readback_wait",
     "tray_cuda_scene_build_tlas", "tray_cuda_scene_download_instances",
+    "tray_cuda_scene_set_variant", "tray_cuda_shard_items", "tray_cuda_scene_set_frames_in_flight", "tray_cuda_scene_fence",
+    "tray_cuda_scene_after", "tray_cuda_scene_set_geometry_offsets", "tray_cuda_hits_to_geometry",
+    "tray_cuda_group_create", "tray_cuda_group_destroy", "tray_cuda_group_size", "tray_cuda_group_scene",
+    "tray_cuda_group_set_frames_in_flight", "tray_cuda_group_render", "tray_cuda_group_render_timed",
+    "tray_cuda_group_readback_begin", "tray_cuda_group_readback_wait", "tray_cuda_group_frame_ptr", "tray_cuda_group_sync",
+    "tray_cuda_start_multi",
 )
+# semantic switches of tray_cuda_scene_set_variant (include/tray_cuda.h TRAY_VARIANT_*)
+VARIANT_BOX_DIVIDE, VARIANT_TIE_LAST, VARIANT_BOX_TMIN_RAY, VARIANT_ZERODIR_BOX_ONLY = 1, 2, 4, 8
 
 
 class TrayCudaError(RuntimeError):
@@ -141,6 +149,45 @@ def lib() -> C.CDLL:
         L.tray_cuda_start.restype = i32
         L.tray_cuda_start.argtypes = [vp, u64, vp, u64, vp, u64, u32, u32, i32, C.POINTER(TrayView), u32, u32,
                                       C.c_float, i32, i32, i32, f32p, f32p, C.POINTER(u32)]
+        L.tray_cuda_scene_set_variant.restype = i32
+        L.tray_cuda_scene_set_variant.argtypes = [vp, u32]
+        L.tray_cuda_shard_items.restype = u64
+        L.tray_cuda_shard_items.argtypes = [u32, u32, u32, u32]
+        L.tray_cuda_scene_set_frames_in_flight.restype = i32
+        L.tray_cuda_scene_set_frames_in_flight.argtypes = [vp, u32]
+        L.tray_cuda_scene_fence.restype = i32
+        L.tray_cuda_scene_fence.argtypes = [vp, vp]
+        L.tray_cuda_scene_after.restype = i32
+        L.tray_cuda_scene_after.argtypes = [vp, vp]
+        L.tray_cuda_scene_set_geometry_offsets.restype = i32
+        L.tray_cuda_scene_set_geometry_offsets.argtypes = [vp, vp, u32]
+        L.tray_cuda_hits_to_geometry.restype = i32
+        L.tray_cuda_hits_to_geometry.argtypes = [vp, vp, u64, vp, vp]
+        L.tray_cuda_group_create.restype = i32
+        L.tray_cuda_group_create.argtypes = [vp, u64, vp, u64, u32, vp, u32, u32, vp, i32, C.POINTER(vp)]
+        L.tray_cuda_group_destroy.restype = None
+        L.tray_cuda_group_destroy.argtypes = [vp]
+        L.tray_cuda_group_size.restype = i32
+        L.tray_cuda_group_size.argtypes = [vp]
+        L.tray_cuda_group_scene.restype = i32
+        L.tray_cuda_group_scene.argtypes = [vp, i32, C.POINTER(vp)]
+        L.tray_cuda_group_set_frames_in_flight.restype = i32
+        L.tray_cuda_group_set_frames_in_flight.argtypes = [vp, u32]
+        L.tray_cuda_group_render.restype = i32
+        L.tray_cuda_group_render.argtypes = [vp, C.POINTER(TrayView), u32, u32, u32, u32]
+        L.tray_cuda_group_render_timed.restype = i32
+        L.tray_cuda_group_render_timed.argtypes = [vp, C.POINTER(TrayView), u32, u32, u32, u32, f32p]
+        L.tray_cuda_group_readback_begin.restype = i32
+        L.tray_cuda_group_readback_begin.argtypes = [vp, vp, u32]
+        L.tray_cuda_group_readback_wait.restype = i32
+        L.tray_cuda_group_readback_wait.argtypes = [vp, u32]
+        L.tray_cuda_group_frame_ptr.restype = i32
+        L.tray_cuda_group_frame_ptr.argtypes = [vp, C.POINTER(vp)]
+        L.tray_cuda_group_sync.restype = i32
+        L.tray_cuda_group_sync.argtypes = [vp]
+        L.tray_cuda_start_multi.restype = i32
+        L.tray_cuda_start_multi.argtypes = [vp, i32, vp, u64, vp, u64, vp, u64, u32, u32, i32, C.POINTER(TrayView), u32, u32,
+                                            C.c_float, i32, i32, f32p, f32p, C.POINTER(u32)]
         _lib = L
     return _lib
 
@@ -259,7 +306,8 @@ class TrayCudaScene:
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
-            _lib.tray_cuda_scene_destroy(self._h)
+            if not getattr(self, "_borrowed", False):        # a scene borrowed from a TrayCudaGroup belongs to the group
+                _lib.tray_cuda_scene_destroy(self._h)
             self._h = C.c_void_p()
 
     __del__ = close
@@ -290,6 +338,34 @@ class TrayCudaScene:
 
     def set_counting(self, on: bool):
         _check(lib().tray_cuda_set_counting(self._h, int(on)))
+
+    def set_variant(self, flags: int):
+        """Run the other reading of the semantics that are sourced from memory of obvhs (VARIANT_* flags; 0 = default)."""
+        _check(lib().tray_cuda_scene_set_variant(self._h, int(flags)))
+
+    def set_frames_in_flight(self, n: int):
+        """1 (default) or 2: consecutive render() calls alternate between two frame slots / streams (include/tray_cuda.h)."""
+        _check(lib().tray_cuda_scene_set_frames_in_flight(self._h, int(n)))
+
+    def fence(self, cuda_stream: int = 0):
+        """`cuda_stream` (0 = the scene stream) waits for every frame enqueued so far."""
+        _check(lib().tray_cuda_scene_fence(self._h, cuda_stream or None))
+
+    def after(self, cuda_stream: int):
+        """Frames enqueued from now on start after the work already enqueued on `cuda_stream`."""
+        _check(lib().tray_cuda_scene_after(self._h, cuda_stream))
+
+    def set_geometry_offsets(self, tri_offsets):
+        """First global triangle of every BLAS / object (n + 1 entries) — the runner's running `tri_offset`, rt_gpu/mod.rs:45-47."""
+        off = np.ascontiguousarray(tri_offsets, dtype=np.uint32)
+        _check(lib().tray_cuda_scene_set_geometry_offsets(self._h, off.ctypes.data if off.size else None, max(0, off.size - 1)))
+
+    def hits_to_geometry(self, hits: np.ndarray):
+        """(geometry_id, primitive_id) per hit, as `CwBvhTlasScene::traverse` reports them (src/cwbvh.rs:144-166)."""
+        hits = np.ascontiguousarray(hits, dtype=HIT_DTYPE)
+        g, pr = np.empty(hits.shape[0], dtype=np.uint32), np.empty(hits.shape[0], dtype=np.uint32)
+        _check(lib().tray_cuda_hits_to_geometry(self._h, hits.ctypes.data, hits.shape[0], g.ctypes.data, pr.ctypes.data))
+        return g, pr
 
     def counters(self):
         a, b = Counters(), Counters()
@@ -374,6 +450,91 @@ class TrayCudaScene:
 
     def untile_rgba(self, d_compact: int, width: int, height: int, shard: int, shards: int, d_frame: int):
         _check(lib().tray_cuda_untile_rgba(self._h, d_compact, width, height, shard, shards, d_frame))
+
+
+class TrayCudaGroup:
+    """One process, several GPUs (include/tray_cuda.h `tray_group`): BVH replicated on `devices`, tiles dealt round-robin,
+    pixels stored straight into one row-major frame on devices[0] over peer access, completion by events."""
+
+    def __init__(self, bvh_bytes, tri_bytes, tri_stride=48, blas_offsets=None, tlas_start=0, devices=(0,)):
+        nodes, tris = _as_u8(bvh_bytes), _as_u8(tri_bytes)
+        blas = None if blas_offsets is None else np.ascontiguousarray(blas_offsets, dtype=np.uint32)
+        dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+        h = C.c_void_p()
+        _check(lib().tray_cuda_group_create(nodes.ctypes.data, nodes.size // 80, tris.ctypes.data, tris.size // tri_stride, tri_stride,
+                                            None if blas is None else blas.ctypes.data, 0 if blas is None else blas.size, tlas_start,
+                                            dev.ctypes.data, dev.size, C.byref(h)))
+        self._h = h
+        self.devices = list(devices)
+        self.frame_size = None
+
+    @classmethod
+    def from_packed(cls, p, devices=(0,)) -> "TrayCudaGroup":
+        return cls(p.bvh_bytes, p.tri_bytes, p.tri_stride, p.blas_offsets if p.use_tlas else None, p.tlas_start, devices)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value and _lib is not None:
+            _lib.tray_cuda_group_destroy(self._h)
+            self._h = C.c_void_p()
+
+    __del__ = close
+
+    def scene(self, i: int) -> "TrayCudaScene":
+        """Borrowed scene of devices[i] (do not close it)."""
+        h = C.c_void_p()
+        _check(lib().tray_cuda_group_scene(self._h, i, C.byref(h)))
+        sc = TrayCudaScene.__new__(TrayCudaScene)
+        sc._h, sc.tri_stride, sc.frame_size, sc._borrowed = h, None, self.frame_size, True
+        sc.frame_shard = (i, len(self.devices))
+        return sc
+
+    def set_frames_in_flight(self, n: int):
+        _check(lib().tray_cuda_group_set_frames_in_flight(self._h, int(n)))
+
+    def render(self, view: TrayView, width: int, height: int, frame_count: int = 0, flags: int = RENDER_BOUNCE | RENDER_RGBA, timed: bool = False):
+        self.frame_size = (width, height)
+        if timed:
+            ms = C.c_float()
+            _check(lib().tray_cuda_group_render_timed(self._h, C.byref(view), width, height, frame_count, flags, C.byref(ms)))
+            return ms.value
+        _check(lib().tray_cuda_group_render(self._h, C.byref(view), width, height, frame_count, flags))
+        return None
+
+    def readback_begin(self, rgba: np.ndarray, slot: int):
+        w, h = self.frame_size
+        assert rgba.dtype == np.uint8 and rgba.size == w * h * 4 and rgba.flags["C_CONTIGUOUS"]
+        _check(lib().tray_cuda_group_readback_begin(self._h, rgba.ctypes.data, slot))
+
+    def readback_wait(self, slot: int):
+        _check(lib().tray_cuda_group_readback_wait(self._h, slot))
+
+    def frame(self) -> np.ndarray:
+        """The last frame, (h, w, 4) uint8, synchronously."""
+        w, h = self.frame_size
+        out = np.zeros((h, w, 4), dtype=np.uint8)
+        self.readback_begin(out, 0)
+        self.readback_wait(0)
+        return out
+
+    def frame_ptr(self) -> int:
+        p = C.c_void_p()
+        _check(lib().tray_cuda_group_frame_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def sync(self):
+        _check(lib().tray_cuda_group_sync(self._h))
+
+
+def start_multi(devices, bvh_bytes, instance_bytes, tri_bytes, tlas_start, view: TrayView, width=1920, height=1080, render_time=1.0,
+                benchmark=True, animate=False, use_tlas=False, tri_stride=48):
+    """tray_cuda_start on several GPUs in ONE process (tray_cuda_start_multi).  Returns (min_ms, mean_ms, frames)."""
+    nodes, inst, tris = _as_u8(bvh_bytes), _as_u8(instance_bytes), _as_u8(tri_bytes)
+    dev = np.ascontiguousarray(list(devices), dtype=np.int32)
+    mn, mean, frames = C.c_float(), C.c_float(), C.c_uint32()
+    _check(lib().tray_cuda_start_multi(dev.ctypes.data, dev.size, nodes.ctypes.data, nodes.size, inst.ctypes.data, inst.size,
+                                       tris.ctypes.data, tris.size, tri_stride, tlas_start, int(use_tlas), C.byref(view), width, height,
+                                       float(render_time), int(benchmark), int(animate), C.byref(mn), C.byref(mean), C.byref(frames)))
+    return mn.value, mean.value, frames.value
 
 
 def shard_mask(width: int, height: int, shard: int, shards: int) -> np.ndarray:
