@@ -127,11 +127,11 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic(kernel="primary"):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture (profiles/), or None."""
+def ncu_figure(key):
+    """a per-launch figure of the committed ncu capture (profiles/roofline_traffic.json), or None"""
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
-        return json.load(open(p))[f"{kernel}_kernel_dram_bytes_per_launch"]
+        return json.load(open(p))[key]
     except Exception:
         return None
 
@@ -144,21 +144,29 @@ def build_scene(nthreads=0):
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_oracle_run(packed, mesh, seconds_budget: float, frames_min: int, w=960, h=540):
-    """The oracle (C restatement of rt_cpu) timed on this host's cores on a bounded sample of the workload:
-    the same scene and camera at w x h (a 2x2-decimated 1080p frame), primary + bounce, all host threads."""
+def host_threads() -> int:
+    """Every host core this process may use — NOT omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1 to its workers."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_oracle_run(packed, mesh, w, h, seconds_budget: float, frames_min: int):
+    """The oracle (C restatement of rt_cpu) timed on this host's cores on a bounded sample of the workload: whole frames of
+    the same scene, camera and frame size (primary + bounce), all host threads, as many frames as fit the time budget."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
     from tray_racing_b200 import host
     orc = ob.Oracle.from_packed(packed)
     view = host.view_from_camera(mesh.camera, w, h, packed.tlas_start)
-    threads = ob.lib().orc_max_threads()
-    orc.render(view, w, h, 0)                      # warm-up frame (page in the BVH)
+    threads = host_threads()
+    orc.render(view, w, h, 0, nthreads=threads)                      # warm-up frame (page in the BVH)
     times, rays = [], 0
     t_start = time.perf_counter()
     while len(times) < frames_min or (time.perf_counter() - t_start) < seconds_budget:
         t0 = time.perf_counter()
-        r = orc.render(view, w, h, 0)
+        r = orc.render(view, w, h, 0, nthreads=threads)
         times.append(time.perf_counter() - t0)
         rays = r["primary_totals"]["rays"] + r["bounce_totals"]["rays"]
         if len(times) >= 64:
@@ -166,35 +174,35 @@ def cpu_oracle_run(packed, mesh, seconds_budget: float, frames_min: int, w=960, 
     mean = sum(times) / len(times)
     return {"value": rays / mean / 1e6, "unit": UNIT, "cores": threads, "kind": "port",
             "simd": "AVX2 node test (8 children per vector), scalar triangle test" if ob.simd() else "scalar",
-            "sample": f"{len(times)} frames of the same scene+camera at {w}x{h} (decimated {WL['w']}x{WL['h']}; {rays} rays/frame, primary+bounce), mean frame time",
+            "sample": f"{len(times)} whole frames of the workload ({w}x{h}, {rays} rays/frame, primary+bounce), mean frame time",
             "ms_per_frame": mean * 1e3, "rays_per_frame": rays}, times
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU algorithm for this path.  The Rust reference cannot be built in this
-    image (no cargo/rustc; arithmetic in an un-vendored crate), so this is the oracle port, all host threads."""
+    image (no cargo/rustc; arithmetic in an un-vendored crate), so this is the oracle port, all host threads, on the SAME
+    frame as our arm (frame_size(): same scene, camera, width and height)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    mesh, packed = build_scene()
+    mesh, packed = build_scene(nthreads=host_threads())
     w, h = frame_size(args.gpus)
-    sw, sh = 960, 540
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import oracle_binding as ob
     from tray_racing_b200 import host
     orc = ob.Oracle.from_packed(packed)
-    view = host.view_from_camera(mesh.camera, sw, sh, packed.tlas_start)
-    threads = ob.lib().orc_max_threads()
+    view = host.view_from_camera(mesh.camera, w, h, packed.tlas_start)
+    threads = host_threads()
     for _ in range(args.warmup):
-        orc.render(view, sw, sh, 0)
+        orc.render(view, w, h, 0, nthreads=threads)
     t0 = time.perf_counter()
     rays = 0
     for _ in range(args.steps):
-        r = orc.render(view, sw, sh, 0)
+        r = orc.render(view, w, h, 0, nthreads=threads)
         rays += r["primary_totals"]["rays"] + r["bounce_totals"]["rays"]
     dt = time.perf_counter() - t0
     val = rays / dt / 1e6
-    sample = f"each step = one {sw}x{sh} frame (decimated {WL['w']}x{WL['h']}) of the same scene+camera, primary+bounce"
+    sample = f"each step = one whole {w}x{h} frame of the workload (same scene, camera and size as our arm), primary+bounce"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": WL["scaling"],
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -207,6 +215,197 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+class Rig:
+    """One rank's scene + the plumbing of a step: render this rank's tile shard, then the path's one exchange step
+    (every shard's pixels reach ONE row-major frame on rank 0) — for one or two frames in flight.
+
+    exchange "peer": rank 0 owns row-major frames that every rank maps (CUDA IPC); the traversal kernels store finished
+        pixels straight into them over NVLink; a 4-byte all-reduce ON THE FRAME'S OWN STREAM completes the frame (one NCCL
+        communicator per frame slot, so the two frames in flight never wait for each other's collective).
+    exchange "nccl": gather of the compact RGBA8 shards to rank 0 + one untile launch per shard (one frame at a time).
+    single GPU: compact buffer + one untile launch into the row-major frame."""
+
+    def __init__(self, torch, dist, cuda, scene, view, w, h, rank, world, local_rank, stream, exchange):
+        self.torch, self.dist, self.cuda, self.scene, self.view = torch, dist, cuda, scene, view
+        self.w, self.h, self.rank, self.world, self.local_rank, self.main = w, h, rank, world, local_rank, stream
+        self.exchange = exchange
+        self.in_flight, self.flags = 1, cuda.RENDER_BOUNCE | cuda.RENDER_RGBA
+        self.max_items = cuda.local_items(w, h, 0, world)
+        self.frames = [torch.zeros(h * w, dtype=torch.int32, device="cuda") for _ in range(2)] if (rank == 0 and (world == 1 or exchange == "nccl")) else None
+        self.gathered = [torch.empty(self.max_items, dtype=torch.int32, device="cuda") for _ in range(world)] if (rank == 0 and world > 1 and exchange == "nccl") else None
+        self.peer_frames, self.peer_ptrs = [], []          # 4 targets: a frame's target is reused 4 frames later (see e2e)
+        self.done = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(2)]
+        self.groups = [None, None]
+        self.ext = {}
+        self.k = 0
+        if world > 1 and exchange == "peer":
+            self.groups = [dist.new_group(list(range(world))), dist.new_group(list(range(world)))]
+            for _ in range(4):
+                if rank == 0:
+                    f = cuda.frame_alloc(w * h * 4, local_rank)
+                    self.peer_frames.append(f)
+                    box = [cuda.ipc_export(f, local_rank)]
+                else:
+                    box = [None]
+                dist.broadcast_object_list(box, src=0)
+                self.peer_ptrs.append(self.peer_frames[-1] if rank == 0 else cuda.ipc_open(box[0], local_rank))
+
+    def torch_stream(self, ptr):
+        if ptr == self.main.cuda_stream:
+            return self.main
+        if ptr not in self.ext:
+            self.ext[ptr] = self.torch.cuda.ExternalStream(ptr)
+        return self.ext[ptr]
+
+    def configure(self, overlap, in_flight):
+        self.scene.sync()
+        self.flags = self.cuda.RENDER_BOUNCE | self.cuda.RENDER_RGBA | (self.cuda.RENDER_OVERLAP if overlap else 0)
+        self.in_flight = in_flight if (self.world == 1 or self.exchange == "peer") else 1
+        self.scene.set_frames_in_flight(self.in_flight)
+        self.k = 0
+
+    def step(self):
+        sc, k = self.scene, self.k
+        self.k += 1
+        if self.world > 1 and self.exchange == "peer":
+            sc.set_frame_target(self.peer_ptrs[k & 3])
+            sc.render(self.view, self.w, self.h, 0, self.flags, self.rank, self.world, timed=False)
+            slot = 0 if sc.frame_stream(-1) == sc.frame_stream(0) else 1
+            with self.torch.cuda.stream(self.torch_stream(sc.frame_stream(-1))):
+                self.dist.all_reduce(self.done[slot], group=self.groups[slot])   # behind the kernels: frame complete on rank 0
+        elif self.world > 1:
+            sc.render(self.view, self.w, self.h, 0, self.flags, self.rank, self.world, timed=False)
+            _, _, d_rgba = sc.frame_device_ptrs()
+            local = self.torch.as_tensor(self.cuda.DeviceArray(d_rgba, (self.max_items,), "<i4", sc), device="cuda")
+            self.dist.gather(local, self.gathered, dst=0)
+            if self.rank == 0:
+                for s in range(self.world):
+                    sc.untile_rgba(self.gathered[s].data_ptr(), self.w, self.h, s, self.world, self.frames[0].data_ptr())
+        else:
+            sc.render(self.view, self.w, self.h, 0, self.flags, 0, 1, timed=False)
+            _, _, d_rgba = sc.frame_device_ptrs()
+            sc.untile_rgba(d_rgba, self.w, self.h, 0, 1, self.frames[k & 1].data_ptr())      # on the frame's own stream
+        return k
+
+    def last_frame_tensor(self, k):
+        """rank 0: the row-major frame step k produced, as an int32 tensor"""
+        if self.world > 1 and self.exchange == "peer":
+            return self.torch.as_tensor(self.cuda.DeviceArray(self.peer_frames[k & 3], (self.h * self.w,), "<i4", self.scene), device="cuda")
+        return self.frames[0 if self.world > 1 else (k & 1)]
+
+    def sync_all(self):
+        self.scene.sync()
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def timed_run(self, steps, flush_buf=None):
+        """CUDA-event time of `steps` steps on this rank (ms).  One frame at a time: one event pair per step on the launching
+        stream, the L2 flush between steps outside the pairs.  Two frames in flight: one pair around the whole run — the first
+        event ahead of every frame (tray_cuda_scene_after), the second behind all of them (tray_cuda_scene_fence)."""
+        torch = self.torch
+        self.sync_all()
+        if self.in_flight == 1:
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+            for i in range(steps):
+                if flush_buf is not None:
+                    flush_buf.fill_(i & 0xff)                   # L2 flush between timed iterations (not in the timed span)
+                ev[i][0].record(self.main)
+                self.step()
+                ev[i][1].record(self.main)
+            self.sync_all()
+            return sum(a.elapsed_time(b) for a, b in ev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(self.main)
+        self.scene.after(self.main.cuda_stream)
+        for _ in range(steps):
+            self.step()
+        self.scene.fence(self.main.cuda_stream)
+        e1.record(self.main)
+        self.sync_all()
+        return e0.elapsed_time(e1)
+
+    def close(self):
+        if self.rank != 0:
+            for p in self.peer_ptrs:
+                self.cuda.ipc_close(p, self.local_rank)
+        if self.world > 1:
+            self.dist.barrier()
+        for f in self.peer_frames:
+            self.cuda.frame_free(f, self.local_rank)
+
+
+def max_over_ranks(torch, dist, world, x):
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def strong_scaling_record(torch, dist, cuda, host, rank, world, local_rank, stream, steps):
+    """BASELINE.json configs[3] inside every --gpus N line: the San-Miguel-sized scene at a FIXED 3840x2160 frame, tiles dealt
+    over the N ranks (strong scaling).  speedup_vs_n1 = this run's own one-GPU time (rank 0 renders the whole frame alone, the
+    other ranks idle) / the N-GPU time — same box, same build, same protocol.  The BVH is built on each rank's GPU from the
+    triangle soup (tray_cuda_scene_build: deterministic, so the replicas agree)."""
+    global WL
+    saved = WL
+    WL = WORKLOADS["c4"]
+    try:
+        w, h = WL["w"], WL["h"]
+        mesh = host.Mesh.generate(WL["scene"], WL["seed"], 1.0)
+        scene = cuda.TrayCudaScene.build(mesh.tris(), tri_stride=TRI_STRIDE, device=local_rank)
+        scene.set_stream(stream.cuda_stream)
+        view = host.view_from_camera(mesh.camera, w, h, 0)
+        flags = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA
+        scene.render(view, w, h, 0, flags | cuda.RENDER_COUNTERS, rank, world)
+        cp, cb = scene.counters()
+        rays = torch.tensor([cp["rays"] + cb["rays"]], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(rays)
+        rays = float(rays.item())
+        out = {"workload": f"{WL['label']} ({mesh.n_tris} tris, BVH built on the device), fixed {w}x{h} frame, tiles dealt over {world} GPU(s), primary + 1spp bounce",
+               "rays_per_step": rays}
+        rig = Rig(torch, dist, cuda, scene, view, w, h, rank, world, local_rank, stream, "peer" if world > 1 else "local")
+        for in_flight in (2, 1):
+            rig.configure(False, in_flight)
+            for _ in range(4):
+                rig.step()
+            ms = max_over_ranks(torch, dist, world, rig.timed_run(steps)) / steps
+            rec = {"ms_per_step": ms, "value": rays / ms / 1e3}
+            if world > 1:
+                # the one-GPU time of the same frame in the same run: rank 0 alone, whole frame
+                n1 = 0.0
+                scene.sync()
+                scene.set_frame_target(None)
+                if rank == 0:
+                    solo = Rig(torch, dist, cuda, scene, view, w, h, 0, 1, local_rank, stream, "local")
+                    solo.configure(False, in_flight)
+                    for _ in range(3):
+                        solo.step()
+                    torch.cuda.synchronize()
+                    n1 = solo.timed_run(max(5, steps // 2)) / max(5, steps // 2)
+                    scene.sync()
+                n1 = max_over_ranks(torch, dist, world, n1)
+                rec["n1_ms_per_step"] = n1
+                rec["speedup_vs_n1"] = n1 / ms
+            else:
+                rec["n1_ms_per_step"], rec["speedup_vs_n1"] = ms, 1.0
+            if in_flight == 2:
+                out.update(rec)
+                out["frames_in_flight"] = 2
+            else:
+                out["one_frame_at_a_time"] = rec
+        out["unit"] = UNIT
+        out["note"] = ("ms_per_step = CUDA-event time of the steps / steps, max over ranks, exchange included (kernels store pixels into "
+                       "rank 0's frame over NVLink, all-reduce completes the frame); no L2 flush (working set 300 MB > 126 MB L2)")
+        rig.close()
+        scene.close()
+        return out
+    finally:
+        WL = saved
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -226,171 +425,98 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    ncpu = os.cpu_count() or 8
+    ncpu = host_threads()
     mesh, packed = build_scene(nthreads=max(1, ncpu // world))
     w, h = frame_size(world)
     view = host.view_from_camera(mesh.camera, w, h, packed.tlas_start)
     scene = cuda.TrayCudaScene.from_packed(packed, device=local_rank)
-    # one explicit (non-default) torch stream carries the kernels, the NCCL gather, the untile and the timing events
+    # one explicit (non-default) torch stream carries slot-0 frames, the collectives, the untile and the timing events
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     assert stream.cuda_stream != 0
     scene.set_stream(stream.cuda_stream)
-    # two bit-identical ways to render the frame: two launches, or the one-launch frame kernel (TRAY_RENDER_OVERLAP).  Which is
-    # faster depends on the scene's drain phases (measured: -4 % on C3, +0.5 % / +3.7 % on the kitchen- and San-Miguel-sized
-    # scenes), so the bench picks it the way tray_cuda_start does; TRAY_BENCH_OVERLAP=0|1 forces it
+    steps, warmup = args.steps, max(args.warmup, 3)
+
+    exchange = args.exchange
+    if world == 1:
+        exchange = "local"
+    elif exchange == "auto":
+        exchange = "peer"
+    try:
+        rig = Rig(torch, dist, cuda, scene, view, w, h, rank, world, local_rank, stream, exchange)
+    except cuda.TrayCudaError as e:
+        if args.exchange == "peer":
+            raise
+        print(f"[bench] rank {rank}: peer frame unavailable ({e}); falling back to the NCCL gather", file=sys.stderr)
+        exchange = "nccl"
+        rig = Rig(torch, dist, cuda, scene, view, w, h, rank, world, local_rank, stream, exchange)
+
+    # ---- which of the bit-identical ways to run the frames: two launches / one-launch frame kernel x one / two frames in flight.
+    # An untimed calibration decides, the way tray_cuda_start picks its frame path (TRAY_BENCH_OVERLAP / TRAY_BENCH_IN_FLIGHT force).
+    f_overlap, f_inflight = os.environ.get("TRAY_BENCH_OVERLAP"), os.environ.get("TRAY_BENCH_IN_FLIGHT")
+    calib = {}
+    for ov in ((False, True) if f_overlap is None else (f_overlap != "0",)):
+        for nf in ((1, 2) if f_inflight is None else (int(f_inflight),)):
+            rig.configure(ov, nf)
+            for _ in range(3):
+                rig.step()
+            calib[(ov, rig.in_flight)] = max_over_ranks(torch, dist, world, rig.timed_run(10)) / 10
+    (overlap, in_flight), _ = min(calib.items(), key=lambda kv: kv[1])
     flags2 = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA            # the two-launch path: per-kernel figures, counters
-    forced = os.environ.get("TRAY_BENCH_OVERLAP")
-    if forced is not None:
-        overlap, calib = forced != "0", None
-    else:
-        # untimed calibration, as tray_cuda_start does it: a few frames of each path on this rank's shard, the slowest rank counts
-        best = [float("inf"), float("inf")]
-        for rep in range(5):
-            for path in (0, 1):
-                a, b = scene.render(view, w, h, 0, flags2 | (cuda.RENDER_OVERLAP if path else 0), rank, world, timed=True)
-                if rep > 0:
-                    best[path] = min(best[path], a + b)
-        bt = torch.tensor(best, dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(bt, op=dist.ReduceOp.MAX)
-        calib = {"two_launches_ms": float(bt[0]), "one_launch_ms": float(bt[1])}
-        overlap = calib["one_launch_ms"] < calib["two_launches_ms"]
-    flags = flags2 | (cuda.RENDER_OVERLAP if overlap else 0)
-    n_items = cuda.local_items(w, h, rank, world)
-    max_items = cuda.local_items(w, h, 0, world)
 
     # one counting frame (outside the timed region): rays and algorithmic bytes per step
+    rig.configure(False, 1)
     scene.render(view, w, h, 0, flags2 | cuda.RENDER_COUNTERS, rank, world)
     cp, cb = scene.counters()
-    scene.render(view, w, h, 0, flags, rank, world)       # switch back to the non-counting kernels
-    _, _, d_rgba = scene.frame_device_ptrs()
-    rgba_local = torch.as_tensor(cuda.DeviceArray(d_rgba, (max_items,), "<i4", scene), device="cuda")
-    gathered = [torch.empty(max_items, dtype=rgba_local.dtype, device="cuda") for _ in range(world)] if (rank == 0 and world > 1) else None
-    frame = torch.zeros(h * w, dtype=torch.int32, device="cuda") if rank == 0 else None
+    scene.render(view, w, h, 0, flags2, rank, world)          # switch back to the non-counting kernels
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
 
-    # ---- the one exchange step: every shard's pixels reach ONE row-major frame on rank 0 ----
-    #   peer: rank 0 owns the frame, the other ranks map it (CUDA IPC) and their traversal kernels store finished
-    #         pixels straight into it over NVLink while tracing; a 4-byte all-reduce is the completion barrier
-    #   nccl: gather the compact RGBA shards to rank 0, one untile launch per shard
-    exchange, peer_frame, peer_ptr, done = args.exchange, None, None, None
-    peer_frame2, peer_ptr2 = None, None                   # second frame: the e2e loop alternates targets (readback overlap)
-    if exchange == "auto" and world == 1:
-        exchange = "nccl"           # one GPU: nothing to exchange; compact buffer + one untile launch measured 1.8 % faster
-    if exchange in ("auto", "peer"):
-        try:
-            if rank == 0:
-                peer_frame = cuda.frame_alloc(w * h * 4, local_rank)
-                peer_frame2 = cuda.frame_alloc(w * h * 4, local_rank) if world > 1 else None
-                box = [cuda.ipc_export(peer_frame, local_rank), cuda.ipc_export(peer_frame2, local_rank) if world > 1 else None]
-            else:
-                box = [None, None]
-            if world > 1:
-                dist.broadcast_object_list(box, src=0)
-            peer_ptr = peer_frame if rank == 0 else cuda.ipc_open(box[0], local_rank)
-            if world > 1:
-                peer_ptr2 = peer_frame2 if rank == 0 else cuda.ipc_open(box[1], local_rank)
-            ok = torch.ones(1, device="cuda")
-        except cuda.TrayCudaError as e:
-            if exchange == "peer":
-                raise
-            print(f"[bench] rank {rank}: peer frame unavailable ({e}); falling back to the NCCL gather", file=sys.stderr)
-            ok = torch.zeros(1, device="cuda")
-        if world > 1:
-            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        exchange = "peer" if float(ok.item()) > 0 else "nccl"
-    if exchange == "peer":
-        done = torch.zeros(1, dtype=torch.int32, device="cuda")
-
-    def step_nccl():
-        scene.render(view, w, h, 0, flags, rank, world, timed=False)
-        if world > 1:
-            dist.gather(rgba_local, gathered, dst=0)
-            if rank == 0:
-                for s in range(world):
-                    scene.untile_rgba(gathered[s].data_ptr(), w, h, s, world, frame.data_ptr())
-        else:
-            scene.untile_rgba(d_rgba, w, h, 0, 1, frame.data_ptr())
-
-    def step_peer():
-        scene.render(view, w, h, 0, flags, rank, world, timed=False)
-        if world > 1:
-            dist.all_reduce(done)                       # stream-ordered after the kernels: frame complete on rank 0
-
-    if exchange == "peer":
-        # bit-equality of the two exchange paths, once, outside the timed region
-        step_nccl()
-        scene.set_frame_target(peer_ptr)
-        step_peer()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        exchange_verified = None
+    # ---- bit-equality of the exchange paths, once, outside the timed region: peer frame == NCCL gather + untile ----
+    exchange_verified = None
+    if world > 1 and exchange == "peer":
+        chk = Rig(torch, dist, cuda, scene, view, w, h, rank, world, local_rank, stream, "nccl")
+        chk.configure(overlap, 1); chk.step(); chk.sync_all()
+        rig.configure(overlap, in_flight); k = rig.step(); rig.sync_all()
         if rank == 0:
-            got = torch.as_tensor(cuda.DeviceArray(peer_frame, (h * w,), "<i4", scene), device="cuda")
-            exchange_verified = bool(torch.equal(got, frame))
-        step = step_peer
-    else:
-        exchange_verified = None
-        step = step_nccl
+            exchange_verified = bool(torch.equal(rig.last_frame_tensor(k), chk.last_frame_tensor(0)))
+        scene.set_frame_target(None)
 
-    def sync_all():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
+    # ---- headline: `steps` timed steps in the calibrated mode ----
+    rig.configure(overlap, in_flight)
+    for _ in range(warmup):
         flush_buf.fill_(1)
-        step()
-    sync_all()
-
+        rig.step()
+    rig.sync_all()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
         time.sleep(0.25)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    sync_all()
     t_wall0 = time.time()
-    for k in range(args.steps):
-        flush_buf.fill_(k & 0xff)                       # L2 flush between timed iterations (not in the timed span)
-        ev[k][0].record(stream)
-        step()
-        ev[k][1].record(stream)
-    sync_all()
+    total_ms = rig.timed_run(steps, flush_buf)
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    total_ms = max_over_ranks(torch, dist, world, total_ms)
     rays_step = torch.tensor([cp["rays"] + cb["rays"], cp["rays"], cb["rays"]], dtype=torch.float64, device="cuda")
     if world > 1:
-        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
         dist.all_reduce(rays_step, op=dist.ReduceOp.SUM)
-    total_ms = float(total_ms.item())
     rays_all, rays_p, rays_b = (float(x) for x in rays_step.tolist())
-    value = rays_all * args.steps / (total_ms * 1e-3) / 1e6
+    value = rays_all * steps / (total_ms * 1e-3) / 1e6
 
-    # the same steps WITHOUT the L2 flush (consecutive frames of one scene, the case the persisting-L2 window over the node
-    # array is for): reported beside the headline, never instead of it
-    warm_steps = max(5, min(args.steps, 50))
-    sync_all()
-    w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    w0.record(stream)
-    for _ in range(warm_steps):
-        step()
-    w1.record(stream)
-    sync_all()
-    warm_ms = torch.tensor([w0.elapsed_time(w1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(warm_ms, op=dist.ReduceOp.MAX)
-    warm_ms = float(warm_ms.item()) / warm_steps
+    # ---- beside it: one frame at a time with the L2 flushed between steps (round 1's protocol), and without the flush ----
+    side = {}
+    for name, nf, fl in (("one_frame_at_a_time_l2_flushed", 1, flush_buf), ("one_frame_at_a_time_warm_l2", 1, None)):
+        rig.configure(overlap, nf)
+        for _ in range(3):
+            rig.step()
+        n = max(5, min(steps, 50))
+        ms = max_over_ranks(torch, dist, world, rig.timed_run(n, fl)) / n
+        side[name] = {"ms_per_step": ms, "value": rays_all / ms / 1e3}
 
-    if exchange == "peer":
-        scene.set_frame_target(None)                    # the per-rank measurements below use the compact local buffers
-    # ---- dominant kernel alone (this rank): live CUDA-event duration of primary and bounce launches ----
+    scene.set_frame_target(None)                       # the per-rank measurements below use the compact local buffers
+    rig.configure(False, 1)
+    # ---- the traversal kernels alone (this rank): live CUDA-event duration of primary and bounce launches, L2 flushed ----
     kp, kb = [], []
-    for _ in range(max(5, min(args.steps, 20))):
+    for _ in range(max(5, min(steps, 20))):
         flush_buf.fill_(3)
         a, b = scene.render(view, w, h, 0, flags2, rank, world, timed=True)
         kp.append(a); kb.append(b)
@@ -398,88 +524,89 @@ def run_ours(args):
     kf_ms = None
     if overlap:                                        # the frame kernel (+ primary ray generation), CUDA events, L2 flushed
         kf = []
-        for _ in range(max(5, min(args.steps, 20))):
+        for _ in range(max(5, min(steps, 20))):
             flush_buf.fill_(3)
-            kf.append(scene.render(view, w, h, 0, flags, rank, world, timed=True)[0])
+            kf.append(scene.render(view, w, h, 0, flags2 | cuda.RENDER_OVERLAP, rank, world, timed=True)[0])
         kf_ms = sum(kf) / len(kf)
     bytes_p = 80 * cp["nodes"] + TRI_STRIDE * cp["tris"] + 4 * cp["instances"] + 8 * cp["rays"]
     bytes_b = 80 * cb["nodes"] + TRI_STRIDE * cb["tris"] + 4 * cb["instances"] + 8 * cb["rays"] + 8 * cp["rays"]
-    peak, peak_src = measured_peaks()
+    hbm_peak, hbm_src = measured_peaks()
     l2_peak = cuda.bandwidth_probe(48 << 20, 50, local_rank)          # streaming read of an L2-resident 48 MiB buffer
     hbm_read = cuda.bandwidth_probe(2048 << 20, 8, local_rank)        # same kernel, buffer >> L2
-    dominant = "frame" if overlap else ("primary" if kp_ms >= kb_ms else "bounce")
-    # frame kernel: both ray kinds in one launch (the 8 B/pixel primary hit is written and read back inside it)
-    dom_bytes = {"frame": bytes_p + bytes_b, "primary": bytes_p, "bounce": bytes_b}[dominant]
-    dom_ms = {"frame": kf_ms, "primary": kp_ms, "bounce": kb_ms}[dominant]
-    ach = dom_bytes / dom_ms / 1e6                     # GB/s
 
     # ---- end to end through the public API with HOST buffers ----
-    # Every step: tray_cuda_render on every rank (view + frame parameters go in by value, 160 B per rank), the exchange
-    # step, and the readback of that frame's RGBA8 into pinned host memory (tray_cuda_frame_readback_begin / _wait: staging
-    # on the scene stream, D2H on the copy stream, double-buffered, so the copy of frame k overlaps the kernels of frame
-    # k + 1).  N = 1: the rank's own frame.  N > 1: the frame assembled on rank 0 (peer exchange: two frame targets used
-    # alternately, rank 0 snapshots the complete frame after the barrier; NCCL exchange: rank 0 copies the gathered frame).
-    # Frame k is waited for — i.e. is in host memory — before frame k + 2 is issued, and the last frames are waited for
-    # inside the timed region.
-    host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)] if (rank == 0 or world == 1) else None
-    host_t = [torch.from_numpy(a) for a in host_frames] if (host_frames is not None and world > 1 and exchange != "peer") else None
-    e2e_steps = max(3, min(args.steps, 50))
-    targets = [peer_ptr, peer_ptr2] if (world > 1 and exchange == "peer") else None
+    # Every step: tray_cuda_render on every rank (view + frame parameters go in by value, 160 B per rank), the exchange step,
+    # and the readback of that frame's RGBA8 into pinned host memory on rank 0, double-buffered: the D2H of frame k overlaps the
+    # kernels of frame k+1; frame k is in host memory before frame k+2 is issued, the last frames are waited for inside the
+    # timed region.  N = 1: tray_cuda_frame_readback_begin / _wait.  N > 1 (peer exchange): rank 0 copies the complete frame
+    # out of its target on the frame's own stream, behind the all-reduce that completes it; a target is reused four frames later,
+    # i.e. behind the next-but-one collective of its slot, which rank 0 only joins once the copy has been enqueued ahead of it.
+    rig.configure(overlap, in_flight)
+    e2e_steps = max(3, min(steps, 50))
+    owner = rank == 0
+    host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)] if owner else None
+    copy_ev = [None, None]
 
-    def e2e_step(i, wait_prev=True):
-        slot = i & 1
-        if targets:
-            scene.set_frame_target(targets[slot])
-            scene.render(view, w, h, 0, flags, rank, world, timed=False)
-            dist.all_reduce(done)                       # frame i complete in targets[slot] on rank 0
-            if rank == 0:
-                scene.readback_begin(host_frames[slot], slot)
-        elif world > 1:
-            step_nccl()                                 # gather + untile into `frame` on rank 0
-            if rank == 0:
-                host_t[slot].view(-1).view(torch.int32).copy_(frame, non_blocking=False)
-        else:
-            scene.render(view, w, h, 0, flags, rank, world, timed=False)
-            scene.readback_begin(host_frames[slot], slot)
-        if wait_prev and i > 0 and (rank == 0 or world == 1) and (targets or world == 1):
-            scene.readback_wait(slot ^ 1)
+    def e2e_step(i):
+        b = i & 1
+        if world == 1:
+            scene.render(view, w, h, 0, rig.flags, 0, 1, timed=False)
+            scene.readback_begin(host_frames[b].numpy(), b)       # untile on the frame's stream, D2H on the copy stream
+            if i > 0:
+                scene.readback_wait(b ^ 1)
+            return
+        k = rig.step()
+        if owner:
+            if copy_ev[b] is not None:
+                copy_ev[b].synchronize()                # host buffer b is free again (frame i-2 has landed)
+            st = rig.torch_stream(scene.frame_stream(-1)) if exchange == "peer" else stream
+            with torch.cuda.stream(st):
+                host_frames[b].view(-1).view(torch.int32).copy_(rig.last_frame_tensor(k), non_blocking=True)
+                copy_ev[b] = torch.cuda.Event(); copy_ev[b].record(st)
+            if i > 0 and copy_ev[b ^ 1] is not None:
+                copy_ev[b ^ 1].synchronize()
 
-    e2e_step(0, wait_prev=False)                        # untimed: both staging slots allocated, copy stream warm
-    e2e_step(1, wait_prev=True)
-    if rank == 0 or world == 1:
-        scene.readback_wait(0)
-        scene.readback_wait(1)
-    sync_all()
+    def e2e_drain():
+        if world == 1:
+            scene.readback_wait(0); scene.readback_wait(1)
+        elif owner:
+            for e in copy_ev:
+                if e is not None:
+                    e.synchronize()
+
+    e2e_step(0); e2e_step(1); e2e_drain()             # untimed: staging allocated, copy paths warm
+    rig.sync_all()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(i)
-    if rank == 0 or world == 1:
-        scene.readback_wait((e2e_steps - 1) & 1)
+    e2e_drain()
+    scene.sync()
     torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    if targets:
-        scene.set_frame_target(None)
+    e2e_s = max_over_ranks(torch, dist, world, time.perf_counter() - t0)
+    e2e_val = rays_all * e2e_steps / e2e_s / 1e6
     # the same, fully synchronous (render, then download, then the next frame): what a caller without the readback pair gets
-    into = {"rgba": host_frames[0] if host_frames is not None else np.zeros((h, w, 4), dtype=np.uint8)}
-    scene.render(view, w, h, 0, flags, rank, world, timed=False); scene.download(rgba=True, into=into)     # allocates its staging
-    sync_all()
+    scene.set_frame_target(None)
+    rig.configure(overlap, 1)
+    into = {"rgba": host_frames[0].numpy() if owner else np.zeros((h, w, 4), dtype=np.uint8)}
+    scene.render(view, w, h, 0, rig.flags, rank, world, timed=False); scene.download(rgba=True, into=into)     # allocates its staging
+    rig.sync_all()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        scene.render(view, w, h, 0, flags, rank, world, timed=False)
+        scene.render(view, w, h, 0, rig.flags, rank, world, timed=False)
         scene.download(rgba=True, into=into)
     torch.cuda.synchronize()
-    e2e_sync_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_sync_s, op=dist.ReduceOp.MAX)
-    e2e_sync_val = rays_all * e2e_steps / float(e2e_sync_s.item()) / 1e6
-    e2e_val = rays_all * e2e_steps / float(e2e_s.item()) / 1e6
+    e2e_sync_val = rays_all * e2e_steps / max_over_ranks(torch, dist, world, time.perf_counter() - t0) / 1e6
+
+    # ---- strong scaling on BASELINE.json configs[3] (every N), outside every timed region above ----
+    strong = None
+    if args.workload == "c3" and os.environ.get("TRAY_BENCH_STRONG", "1") != "0":
+        strong = strong_scaling_record(torch, dist, cuda, host, rank, world, local_rank, stream, max(10, min(steps, 40)))
 
     # ---- beside the headline (N = 1 only, outside every timed region above): the rows SURVEY.md §8 marks "next" ----
     extras = None
     if rank == 0 and world == 1 and args.workload == "c3":
         extras = {}
+        rig.configure(False, 1)
         # f4: AO rays as an any-hit query (rt_cpu.rs:78-79) — same rays, each stopped at its first hit
         ka = [scene.render(view, w, h, 0, flags2 | cuda.RENDER_ANYHIT_AO, rank, world, timed=True) for _ in range(6)][1:]
         kb_any = min(b for _, b in ka)
@@ -505,66 +632,98 @@ def run_ours(args):
                                     "bounce_kernel_ms_on_device_built_bvh": min(b for _, b in kg),
                                     "note": "PLOC radius 14 on the GPU vs binned SAH on the host cores; same collapse + encoder"}
         g.close()
+        # b: the one-process entry point on this box's GPU(s): tray_group (peer access + events, no torch / NCCL) gives the same frame
+        grp = cuda.TrayCudaGroup.from_packed(packed, devices=[local_rank])
+        grp.set_frames_in_flight(2)
+        for _ in range(4):
+            grp.render(view, w, h, 0, flags2)
+        grp.sync()
+        t0 = time.perf_counter()
+        for _ in range(40):
+            grp.render(view, w, h, 0, flags2)
+        grp.sync()
+        gms = (time.perf_counter() - t0) * 1e3 / 40
+        same = bool((grp.frame().reshape(-1).view(np.int32) == rig.frames[0].cpu().numpy()).all()) if rig.frames is not None else None
+        extras["single_process_group"] = {"devices": 1, "ms_per_frame": gms, "mrays_s": rays_all / gms / 1e3, "frames_in_flight": 2,
+                                          "frame_equals_bench_frame": same, "note": "tray_cuda_group_render, two-launch path, host wall clock over 40 frames"}
+        grp.close()
 
     if rank == 0:
-        cpu_base, _ = cpu_oracle_run(packed, mesh, seconds_budget=10.0, frames_min=3) if world == 1 else (None, None)
+        cpu_base, _ = cpu_oracle_run(packed, mesh, w, h, seconds_budget=10.0, frames_min=3) if world == 1 else (None, None)
+        clk_hz = (clocks or {}).get("sm_mhz") or 1965.0
+        sm_count = scene.info()["sm_count"]
+        issue_peak = sm_count * 4 * clk_hz * 1e6                    # warp instructions per second the chip can issue
+        winst_p = ncu_figure("primary_kernel_warp_inst_per_launch") if (args.workload == "c3" and world == 1) else None
+        tinst_p = ncu_figure("primary_kernel_thread_inst_per_launch") if (args.workload == "c3" and world == 1) else None
+        roof = {
+            # what the north_star names: the node + triangle bytes the PRIMARY rays fetch x rays/s against the measured L2 bandwidth
+            "bound": "l2", "kernel": "trace_kernel (primary rays; two-launch path, CUDA events, L2 flushed before each launch)",
+            "achieved": bytes_p / kp_ms / 1e6, "peak": l2_peak, "unit": "GB/s", "frac": bytes_p / kp_ms / 1e6 / l2_peak,
+            "peak_source": "measured in this run: streaming 16-byte reads of an L2-resident 48 MiB buffer by a chip-filling grid "
+                           "(tray_cuda_bandwidth_probe); MEASURED_PEAKS.json holds no L2 figure",
+            "traffic": ncu_figure("primary_kernel_dram_bytes_per_launch") if args.workload == "c3" else None,
+            "algorithmic_bytes_per_launch": bytes_p, "bytes_per_ray": bytes_p / max(1, cp["rays"]), "ms_per_launch": kp_ms,
+            "nodes_per_ray": cp["nodes"] / max(1, cp["rays"]), "tris_per_ray": cp["tris"] / max(1, cp["rays"]),
+            "what_binds": "SM issue slots, not a memory pipe: DRAM moves ~4 % of the algorithmic bytes, L2 runs at ~12 % of its throughput (ncu, profiles/)",
+            "issue": {"peak_warp_inst_per_s": issue_peak, "sm_mhz": clk_hz,
+                      "warp_inst_per_launch": winst_p, "thread_inst_per_launch": tinst_p,
+                      "warp_inst_per_ray": (winst_p / cp["rays"]) if winst_p else None,
+                      "lanes_per_inst": (tinst_p / winst_p) if (winst_p and tinst_p) else None,
+                      "frac_of_issue_peak": (winst_p / (kp_ms * 1e-3) / issue_peak) if winst_p else None,
+                      "note": "instruction counts per launch from the committed ncu capture of this kernel (profiles/roofline_traffic.json), duration live"},
+            "hbm": {"peak": hbm_peak, "peak_source": hbm_src, "frac": bytes_p / kp_ms / 1e6 / hbm_peak,
+                    "hbm_read_gbs_measured_here": hbm_read, "note": "side figure: the kernel is not HBM-bound (see traffic)"},
+            "bounce_kernel": {"achieved": bytes_b / kb_ms / 1e6 if cb["rays"] else None, "frac": (bytes_b / kb_ms / 1e6 / l2_peak) if cb["rays"] else None,
+                              "ms_per_launch": kb_ms, "algorithmic_bytes_per_launch": bytes_b},
+        }
+        if kf_ms:
+            roof["frame_kernel"] = {"achieved": (bytes_p + bytes_b) / kf_ms / 1e6, "frac": (bytes_p + bytes_b) / kf_ms / 1e6 / l2_peak,
+                                    "ms_per_launch": kf_ms, "algorithmic_bytes_per_launch": bytes_p + bytes_b,
+                                    "note": "trace_kernel<FRAME>: both ray kinds in one launch; span includes raygen_primary"}
+        per_frame = (2 if overlap else 4) + (0 if exchange == "peer" else 1)
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": WL["scaling"], "vs_baseline": None,
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
+            "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": WL["scaling"], "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(w, h, world), "n_tris": packed.n_tris, "n_nodes": packed.n_nodes,
                        "working_set_mb": round(packed.working_set_bytes() / 1e6, 1), "tri_stride": TRI_STRIDE,
                        "rays_per_step": {"primary": rays_p, "bounce": rays_b},
                        "frame_path": ("one launch per frame (TRAY_RENDER_OVERLAP: raygen_primary + trace_kernel<FRAME>)" if overlap
                                       else "two launches per frame (raygen_primary, trace, raygen_bounce, trace)"),
-                       "frame_path_calibration": calib if calib is not None else "forced by TRAY_BENCH_OVERLAP",
-                       "l2": "flushed between timed steps (256 MiB device write)", "parallelism": f"tile-sharded x{world}, BVH replicated",
-                       "exchange": ("peer: kernels store pixels into rank 0's IPC-mapped row-major frame over NVLink + 4-byte all-reduce barrier"
+                       "frames_in_flight": in_flight,
+                       "calibration_ms_per_step": {f"{'one' if ov else 'two'}_launch_x{nf}_in_flight": v for (ov, nf), v in calib.items()},
+                       "l2": ("flushed between timed steps (256 MiB device write)" if in_flight == 1 else
+                              f"not flushed: two frames in flight, consecutive frames of a {round(packed.working_set_bytes() / 1e6)} MB working set "
+                              "(> 126 MB L2 for c3/c4/c5); the one-frame-at-a-time figures beside it are with and without the flush"),
+                       "parallelism": f"tile-sharded x{world}, BVH replicated",
+                       "exchange": ("peer: kernels store pixels into rank 0's IPC-mapped row-major frame over NVLink + a 4-byte all-reduce on the frame's own stream"
                                     if exchange == "peer" else "NCCL gather of RGBA8 shards to rank 0 + untile per shard") if world > 1
-                       else ("none (single GPU): row-major frame written by the traversal kernels" if exchange == "peer" else "untile only (single GPU)"),
+                       else "untile only (single GPU)",
                        "exchange_verified_bit_equal_to_nccl_path": exchange_verified},
-            "warm_l2": {"value": rays_all / (warm_ms * 1e-3) / 1e6, "ms_per_step": warm_ms, "steps": warm_steps,
-                        "note": "same steps back to back without the L2 flush (working set 174 MB > 126 MB L2; node array under the persisting-L2 window)"},
+            **side,
             "mrays_s": {"primary_kernel": cp["rays"] / kp_ms / 1e3, "bounce_kernel": (cb["rays"] / kb_ms / 1e3) if cb["rays"] else None,
-                        "note": "rank-0 shard, the two-launch path's kernels alone, CUDA events"},
-            "roofline": {"bound": "hbm", "kernel": "trace_kernel<FRAME> (primary + bounce rays in one launch; span includes raygen_primary)" if overlap else f"trace_kernel<{dominant}>", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "peak_source": peak_src, "traffic": ncu_traffic(dominant) if args.workload == "c3" else None,
-                         "l2_peak_gbs_measured_here": l2_peak, "frac_of_l2_peak": ach / l2_peak, "hbm_read_gbs_measured_here": hbm_read,
-                         "algorithmic_bytes_per_launch": dom_bytes,
-                         "bytes_per_ray": dom_bytes / {"frame": cp["rays"] + cb["rays"], "primary": cp["rays"], "bounce": max(1, cb["rays"])}[dominant],
-                         "ms_per_launch": dom_ms,
-                         "nodes_per_ray": cp["nodes"] / cp["rays"], "tris_per_ray": cp["tris"] / cp["rays"],
-                         "two_launch_path": {"primary_kernel_gbs": bytes_p / kp_ms / 1e6, "primary_kernel_frac": bytes_p / kp_ms / 1e6 / peak,
-                                             "bounce_kernel_gbs": bytes_b / kb_ms / 1e6, "bounce_kernel_frac": bytes_b / kb_ms / 1e6 / peak,
-                                             "note": "the same frame as two launches (the roofline object of earlier bench lines was the primary kernel of this path)"}},
+                        "note": "rank-0 shard, the two-launch path's kernels alone, CUDA events, L2 flushed"},
+            "roofline": roof,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": 160 * world, "d2h_bytes_per_step": w * h * 4,
+                    "l2": "not flushed (back-to-back frames; the flushed and unflushed one-frame-at-a-time device figures are beside `value`)",
                     "synchronous_note": "per rank: render, then tray_cuda_frame_download of a full-size frame (other shards zero), no exchange, no overlap",
                     "synchronous_value": e2e_sync_val,
-                    "note": "per step and rank: tray_cuda_render + RGBA8 frame to pinned host memory (readback_begin/_wait, double-buffered: "
-                            "the D2H of frame k overlaps the kernels of frame k+1; every frame is waited for inside the timed region), wall clock; "
-                            "synchronous_value = render then tray_cuda_frame_download, no overlap"},
-            # per step and rank: raygen_primary, trace (primary), raygen_bounce, trace (bounce); the NCCL path adds one
-            # untile per shard on rank 0
-            "gpu_launches": args.steps * world * ((2 if overlap else 4) + (0 if exchange == "peer" else 1)),
+                    "note": "per step and rank: tray_cuda_render + exchange + the complete RGBA8 frame to pinned host memory on rank 0, double-buffered "
+                            "(the D2H of frame k overlaps the kernels of frame k+1; every frame is waited for inside the timed region), wall clock"},
+            "gpu_launches": steps * world * per_frame,
             "clocks": clocks,
         }
+        if strong is not None:
+            line["strong"] = strong
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         if extras:
             line["next_rows"] = extras
         emit(line)
+    rig.close()
     scene.close()
-    if peer_ptr is not None and rank != 0:
-        cuda.ipc_close(peer_ptr, local_rank)
-        if peer_ptr2 is not None:
-            cuda.ipc_close(peer_ptr2, local_rank)
     if world > 1:
         dist.barrier()
-    if peer_frame is not None:
-        cuda.frame_free(peer_frame, local_rank)
-    if peer_frame2 is not None:
-        cuda.frame_free(peer_frame2, local_rank)
-    if world > 1:
         dist.destroy_process_group()
     return 0
 

@@ -300,7 +300,8 @@ int tray_cuda_frame_device_ptrs(tray_scene* scene, void** d_primary, void** d_bo
 
 /* Assemble a row-major width x height RGBA8 frame on the device from the compact buffer of ONE shard
  * (`d_compact` = that shard's rgba in local order, e.g. as received from another GPU by an NCCL gather).
- * Enqueued on the scene stream; pixels of other shards in `d_frame` are left untouched.              */
+ * Enqueued on the stream of the last rendered frame (the scene stream unless two frames are in flight); pixels of other
+ * shards in `d_frame` are left untouched.                                                                            */
 int tray_cuda_untile_rgba(tray_scene* scene, const void* d_compact, uint32_t width, uint32_t height,
                           uint32_t shard_index, uint32_t shard_count, void* d_frame);
 
@@ -339,6 +340,10 @@ int tray_cuda_scene_set_frames_in_flight(tray_scene* scene, uint32_t n);
 int tray_cuda_scene_fence(tray_scene* scene, void* stream);
 /* Frames enqueued from now on start after the work already enqueued on `stream`. */
 int tray_cuda_scene_after(tray_scene* scene, void* stream);
+/* The cudaStream_t (as void*) frames of slot `which` (0 / 1) run on, or — which = -1 — the stream of the last rendered frame:
+ * work enqueued on it right after tray_cuda_render (a collective that completes the frame, a copy) is ordered behind that
+ * frame and ahead of the next frame of the same slot, without holding back the frame in the other slot. */
+int tray_cuda_scene_frame_stream(tray_scene* scene, int which, void** stream);
 
 /* Run all subsequent work of this scene on `stream` (a cudaStream_t as void*; NULL restores the scene's own
  * stream) — lets a host that already owns a stream (torch, NCCL) order its collectives after the kernels. */

@@ -54,19 +54,25 @@ def main():
         p = host.PackedScene(m, use_tlas=tlas)
         view = host.view_from_camera(m.camera, w, h, p.tlas_start)
         sc = cuda.TrayCudaScene.from_packed(p)
-        sc.render(view, w, h, 0, cuda.RENDER_BOUNCE)
-        base = sc.download(primary=True, bounce=True)
-        n_p, n_b = w * h, int((base["primary"]["prim"] != INVALID).sum())
-        zero_dir = None
-        res[c] = {"scene": name, "n_tris": p.n_tris, "frame": [w, h], "tlas": tlas, "primary_rays": n_p, "bounce_rays": n_b, "switches": {}}
+        # the rays of the DEFAULT frame: its primary rays (a function of the pixel) and its bounce rays, kept, so that every
+        # switch is asked about the very same rays (a bounce ray regenerated from a moved primary hit is a different ray)
+        sc.render(view, w, h, 0, cuda.RENDER_BOUNCE | cuda.RENDER_KEEP_RAYS)
+        fr = sc.download(primary=True, bounce=True, bounce_rays=True)
+        hitpix = fr["primary"]["prim"] != INVALID
+        brays = np.ascontiguousarray(fr["bounce_rays"][hitpix])
+        base = {"primary": fr["primary"], "bounce": sc.traverse(brays)}
+        assert (base["bounce"]["prim"] == fr["bounce"]["prim"][hitpix]).all()
+        n_p, n_b = w * h, int(hitpix.sum())
+        res[c] = {"scene": name, "n_tris": p.n_tris, "frame": [w, h], "tlas": tlas, "primary_rays": n_p, "bounce_rays": n_b,
+                  "bounce_rays_with_a_zero_direction_component": int((brays["d"] == 0).any(axis=1).sum()), "switches": {}}
         for sw, v in SWITCHES.items():
             sc.set_variant(v)
-            sc.render(view, w, h, 0, cuda.RENDER_BOUNCE)
-            out = sc.download(primary=True, bounce=True)
+            sc.render(view, w, h, 0, 0)
+            out = {"primary": sc.download(primary=True)["primary"], "bounce": sc.traverse(brays)}
             res[c]["switches"][sw] = compare(base, out)
         sc.set_variant(0)
-        sc.render(view, w, h, 0, cuda.RENDER_BOUNCE)
-        again = sc.download(primary=True, bounce=True)
+        sc.render(view, w, h, 0, 0)
+        again = {"primary": sc.download(primary=True)["primary"], "bounce": sc.traverse(brays)}
         assert compare(base, again)["primary"]["changed"] == 0 and compare(base, again)["bounce"]["changed"] == 0
         sc.close()
         print(c, json.dumps(res[c]["switches"]), flush=True)

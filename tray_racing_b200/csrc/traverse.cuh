@@ -28,12 +28,18 @@
 
 namespace tray {
 
-constexpr int BLOCK_THREADS = 128;
+#ifndef TRAY_BLOCK_THREADS
+#define TRAY_BLOCK_THREADS 128
+#endif
+constexpr int BLOCK_THREADS = TRAY_BLOCK_THREADS;
 #ifndef TRAY_MIN_BLOCKS
-#define TRAY_MIN_BLOCKS 8
+#define TRAY_MIN_BLOCKS (1024 / TRAY_BLOCK_THREADS)
 #endif
 #ifndef TRAY_STACK_SMEM
 #define TRAY_STACK_SMEM 12
+#endif
+#ifndef TRAY_TRI2
+#define TRAY_TRI2 1          // two triangles of a lane's pending group per triangle step (bit-exact; -2.5 % frame time, profiles/experiments/r2_ab_*)
 #endif
 constexpr int STACK_SMEM = TRAY_STACK_SMEM;      // entries per thread in shared memory
 constexpr int STACK_SPILL = 48 - STACK_SMEM;     // further entries per thread in local memory (total 48 > obvhs' 32, cwbvh.rs:88)
@@ -610,6 +616,9 @@ __device__ __forceinline__ bool poll_hit(const tray_hit* src, float2& ph) {     
 // rule, slab-test lower clamp, reach of the zero-direction patch) and the HLSL's divide-form box test become RUN-TIME switches
 // (P.variant, TRAY_VARIANT_*), so that the day a real obvhs dump arrives the answer is a flag.  Slower (unfused node test);
 // MODE 0, the default, compiles them away.
+// (A MODE 2 — relaxed order: triangle postponing, tolerance parity — was built and measured in round 2 and is NOT in the
+// product: on CWBVHs of this shape 81 % of the nodes hold only leaves, so a lane almost never has triangles and child nodes in
+// hand at once; nothing was postponed, nothing mismatched, and the extra vote cost 3 %.  profiles/experiments/r2_relaxed_*.)
 template <bool TLAS, bool COUNT, int TRI_STRIDE, bool ANYHIT = false, bool FRAME = false, int MODE = 0>
 __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
@@ -879,10 +888,28 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                     SC({ const uint4 q0 = __ldg(P.tris + (size_t)g * (TRI_STRIDE / 16)), q2 = __ldg(P.tris + (size_t)g * (TRI_STRIDE / 16) + 2);
                          sc_acc[6] -= sc_a; sc_acc[6] += clk_after(q0.x ^ q2.x); })
                     SC(const long long sc_b = clk();)
+#if TRAY_TRI2
+                    // Two triangles of the lane's pending group per iteration (82 % of the groups hold >= 2): both records are
+                    // fetched together and the two tests run side by side.  The second test's only use of tmax is its final
+                    // `tt <= tmax` (query.hlsl:119), so running it against the OLD tmax and comparing with the updated best_t
+                    // afterwards accepts exactly what the sequential order accepts — bit-exact, ties included.
+                    const bool two = MODE != 1 && tri_y != 0u;
+                    const uint32_t local2 = two ? 31u - (uint32_t)__clz((int)tri_y) : local;
+                    const uint32_t g2 = tri_x + local2;
+                    if (two) tri_y &= ~(1u << local2);
+                    float t2 = __int_as_float(0x7f800000);
+                    if (two) t2 = tri_test<TRI_STRIDE, false>(r, best_t, P.tris, g2);
+#endif
                     const float t = tri_test<TRI_STRIDE, MODE == 1>(r, best_t, P.tris, g);
                     // CPU tie rule: first of equal t wins (§8a a11); TRAY_VARIANT_TIE_LAST: the HLSL's `tt <= t` (query.hlsl:120)
                     const bool closer = (MODE == 1 && (P.variant & TRAY_VARIANT_TIE_LAST)) ? (t <= best_t && t < __int_as_float(0x7f800000)) : (t < best_t);
                     if (closer) { best_t = t; best_prim = g; }
+#if TRAY_TRI2
+                    if (two && !(ANYHIT && best_prim != INVALID)) {      // (any-hit: the reference never runs the second test after a hit)
+                        TRAY_CNT(tris);
+                        if (t2 < best_t) { best_t = t2; best_prim = g2; }
+                    }
+#endif
                     if (ANYHIT && best_prim != INVALID) { sp = 0; tri_y = 0u; cur_y = 0u; }   // drop the rest of the traversal
                     if (tri_y == 0u && cur_y < 0x01000000u) pop_or_retire();
                     SC(sc_acc[7] += clk_after(cur_y ^ tri_y ^ __float_as_uint(best_t)) - sc_b; sc_n[1]++;)

@@ -597,7 +597,8 @@ int tray_cuda_untile_rgba(tray_scene* s, const void* d_compact, uint32_t w, uint
     CU(cudaSetDevice(s->device));
     FrameParams F; frame_params(F, nullptr, w, h, 0, shard, shards);
     if (F.n_items == 0) return TRAY_OK;
-    tray::untile_kernel<uchar4><<<(F.n_items + 255) / 256, 256, 0, s->stream>>>(F, (const uchar4*)d_compact, (uchar4*)d_frame);
+    // on the stream of the last rendered frame (its compact buffer is the usual source); with one frame in flight: the scene stream
+    tray::untile_kernel<uchar4><<<(F.n_items + 255) / 256, 256, 0, slot_stream(s, s->cur)>>>(F, (const uchar4*)d_compact, (uchar4*)d_frame);
     CU(cudaGetLastError());
     return TRAY_OK;
 }
@@ -829,6 +830,12 @@ int tray_cuda_scene_fence(tray_scene* s, void* stream) {
         CU(cudaEventRecord(s->slot[k].done, fs));
         CU(cudaStreamWaitEvent(st, s->slot[k].done, 0));
     }
+    return TRAY_OK;
+}
+
+int tray_cuda_scene_frame_stream(tray_scene* s, int which, void** stream) {
+    if (!s || !stream || which < -1 || which > 1) return fail(TRAY_ERR_ARG, "bad argument");
+    *stream = (void*)slot_stream(s, which < 0 ? s->cur : which);
     return TRAY_OK;
 }
 

@@ -27,7 +27,7 @@ EXPORTS = (
     "tray_cuda_scene_build", "tray_cuda_scene_download", "tray_cuda_frame_readback_begin", "tray_cuda_frame_readback_wait",
     "tray_cuda_scene_build_tlas", "tray_cuda_scene_download_instances",
     "tray_cuda_scene_set_variant", "tray_cuda_shard_items", "tray_cuda_scene_set_frames_in_flight", "tray_cuda_scene_fence",
-    "tray_cuda_scene_after", "tray_cuda_scene_set_geometry_offsets", "tray_cuda_hits_to_geometry",
+    "tray_cuda_scene_after", "tray_cuda_scene_frame_stream", "tray_cuda_scene_set_geometry_offsets", "tray_cuda_hits_to_geometry",
     "tray_cuda_group_create", "tray_cuda_group_destroy", "tray_cuda_group_size", "tray_cuda_group_scene",
     "tray_cuda_group_set_frames_in_flight", "tray_cuda_group_render", "tray_cuda_group_render_timed",
     "tray_cuda_group_readback_begin", "tray_cuda_group_readback_wait", "tray_cuda_group_frame_ptr", "tray_cuda_group_sync",
@@ -159,6 +159,8 @@ def lib() -> C.CDLL:
         L.tray_cuda_scene_fence.argtypes = [vp, vp]
         L.tray_cuda_scene_after.restype = i32
         L.tray_cuda_scene_after.argtypes = [vp, vp]
+        L.tray_cuda_scene_frame_stream.restype = i32
+        L.tray_cuda_scene_frame_stream.argtypes = [vp, i32, C.POINTER(vp)]
         L.tray_cuda_scene_set_geometry_offsets.restype = i32
         L.tray_cuda_scene_set_geometry_offsets.argtypes = [vp, vp, u32]
         L.tray_cuda_hits_to_geometry.restype = i32
@@ -354,6 +356,12 @@ class TrayCudaScene:
     def after(self, cuda_stream: int):
         """Frames enqueued from now on start after the work already enqueued on `cuda_stream`."""
         _check(lib().tray_cuda_scene_after(self._h, cuda_stream))
+
+    def frame_stream(self, which: int = -1) -> int:
+        """cudaStream_t of frame slot `which` (0 / 1), or of the last rendered frame (-1); 0 = the legacy default stream."""
+        p = C.c_void_p()
+        _check(lib().tray_cuda_scene_frame_stream(self._h, which, C.byref(p)))
+        return p.value or 0
 
     def set_geometry_offsets(self, tri_offsets):
         """First global triangle of every BLAS / object (n + 1 entries) — the runner's running `tri_offset`, rt_gpu/mod.rs:45-47."""
