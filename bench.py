@@ -220,8 +220,12 @@ class Rig:
     (every shard's pixels reach ONE row-major frame on rank 0) — for one or two frames in flight.
 
     exchange "peer": rank 0 owns row-major frames that every rank maps (CUDA IPC); the traversal kernels store finished
-        pixels straight into them over NVLink; a 4-byte all-reduce ON THE FRAME'S OWN STREAM completes the frame (one NCCL
-        communicator per frame slot, so the two frames in flight never wait for each other's collective).
+        pixels straight into them over NVLink.  Completion is a set of 32-bit flags moved by the stream front-end
+        (tray_cuda_frame_signal / _wait_flag = cuStreamWriteValue32 / cuStreamWaitValue32): rank k writes "frame seq is there"
+        into rank 0's memory behind its kernels, rank 0's frame stream waits for all of them, and rank 0 writes "target t is
+        consumed" back before a rank may overwrite that target four frames later.  No collective kernel: with two frames in
+        flight one would wait for an SM slot until the next frame's persistent grid drains.  (--exchange peer-nccl keeps the
+        round-1 barrier, a 4-byte all-reduce, for comparison.)
     exchange "nccl": gather of the compact RGBA8 shards to rank 0 + one untile launch per shard (one frame at a time).
     single GPU: compact buffer + one untile launch into the row-major frame."""
 
@@ -233,13 +237,14 @@ class Rig:
         self.max_items = cuda.local_items(w, h, 0, world)
         self.frames = [torch.zeros(h * w, dtype=torch.int32, device="cuda") for _ in range(2)] if (rank == 0 and (world == 1 or exchange == "nccl")) else None
         self.gathered = [torch.empty(self.max_items, dtype=torch.int32, device="cuda") for _ in range(world)] if (rank == 0 and world > 1 and exchange == "nccl") else None
-        self.peer_frames, self.peer_ptrs = [], []          # 4 targets: a frame's target is reused 4 frames later (see e2e)
+        self.peer_frames, self.peer_ptrs = [], []          # 4 targets: a frame's target is reused 4 frames later
         self.done = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(2)]
         self.groups = [None, None]
         self.ext = {}
-        self.k = 0
-        if world > 1 and exchange == "peer":
-            self.groups = [dist.new_group(list(range(world))), dist.new_group(list(range(world)))]
+        self.k = self.seq = 0
+        self.local_flags, self.remote_flags, self.target_seq = None, {}, [0, 0, 0, 0]
+        peer = world > 1 and exchange in ("peer", "peer-nccl")
+        if peer:
             for _ in range(4):
                 if rank == 0:
                     f = cuda.frame_alloc(w * h * 4, local_rank)
@@ -249,6 +254,19 @@ class Rig:
                     box = [None]
                 dist.broadcast_object_list(box, src=0)
                 self.peer_ptrs.append(self.peer_frames[-1] if rank == 0 else cuda.ipc_open(box[0], local_rank))
+        if peer and exchange == "peer-nccl":
+            self.groups = [dist.new_group(list(range(world))), dist.new_group(list(range(world)))]
+        elif peer:
+            # flag words: rank 0's buffer holds "arrived" [r * 2 + slot]; every rank's buffer holds "consumed" [32 + target]
+            self.local_flags = cuda.frame_alloc(256, local_rank)
+            handles = [None] * world
+            dist.all_gather_object(handles, cuda.ipc_export(self.local_flags, local_rank))
+            if rank == 0:
+                self.remote_flags = {r: cuda.ipc_open(handles[r], local_rank) for r in range(1, world)}
+            else:
+                self.remote_flags = {0: cuda.ipc_open(handles[0], local_rank)}
+            torch.cuda.synchronize()
+            dist.barrier()
 
     def torch_stream(self, ptr):
         if ptr == self.main.cuda_stream:
@@ -260,20 +278,40 @@ class Rig:
     def configure(self, overlap, in_flight):
         self.scene.sync()
         self.flags = self.cuda.RENDER_BOUNCE | self.cuda.RENDER_RGBA | (self.cuda.RENDER_OVERLAP if overlap else 0)
-        self.in_flight = in_flight if (self.world == 1 or self.exchange == "peer") else 1
+        self.in_flight = in_flight if (self.world == 1 or self.exchange in ("peer", "peer-nccl")) else 1
         self.scene.set_frames_in_flight(self.in_flight)
-        self.k = 0
+        self.k = 0                                         # (self.seq keeps counting: the flags only ever grow)
 
-    def step(self):
+    def step(self, copy_out=None):
+        """one frame; `copy_out(k)` (rank 0) is called where the COMPLETE frame k may be read on the frame's own stream"""
         sc, k = self.scene, self.k
         self.k += 1
-        if self.world > 1 and self.exchange == "peer":
-            sc.set_frame_target(self.peer_ptrs[k & 3])
+        if self.world > 1 and self.exchange in ("peer", "peer-nccl"):
+            t = k & 3
+            self.seq += 1
+            if self.local_flags is not None and self.rank != 0 and self.target_seq[t]:
+                # this target's previous frame must have been consumed on rank 0 before this rank's kernels overwrite it
+                sc.wait_flag(self.local_flags + 4 * (32 + t), self.target_seq[t], before_next_frame=True)
+            sc.set_frame_target(self.peer_ptrs[t])
             sc.render(self.view, self.w, self.h, 0, self.flags, self.rank, self.world, timed=False)
             slot = 0 if sc.frame_stream(-1) == sc.frame_stream(0) else 1
-            with self.torch.cuda.stream(self.torch_stream(sc.frame_stream(-1))):
-                self.dist.all_reduce(self.done[slot], group=self.groups[slot])   # behind the kernels: frame complete on rank 0
+            if self.local_flags is None:                  # peer-nccl: the round-1 barrier, on the frame's own stream / communicator
+                with self.torch.cuda.stream(self.torch_stream(sc.frame_stream(-1))):
+                    self.dist.all_reduce(self.done[slot], group=self.groups[slot])
+                if copy_out is not None and self.rank == 0:
+                    copy_out(k)
+            elif self.rank != 0:
+                sc.signal(self.remote_flags[0] + 4 * (self.rank * 2 + slot), self.seq)       # into rank 0's memory, behind my kernels
+            else:
+                for r in range(1, self.world):
+                    sc.wait_flag(self.local_flags + 4 * (r * 2 + slot), self.seq)             # every shard's pixels are there
+                if copy_out is not None:
+                    copy_out(k)
+                for r in range(1, self.world):
+                    sc.signal(self.remote_flags[r] + 4 * (32 + t), self.seq)                  # target t may be overwritten again
+            self.target_seq[t] = self.seq
         elif self.world > 1:
+            sc.set_frame_target(None)
             sc.render(self.view, self.w, self.h, 0, self.flags, self.rank, self.world, timed=False)
             _, _, d_rgba = sc.frame_device_ptrs()
             local = self.torch.as_tensor(self.cuda.DeviceArray(d_rgba, (self.max_items,), "<i4", sc), device="cuda")
@@ -281,15 +319,20 @@ class Rig:
             if self.rank == 0:
                 for s in range(self.world):
                     sc.untile_rgba(self.gathered[s].data_ptr(), self.w, self.h, s, self.world, self.frames[0].data_ptr())
+                if copy_out is not None:
+                    copy_out(k)
         else:
+            sc.set_frame_target(None)
             sc.render(self.view, self.w, self.h, 0, self.flags, 0, 1, timed=False)
             _, _, d_rgba = sc.frame_device_ptrs()
             sc.untile_rgba(d_rgba, self.w, self.h, 0, 1, self.frames[k & 1].data_ptr())      # on the frame's own stream
+            if copy_out is not None:
+                copy_out(k)
         return k
 
     def last_frame_tensor(self, k):
         """rank 0: the row-major frame step k produced, as an int32 tensor"""
-        if self.world > 1 and self.exchange == "peer":
+        if self.world > 1 and self.exchange in ("peer", "peer-nccl"):
             return self.torch.as_tensor(self.cuda.DeviceArray(self.peer_frames[k & 3], (self.h * self.w,), "<i4", self.scene), device="cuda")
         return self.frames[0 if self.world > 1 else (k & 1)]
 
@@ -327,13 +370,22 @@ class Rig:
         return e0.elapsed_time(e1)
 
     def close(self):
+        self.scene.sync()
+        self.torch.cuda.synchronize()
+        self.scene.set_frame_target(None)
+        self.ext.clear()
         if self.rank != 0:
             for p in self.peer_ptrs:
                 self.cuda.ipc_close(p, self.local_rank)
+        for p in self.remote_flags.values():
+            self.cuda.ipc_close(p, self.local_rank)
         if self.world > 1:
             self.dist.barrier()
         for f in self.peer_frames:
             self.cuda.frame_free(f, self.local_rank)
+        if self.local_flags is not None:
+            self.cuda.frame_free(self.local_flags, self.local_rank)
+        self.peer_frames, self.peer_ptrs, self.remote_flags, self.local_flags = [], [], {}, None
 
 
 def max_over_ranks(torch, dist, world, x):
@@ -341,6 +393,9 @@ def max_over_ranks(torch, dist, world, x):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+_keep_alive = []
 
 
 def strong_scaling_record(torch, dist, cuda, host, rank, world, local_rank, stream, steps):
@@ -398,9 +453,10 @@ def strong_scaling_record(torch, dist, cuda, host, rank, world, local_rank, stre
                 out["one_frame_at_a_time"] = rec
         out["unit"] = UNIT
         out["note"] = ("ms_per_step = CUDA-event time of the steps / steps, max over ranks, exchange included (kernels store pixels into "
-                       "rank 0's frame over NVLink, all-reduce completes the frame); no L2 flush (working set 300 MB > 126 MB L2)")
+                       "rank 0's frame over NVLink, completion flags); no L2 flush (working set 300 MB > 126 MB L2)")
         rig.close()
-        scene.close()
+        torch.cuda.synchronize()
+        _keep_alive.append(scene)        # closed by the caller after the process group is gone
         return out
     finally:
         WL = saved
@@ -445,7 +501,7 @@ def run_ours(args):
     try:
         rig = Rig(torch, dist, cuda, scene, view, w, h, rank, world, local_rank, stream, exchange)
     except cuda.TrayCudaError as e:
-        if args.exchange == "peer":
+        if args.exchange in ("peer", "peer-nccl"):
             raise
         print(f"[bench] rank {rank}: peer frame unavailable ({e}); falling back to the NCCL gather", file=sys.stderr)
         exchange = "nccl"
@@ -473,12 +529,14 @@ def run_ours(args):
 
     # ---- bit-equality of the exchange paths, once, outside the timed region: peer frame == NCCL gather + untile ----
     exchange_verified = None
-    if world > 1 and exchange == "peer":
+    if world > 1 and exchange in ("peer", "peer-nccl"):
         chk = Rig(torch, dist, cuda, scene, view, w, h, rank, world, local_rank, stream, "nccl")
         chk.configure(overlap, 1); chk.step(); chk.sync_all()
-        rig.configure(overlap, in_flight); k = rig.step(); rig.sync_all()
+        rig.configure(overlap, in_flight)
+        ks = [rig.step() for _ in range(3)]             # three frames, so that both frame slots and three targets are checked
+        rig.sync_all()
         if rank == 0:
-            exchange_verified = bool(torch.equal(rig.last_frame_tensor(k), chk.last_frame_tensor(0)))
+            exchange_verified = all(bool(torch.equal(rig.last_frame_tensor(k), chk.last_frame_tensor(0))) for k in ks)
         scene.set_frame_target(None)
 
     # ---- headline: `steps` timed steps in the calibrated mode ----
@@ -545,7 +603,22 @@ def run_ours(args):
     e2e_steps = max(3, min(steps, 50))
     owner = rank == 0
     host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)] if owner else None
+    stage = [torch.empty(h * w, dtype=torch.int32, device="cuda") for _ in range(2)] if (owner and world > 1) else None
+    copy_stream = torch.cuda.Stream() if (owner and world > 1) else None
     copy_ev = [None, None]
+
+    def copy_out(k):
+        """rank 0, N > 1: called by Rig.step where frame k is complete on the frame's own stream — snapshot it there (device to
+        device, so the target can be handed back at once), then D2H on a copy stream of its own"""
+        b = k & 1
+        st = rig.torch_stream(scene.frame_stream(-1))
+        with torch.cuda.stream(st):
+            stage[b].copy_(rig.last_frame_tensor(k))
+            snap = torch.cuda.Event(); snap.record(st)
+        copy_stream.wait_event(snap)
+        with torch.cuda.stream(copy_stream):
+            host_frames[b].view(-1).view(torch.int32).copy_(stage[b], non_blocking=True)
+            copy_ev[b] = torch.cuda.Event(); copy_ev[b].record(copy_stream)
 
     def e2e_step(i):
         b = i & 1
@@ -555,16 +628,11 @@ def run_ours(args):
             if i > 0:
                 scene.readback_wait(b ^ 1)
             return
-        k = rig.step()
-        if owner:
-            if copy_ev[b] is not None:
-                copy_ev[b].synchronize()                # host buffer b is free again (frame i-2 has landed)
-            st = rig.torch_stream(scene.frame_stream(-1)) if exchange == "peer" else stream
-            with torch.cuda.stream(st):
-                host_frames[b].view(-1).view(torch.int32).copy_(rig.last_frame_tensor(k), non_blocking=True)
-                copy_ev[b] = torch.cuda.Event(); copy_ev[b].record(st)
-            if i > 0 and copy_ev[b ^ 1] is not None:
-                copy_ev[b ^ 1].synchronize()
+        if owner and copy_ev[b] is not None:
+            copy_ev[b].synchronize()                    # frame i-2 has landed: host buffer b and staging b are free again
+        rig.step(copy_out if owner else None)
+        if owner and i > 0 and copy_ev[b ^ 1] is not None:
+            copy_ev[b ^ 1].synchronize()                # frame i-1 is in host memory before frame i+1 is issued
 
     def e2e_drain():
         if world == 1:
@@ -574,8 +642,10 @@ def run_ours(args):
                 if e is not None:
                     e.synchronize()
 
+    rig.k = 0
     e2e_step(0); e2e_step(1); e2e_drain()             # untimed: staging allocated, copy paths warm
     rig.sync_all()
+    rig.k = 0
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         e2e_step(i)
@@ -680,7 +750,7 @@ def run_ours(args):
             roof["frame_kernel"] = {"achieved": (bytes_p + bytes_b) / kf_ms / 1e6, "frac": (bytes_p + bytes_b) / kf_ms / 1e6 / l2_peak,
                                     "ms_per_launch": kf_ms, "algorithmic_bytes_per_launch": bytes_p + bytes_b,
                                     "note": "trace_kernel<FRAME>: both ray kinds in one launch; span includes raygen_primary"}
-        per_frame = (2 if overlap else 4) + (0 if exchange == "peer" else 1)
+        per_frame = (2 if overlap else 4) + (0 if exchange in ("peer", "peer-nccl") else 1)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": warmup,
             "ms_per_step": total_ms / steps, "higher_is_better": True, "scaling": WL["scaling"], "vs_baseline": None,
@@ -696,8 +766,10 @@ def run_ours(args):
                               f"not flushed: two frames in flight, consecutive frames of a {round(packed.working_set_bytes() / 1e6)} MB working set "
                               "(> 126 MB L2 for c3/c4/c5); the one-frame-at-a-time figures beside it are with and without the flush"),
                        "parallelism": f"tile-sharded x{world}, BVH replicated",
-                       "exchange": ("peer: kernels store pixels into rank 0's IPC-mapped row-major frame over NVLink + a 4-byte all-reduce on the frame's own stream"
-                                    if exchange == "peer" else "NCCL gather of RGBA8 shards to rank 0 + untile per shard") if world > 1
+                       "exchange": ("peer: kernels store pixels into rank 0's IPC-mapped row-major frame over NVLink; completion by 32-bit flags the stream "
+                                    "front-end writes / awaits (cuStreamWriteValue32 / cuStreamWaitValue32), no collective kernel" if exchange == "peer" else
+                                    "peer-nccl: same stores, a 4-byte all-reduce on the frame's own stream as barrier" if exchange == "peer-nccl" else
+                                    "NCCL gather of RGBA8 shards to rank 0 + untile per shard") if world > 1
                        else "untile only (single GPU)",
                        "exchange_verified_bit_equal_to_nccl_path": exchange_verified},
             **side,
@@ -721,10 +793,85 @@ def run_ours(args):
             line["next_rows"] = extras
         emit(line)
     rig.close()
-    scene.close()
+    torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        dist.destroy_process_group()                   # before the scenes go: NCCL may hold events of the scenes' streams
+    scene.close()
+    for sc in _keep_alive:
+        sc.close()
+    return 0
+
+
+def run_single_process(args):
+    """--single-process: the same frames from ONE process driving all N GPUs through the C ABI's tray_group (peer access + events;
+    no torchrun, no NCCL, no torch on the data path) — the shape of the reference's slot, one call from one host thread
+    (rt_gpu_software.rs:24-32).  The frame is checked byte for byte against the single-GPU frame of the same process."""
+    import torch
+    from tray_racing_b200 import cuda, host
+    n = args.gpus
+    if cuda.device_count() < n:
+        raise SystemExit(f"--single-process --gpus {n}: only {cuda.device_count()} CUDA device(s) visible")
+    mesh, packed = build_scene(nthreads=host_threads())
+    w, h = frame_size(n)
+    view = host.view_from_camera(mesh.camera, w, h, packed.tlas_start)
+    flags = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA
+    one = cuda.TrayCudaScene.from_packed(packed, device=0)
+    one.render(view, w, h, 0, flags | cuda.RENDER_COUNTERS)
+    cp, cb = one.counters()
+    rays = cp["rays"] + cb["rays"]
+    one.render(view, w, h, 0, flags)
+    want = one.download(rgba=True)["rgba"].copy()
+    one.close()
+    g = cuda.TrayCudaGroup.from_packed(packed, devices=list(range(n)))
+    steps, warmup = args.steps, max(args.warmup, 3)
+    res = {}
+    for nf in (1, 2):
+        g.set_frames_in_flight(nf)
+        for _ in range(warmup):
+            g.render(view, w, h, 0, flags)
+        same = bool((g.frame() == want).all())
+        g.sync()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            g.render(view, w, h, 0, flags)
+        g.sync()
+        ms = (time.perf_counter() - t0) * 1e3 / steps
+        res[nf] = {"ms_per_step": ms, "value": rays / ms / 1e3, "frame_equals_single_gpu_frame": same}
+    nf = 2 if res[2]["ms_per_step"] < res[1]["ms_per_step"] else 1
+    g.set_frames_in_flight(nf)
+    per_frame_ms = [g.render(view, w, h, 0, flags, timed=True) for _ in range(12)][2:]
+    host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
+    e2e_steps = max(3, min(steps, 50))
+
+    def e2e(i):
+        g.render(view, w, h, 0, flags)
+        g.readback_begin(host_frames[i & 1], i & 1)
+        if i > 0:
+            g.readback_wait((i - 1) & 1)
+    e2e(0); e2e(1); g.readback_wait(0); g.readback_wait(1); g.sync()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e(i)
+    g.readback_wait((e2e_steps - 1) & 1)
+    g.sync()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    e2e_same = bool((host_frames[(e2e_steps - 1) & 1] == want).all())
+    g.close()
+    line = {"metric": METRIC, "value": res[nf]["value"], "unit": UNIT, "n_gpus": n, "steps": steps, "warmup": warmup,
+            "ms_per_step": res[nf]["ms_per_step"], "higher_is_better": True, "scaling": WL["scaling"], "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl_note": "--single-process: one process, tray_cuda_group_* (C ABI), no torchrun / NCCL",
+            "config": {"workload": workload_name(w, h, n), "n_tris": packed.n_tris, "n_nodes": packed.n_nodes, "frames_in_flight": nf,
+                       "frame_path": "two launches per frame", "parallelism": f"one process, {n} device(s), tiles dealt round-robin, BVH replicated",
+                       "exchange": "kernels store pixels into devices[0]'s frame over peer access; completion by events",
+                       "timing": "host clock around the asynchronous frames, tray_cuda_group_sync on both sides (CUDA events do not span devices); "
+                                 "per_frame_ms_cuda_events = tray_cuda_group_render_timed, one frame at a time"},
+            "by_frames_in_flight": res, "per_frame_ms_cuda_events": {"min": min(per_frame_ms), "mean": sum(per_frame_ms) / len(per_frame_ms)},
+            "e2e": {"value": rays / e2e_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": 160 * n, "d2h_bytes_per_step": w * h * 4,
+                    "frame_in_host_memory_equals_single_gpu_frame": e2e_same,
+                    "note": "tray_cuda_group_render + tray_cuda_group_readback_begin / _wait into pinned host memory, double-buffered, wall clock"},
+            "gpu_launches": steps * n * 4}
+    emit(line)
     return 0
 
 
@@ -736,7 +883,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS),
                     help="c3 (default, the metric's config; weak scaling) | c1 | c2 (1080p) | c4 | c5 (fixed 3840x2160 frame sharded over the GPUs)")
-    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+    ap.add_argument("--single-process", action="store_true",
+                    help="one process drives all --gpus N devices through tray_cuda_group_* (no torchrun)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "peer-nccl", "nccl"],
                     help="how shards reach rank 0's frame: peer-mapped frame written by the kernels, or NCCL gather + untile")
     args = ap.parse_args()
     global WL
@@ -744,6 +893,8 @@ def main():
     claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
+    if args.single_process:
+        return run_single_process(args)
     return run_ours(args)
 
 

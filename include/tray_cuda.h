@@ -321,6 +321,19 @@ int tray_cuda_frame_free(int device, void* d_ptr);
 int tray_cuda_ipc_export(int device, void* d_ptr, uint8_t handle[64]);        /* cudaIpcGetMemHandle                */
 int tray_cuda_ipc_open(int device, const uint8_t handle[64], void** d_ptr);   /* cudaIpcOpenMemHandle + peer access */
 int tray_cuda_ipc_close(int device, void* d_ptr);
+/* Completion flags for that exchange, WITHOUT a kernel: a 32-bit word in device memory (tray_cuda_frame_alloc; it may be a peer
+ * mapping) written / awaited by the stream front-end (cuStreamWriteValue32 / cuStreamWaitValue32), on the stream of the last
+ * rendered frame.  A collective kernel cannot do this job once two frames are in flight: it would wait for an SM slot that the
+ * next frame's persistent grid only frees when it drains.
+ *   rank k > 0, after tray_cuda_render:  tray_cuda_frame_signal(scene, &flags_on_rank0[k], seq)     — "my pixels of frame seq are there"
+ *   rank 0, after tray_cuda_render:      tray_cuda_frame_wait_flag(scene, &flags[k], seq) for every k — whatever follows on that
+ *                                        stream (a copy to the host) sees the complete frame
+ * wait_flag passes once (int32)(*flag - value) >= 0, so sequence numbers may wrap.  Waits should be on LOCAL memory.
+ * before_next_frame != 0 puts the wait on the stream the NEXT tray_cuda_render will use instead: that frame starts only once
+ * the flag has been reached (e.g. "rank 0 has copied the previous frame out of the target this frame is about to overwrite"). */
+int tray_cuda_frame_signal(tray_scene* scene, void* d_flag, uint32_t value);
+int tray_cuda_frame_wait_flag(tray_scene* scene, const void* d_flag, uint32_t value, int before_next_frame);
+
 /* RGBA8 of every later tray_cuda_render goes to `d_frame` (row-major, width*height*4 bytes, on this or a peer
  * device) instead of the scene's compact buffer; NULL restores the compact buffer.  The pointer is borrowed.        */
 int tray_cuda_scene_set_frame_target(tray_scene* scene, void* d_frame);

@@ -183,3 +183,37 @@ def test_start_multi_runs_the_reference_protocol(cornell):
         cuda.start_multi(devs, p.bvh_bytes[:-1], p.instance_bytes, p.tri_bytes, p.tlas_start, view, w, h, render_time=0.05)
     with pytest.raises(cuda.TrayCudaError, match="out of range"):
         cuda.start_multi(list(range(cuda.device_count() + 1)), p.bvh_bytes, p.instance_bytes, p.tri_bytes, p.tlas_start, view, w, h, render_time=0.05)
+
+
+def test_completion_flags_are_stream_memory_operations(cornell):
+    """tray_cuda_frame_signal / _wait_flag: a 32-bit flag written and awaited by the stream front-end (no kernel, no SM slot) —
+    the completion primitive of the multi-process peer exchange.  Here on one device: order, values, wrap-around compare."""
+    import torch
+    p = host.PackedScene(cornell)
+    w, h = 320, 184
+    view = host.view_from_camera(cornell.camera, w, h)
+    sc = cuda.TrayCudaScene.from_packed(p)
+    flag = cuda.frame_alloc(64)
+    try:
+        words = torch.as_tensor(cuda.DeviceArray(flag, (16,), "<u4", sc), device="cuda")
+        sc.render(view, w, h, 0, FLAGS, timed=False)
+        sc.signal(flag, 7)                          # behind the frame's kernels
+        sc.wait_flag(flag, 7)                       # passes: the write is ahead of it on the same stream
+        sc.wait_flag(flag, 5)                       # GEQ
+        sc.signal(flag + 4, 0xFFFFFFF0)
+        sc.wait_flag(flag + 4, 0xFFFFFFE0)          # (int32)(flag - value) >= 0 across the wrap
+        sc.sync()
+        assert int(words[0].item()) == 7 and int(words[1].item()) == 0xFFFFFFF0
+        # the next frame (other slot, other stream) only starts once the last frame has signalled
+        sc.set_frames_in_flight(2)
+        for k in range(8, 14):
+            sc.render(view, w, h, k, FLAGS, timed=False)
+            sc.signal(flag + 8, k)
+            sc.wait_flag(flag + 8, k, before_next_frame=True)
+        sc.sync()
+        assert int(words[2].item()) == 13
+        out = sc.download(primary=True)
+        assert (out["primary"]["prim"] == ob.Oracle.from_packed(p).render(view, w, h, 13)["primary"]["prim"]).all()
+    finally:
+        sc.close()
+        cuda.frame_free(flag)

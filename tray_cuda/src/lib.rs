@@ -111,6 +111,8 @@ extern "C" {
     pub fn tray_cuda_scene_set_frames_in_flight(scene: *mut TrayScene, n: u32) -> c_int;
     pub fn tray_cuda_scene_fence(scene: *mut TrayScene, stream: *mut c_void) -> c_int;
     pub fn tray_cuda_scene_after(scene: *mut TrayScene, stream: *mut c_void) -> c_int;
+    pub fn tray_cuda_frame_signal(scene: *mut TrayScene, d_flag: *mut c_void, value: u32) -> c_int;
+    pub fn tray_cuda_frame_wait_flag(scene: *mut TrayScene, d_flag: *const c_void, value: u32, before_next_frame: c_int) -> c_int;
     pub fn tray_cuda_scene_frame_stream(scene: *mut TrayScene, which: c_int, stream: *mut *mut c_void) -> c_int;
     pub fn tray_cuda_scene_set_geometry_offsets(scene: *mut TrayScene, tri_offsets: *const u32, n_geometries: u32) -> c_int;
     pub fn tray_cuda_hits_to_geometry(scene: *mut TrayScene, hits: *const TrayHit, n: u64, geometry_id: *mut u32,

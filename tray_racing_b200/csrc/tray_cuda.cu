@@ -839,6 +839,45 @@ int tray_cuda_scene_frame_stream(tray_scene* s, int which, void** stream) {
     return TRAY_OK;
 }
 
+// ---- frame completion across GPUs without a kernel: stream memory operations ---------------------------------------------
+// cuStreamWriteValue32 / cuStreamWaitValue32 are executed by the stream front-end, so they need no SM slot — unlike a collective
+// kernel, which cannot start while the persistent grid of the NEXT frame fills every slot of the chip.  They are driver-API
+// entry points: resolved at run time (cudaGetDriverEntryPoint), the library does not link libcuda.
+namespace {
+typedef int (*stream_memop32_fn)(void* stream, unsigned long long addr, unsigned int value, unsigned int flags);
+stream_memop32_fn g_write32 = nullptr, g_wait32 = nullptr;
+int resolve_memops() {
+    if (g_write32 && g_wait32) return TRAY_OK;
+    void* w = nullptr; void* q = nullptr;
+    cudaDriverEntryPointQueryResult st;
+    CU(cudaGetDriverEntryPoint("cuStreamWriteValue32", &w, cudaEnableDefault, &st));
+    if (st != cudaDriverEntryPointSuccess || !w) return fail(TRAY_ERR_CUDA, "cuStreamWriteValue32 is not available in this driver");
+    CU(cudaGetDriverEntryPoint("cuStreamWaitValue32", &q, cudaEnableDefault, &st));
+    if (st != cudaDriverEntryPointSuccess || !q) return fail(TRAY_ERR_CUDA, "cuStreamWaitValue32 is not available in this driver");
+    g_write32 = (stream_memop32_fn)w; g_wait32 = (stream_memop32_fn)q;
+    return TRAY_OK;
+}
+}  // namespace
+
+int tray_cuda_frame_signal(tray_scene* s, void* d_flag, uint32_t value) {
+    if (!s || !d_flag) return fail(TRAY_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = resolve_memops(); if (rc) return rc;
+    const int e = g_write32((void*)slot_stream(s, s->cur), (unsigned long long)(uintptr_t)d_flag, value, 0u /* CU_STREAM_WRITE_VALUE_DEFAULT */);
+    if (e) return fail(TRAY_ERR_CUDA, "cuStreamWriteValue32 failed (CUresult %d)", e);
+    return TRAY_OK;
+}
+
+int tray_cuda_frame_wait_flag(tray_scene* s, const void* d_flag, uint32_t value, int before_next_frame) {
+    if (!s || !d_flag) return fail(TRAY_ERR_ARG, "NULL argument");
+    CU(cudaSetDevice(s->device));
+    int rc = resolve_memops(); if (rc) return rc;
+    const int k = before_next_frame ? (s->n_slots > 1 ? (s->cur + 1) % s->n_slots : 0) : s->cur;
+    const int e = g_wait32((void*)slot_stream(s, k), (unsigned long long)(uintptr_t)d_flag, value, 0u /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (e) return fail(TRAY_ERR_CUDA, "cuStreamWaitValue32 failed (CUresult %d)", e);
+    return TRAY_OK;
+}
+
 int tray_cuda_scene_after(tray_scene* s, void* stream) {
     if (!s || !stream) return fail(TRAY_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(s->device));

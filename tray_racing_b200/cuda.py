@@ -27,7 +27,7 @@ EXPORTS = (
     "tray_cuda_scene_build", "tray_cuda_scene_download", "tray_cuda_frame_readback_begin", "tray_cuda_frame_readback_wait",
     "tray_cuda_scene_build_tlas", "tray_cuda_scene_download_instances",
     "tray_cuda_scene_set_variant", "tray_cuda_shard_items", "tray_cuda_scene_set_frames_in_flight", "tray_cuda_scene_fence",
-    "tray_cuda_scene_after", "tray_cuda_scene_frame_stream", "tray_cuda_scene_set_geometry_offsets", "tray_cuda_hits_to_geometry",
+    "tray_cuda_scene_after", "tray_cuda_scene_frame_stream", "tray_cuda_frame_signal", "tray_cuda_frame_wait_flag", "tray_cuda_scene_set_geometry_offsets", "tray_cuda_hits_to_geometry",
     "tray_cuda_group_create", "tray_cuda_group_destroy", "tray_cuda_group_size", "tray_cuda_group_scene",
     "tray_cuda_group_set_frames_in_flight", "tray_cuda_group_render", "tray_cuda_group_render_timed",
     "tray_cuda_group_readback_begin", "tray_cuda_group_readback_wait", "tray_cuda_group_frame_ptr", "tray_cuda_group_sync",
@@ -159,6 +159,10 @@ def lib() -> C.CDLL:
         L.tray_cuda_scene_fence.argtypes = [vp, vp]
         L.tray_cuda_scene_after.restype = i32
         L.tray_cuda_scene_after.argtypes = [vp, vp]
+        L.tray_cuda_frame_signal.restype = i32
+        L.tray_cuda_frame_signal.argtypes = [vp, vp, u32]
+        L.tray_cuda_frame_wait_flag.restype = i32
+        L.tray_cuda_frame_wait_flag.argtypes = [vp, vp, u32, i32]
         L.tray_cuda_scene_frame_stream.restype = i32
         L.tray_cuda_scene_frame_stream.argtypes = [vp, i32, C.POINTER(vp)]
         L.tray_cuda_scene_set_geometry_offsets.restype = i32
@@ -356,6 +360,14 @@ class TrayCudaScene:
     def after(self, cuda_stream: int):
         """Frames enqueued from now on start after the work already enqueued on `cuda_stream`."""
         _check(lib().tray_cuda_scene_after(self._h, cuda_stream))
+
+    def signal(self, d_flag: int, value: int):
+        """Behind the last frame: write `value` to the 32-bit flag at device address `d_flag` (possibly peer memory) — no kernel."""
+        _check(lib().tray_cuda_frame_signal(self._h, C.c_void_p(d_flag), value & 0xFFFFFFFF))
+
+    def wait_flag(self, d_flag: int, value: int, before_next_frame: bool = False):
+        """The stream of the last frame (or of the next one) waits until the flag at `d_flag` has reached `value` — no kernel."""
+        _check(lib().tray_cuda_frame_wait_flag(self._h, C.c_void_p(d_flag), value & 0xFFFFFFFF, int(before_next_frame)))
 
     def frame_stream(self, which: int = -1) -> int:
         """cudaStream_t of frame slot `which` (0 / 1), or of the last rendered frame (-1); 0 = the legacy default stream."""
