@@ -594,23 +594,25 @@ def run_ours(args):
 
     # ---- end to end through the public API with HOST buffers ----
     # Every step: tray_cuda_render on every rank (view + frame parameters go in by value, 160 B per rank), the exchange step,
-    # and the readback of that frame's RGBA8 into pinned host memory on rank 0, double-buffered: the D2H of frame k overlaps the
-    # kernels of frame k+1; frame k is in host memory before frame k+2 is issued, the last frames are waited for inside the
-    # timed region.  N = 1: tray_cuda_frame_readback_begin / _wait.  N > 1 (peer exchange): rank 0 copies the complete frame
-    # out of its target on the frame's own stream, behind the all-reduce that completes it; a target is reused four frames later,
-    # i.e. behind the next-but-one collective of its slot, which rank 0 only joins once the copy has been enqueued ahead of it.
+    # and the readback of that frame's RGBA8 into pinned host memory on rank 0 through a small ring of buffers: the D2H of frame k
+    # overlaps the kernels of the next frames; frame k is in host memory before frame k + RING is issued (RING = 2 at N = 1, 3
+    # above), the last frames are waited for inside the timed region.  N = 1: tray_cuda_frame_readback_begin / _wait.  N > 1
+    # (peer exchange): rank 0 snapshots the complete frame out of its target on the frame's own stream, behind the flag waits that
+    # complete it, hands the target back (consumed flags) and copies the snapshot to the host on a copy stream.
     rig.configure(overlap, in_flight)
     e2e_steps = max(3, min(steps, 50))
     owner = rank == 0
-    host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True) for _ in range(2)] if owner else None
-    stage = [torch.empty(h * w, dtype=torch.int32, device="cuda") for _ in range(2)] if (owner and world > 1) else None
+    RING = 2 if world == 1 else 3                    # host / staging buffers: frame i is in host memory before frame i + RING is issued
+    host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True) for _ in range(RING)] if owner else None
+    stage = [torch.empty(h * w, dtype=torch.int32, device="cuda") for _ in range(RING)] if (owner and world > 1) else None
     copy_stream = torch.cuda.Stream() if (owner and world > 1) else None
-    copy_ev = [None, None]
+    copy_ev = [None] * RING
+    ring_of = {}
 
     def copy_out(k):
         """rank 0, N > 1: called by Rig.step where frame k is complete on the frame's own stream — snapshot it there (device to
         device, so the target can be handed back at once), then D2H on a copy stream of its own"""
-        b = k & 1
+        b = ring_of[k]
         st = rig.torch_stream(scene.frame_stream(-1))
         with torch.cuda.stream(st):
             stage[b].copy_(rig.last_frame_tensor(k))
@@ -621,7 +623,7 @@ def run_ours(args):
             copy_ev[b] = torch.cuda.Event(); copy_ev[b].record(copy_stream)
 
     def e2e_step(i):
-        b = i & 1
+        b = i % RING
         if world == 1:
             scene.render(view, w, h, 0, rig.flags, 0, 1, timed=False)
             scene.readback_begin(host_frames[b].numpy(), b)       # untile on the frame's stream, D2H on the copy stream
@@ -629,10 +631,9 @@ def run_ours(args):
                 scene.readback_wait(b ^ 1)
             return
         if owner and copy_ev[b] is not None:
-            copy_ev[b].synchronize()                    # frame i-2 has landed: host buffer b and staging b are free again
+            copy_ev[b].synchronize()                    # frame i - RING has landed: host buffer b and staging b are free again
+        ring_of[rig.k] = b
         rig.step(copy_out if owner else None)
-        if owner and i > 0 and copy_ev[b ^ 1] is not None:
-            copy_ev[b ^ 1].synchronize()                # frame i-1 is in host memory before frame i+1 is issued
 
     def e2e_drain():
         if world == 1:

@@ -187,7 +187,8 @@ void tray_cuda_scene_destroy(tray_scene* scene);
 /* ---- device-side builder ----------------------------------------------------------------
  * The step before the path: the reference builds its CwBvh on the CPU (`cwbvh_from_tris`, src/cwbvh.rs:24-105,
  * 0.95-2.9 s for its large scenes) and uploads it.  This builds the same FORMAT on the GPU — Morton sort, PLOC
- * clustering (search radius = obvhs' `search_distance`, default 14, src/main.rs:563-587), collapse to 8-wide,
+ * clustering (search radius = obvhs' `search_distance`, default 14, src/main.rs:563-587), parallel reinsertion passes over the
+ * binary tree (obvhs' reinsertion step), collapse to 8-wide,
  * octant slot order and quantisation as embree/src/bvh_embree_to_cwbvh.rs:85-186 — straight into the scene's device
  * buffers; only the triangle soup crosses PCIe.  (Two-level scenes: tray_cuda_scene_build_tlas.)  Deterministic: the same
  * triangles give the same bytes on every device, so per-rank replicas agree on every primitive id.
@@ -198,6 +199,12 @@ typedef struct tray_build_stats {
     uint64_t n_tris, n_nodes;
     uint32_t ploc_iterations, levels;
     float    ms_upload, ms_sort, ms_ploc, ms_collapse, ms_total;   /* host wall clock around synchronised phases */
+    /* reinsertion passes between PLOC and the collapse (obvhs: reinsertion_batch_ratio, src/main.rs:563-587; environment
+     * TRAY_CUDA_BUILD_REINSERT = number of passes, default 2, 0 = off): time, subtrees moved, SAH cost (sum of the inner nodes'
+     * half areas) of the BVH2 before and after */
+    float    ms_reinsert;
+    uint32_t reinsert_passes, reinsert_moves;
+    float    sah_before, sah_after;
 } tray_build_stats;
 
 int tray_cuda_scene_build(const float* tris9, uint64_t n_tris, uint32_t tri_stride, uint32_t max_prims_per_leaf,

@@ -33,6 +33,7 @@ pub struct TrayTri48 { pub v0: [f32; 3], pub p0: f32, pub e1: [f32; 3], pub p1: 
 pub struct TrayBuildStats {
     pub n_tris: u64, pub n_nodes: u64, pub ploc_iterations: u32, pub levels: u32,
     pub ms_upload: f32, pub ms_sort: f32, pub ms_ploc: f32, pub ms_collapse: f32, pub ms_total: f32,
+    pub ms_reinsert: f32, pub reinsert_passes: u32, pub reinsert_moves: u32, pub sah_before: f32, pub sah_after: f32,
 }
 
 /// `tray_counters` of include/tray_cuda.h (the algorithmic bytes per ray come from these)

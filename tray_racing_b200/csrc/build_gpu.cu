@@ -276,6 +276,179 @@ __global__ void __launch_bounds__(PLOC_TAIL) ploc_tail_kernel(int* __restrict__ 
     if (i == 0) { out->m = m; out->next_node = next_node; out->iters = iters; out->stalled = stalled; }
 }
 
+// ---- 3b. reinsertion: BVH2 optimisation between PLOC and the collapse --------------------------------------------------
+// obvhs runs a reinsertion pass over its PLOC tree before it collapses it (`reinsertion_batch_ratio`, `post_collapse_reinsertion`,
+// reference src/main.rs:563-587); PLOC alone is greedy and pairs e.g. crossing ribbons of the hairball-like scene, which costs
+// ~17 % more node visits per ray than the host's binned-SAH tree.  This is the published parallel formulation (Meister & Bittner,
+// "Parallel Reinsertion for Bounding Volume Hierarchy Optimization", 2018) laid out on this builder's arrays:
+//   find   every node v looks for the position x that lowers the tree's SAH cost (sum of inner-node areas) most if the subtree of
+//          v is cut out and re-inserted as the sibling of x: it climbs from its parent to the root and searches the subtree on the
+//          other side of every ancestor with branch and bound (the induced growth of the boxes on the way down is the bound)
+//   lock   the moves are ordered by (gain, node): each claims every node on the path v .. common ancestor .. x with atomicMax
+//   apply  a move that still owns its whole path rewires six pointers; disjoint paths cannot interfere (nor form a cycle)
+//   refit  boxes and primitive counts bottom-up
+// All of it is deterministic (the lock key is a total order), so replicas built on different GPUs still agree byte for byte.
+struct OptArrays { int* parent; float* gain; int* target; unsigned long long* lock; uint32_t* visits; };
+
+__global__ void opt_parent_kernel(Bvh2 b, uint32_t first_inner, uint32_t n_nodes, int* __restrict__ parent) {
+    const uint32_t i = first_inner + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    parent[node_left(b.lo[i])] = (int)i; parent[node_right(b.hi[i])] = (int)i;
+}
+
+__device__ __forceinline__ float union_area(const float4& alo, const float4& ahi, const float4& blo, const float4& bhi) {
+    const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+__device__ __forceinline__ int sibling_of(const Bvh2& b, const int* parent, int x) {
+    const int p = parent[x];
+    const int l = node_left(b.lo[p]);
+    return l == x ? node_right(b.hi[p]) : l;
+}
+
+__global__ void __launch_bounds__(128) opt_find_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o, uint32_t max_visits) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    o.gain[v] = 0.f; o.target[v] = -1;
+    const int p = o.parent[v];
+    if (p < 0 || o.parent[p] < 0) return;                   // the root and its children stay where they are
+    const float4 Llo = b.lo[v], Lhi = b.hi[v];
+    const float aL = half_area(Llo, Lhi);
+    float best = 0.f; int best_x = -1;
+    float d = half_area(b.lo[p], b.hi[p]);                  // removing v deletes its parent
+    const int s = sibling_of(b, o.parent, (int)v);
+    float4 pblo = b.lo[s], pbhi = b.hi[s];                  // box of the path node once v is gone
+    int pivot = p, region = s;
+    bool skip_root_of_region = true;                        // re-inserting next to the own sibling is the identity
+    uint32_t visits = 0;
+    int stack_n[48]; float stack_c[48];
+    for (;;) {
+        // ---- branch and bound over the subtree `region`: cost of inserting at x = area(x U v) + induced growth on the way down
+        int sp = 0; stack_n[sp] = region; stack_c[sp] = 0.f; sp++;
+        while (sp && visits < max_visits) {
+            sp--; const int x = stack_n[sp]; const float cind = stack_c[sp];
+            visits++;
+            const float4 xlo = b.lo[x], xhi = b.hi[x];
+            const float m = union_area(xlo, xhi, Llo, Lhi);
+            if (!(skip_root_of_region && x == region)) {
+                const float g = d - (cind + m);
+                if (g > best) { best = g; best_x = x; }
+            }
+            const int xl = node_left(xlo);
+            if (xl >= 0) {
+                const float cchild = cind + m - half_area(xlo, xhi);
+                if (d - (cchild + aL) > best && sp + 2 <= 48) {          // a descendant could still beat the best
+                    stack_n[sp] = node_right(xhi); stack_c[sp] = cchild; sp++;
+                    stack_n[sp] = xl; stack_c[sp] = cchild; sp++;
+                }
+            }
+        }
+        skip_root_of_region = false;
+        // ---- climb: the pivot becomes a node between the new common ancestor and v's old place
+        const int up = o.parent[pivot];
+        if (up < 0 || visits >= max_visits) break;
+        if (pivot != p) d += half_area(b.lo[pivot], b.hi[pivot]) - half_area(pblo, pbhi);
+        region = sibling_of(b, o.parent, pivot);
+        const float4 rlo = b.lo[region], rhi = b.hi[region];
+        // (the search of `region` uses the d of the new pivot `up`: nodes strictly between up and p have shrunk)
+        pivot = up;
+        // run the region search first (next loop iteration), then the path node itself; to keep one loop, handle the path node here
+        // with the box it will have: pb' = pb U region
+        float4 nlo = make_float4(fminf(pblo.x, rlo.x), fminf(pblo.y, rlo.y), fminf(pblo.z, rlo.z), 0.f);
+        float4 nhi = make_float4(fmaxf(pbhi.x, rhi.x), fmaxf(pbhi.y, rhi.y), fmaxf(pbhi.z, rhi.z), 0.f);
+        if (o.parent[pivot] >= 0) {                         // insert above the path node `pivot` (never above the root)
+            const float g = d - half_area(nlo, nhi);
+            if (g > best) { best = g; best_x = pivot; }
+        }
+        pblo = nlo; pbhi = nhi;
+    }
+    if (o.visits) o.visits[v] = visits;
+    if (best_x >= 0 && best > aL * 1e-6f) { o.gain[v] = best; o.target[v] = best_x; }
+}
+
+// every node on the path v -> common ancestor -> x (both ends and the parents that get rewired included)
+template <typename F>
+__device__ void opt_walk_path(const Bvh2& b, const int* parent, int v, int x, F f) {
+    // depth is not stored: climb both sides alternately until they meet, marking as we go would need memory; instead climb
+    // v's side to the root collecting nothing, which is O(depth) twice — paths are short (tens of nodes)
+    int depth_v = 0, depth_x = 0;
+    for (int a = v; a >= 0 && depth_v < (1 << 20); a = parent[a]) depth_v++;
+    for (int a = x; a >= 0 && depth_x < (1 << 20); a = parent[a]) depth_x++;
+    int a = v, c = x;
+    while (depth_v > depth_x) { f(a); a = parent[a]; depth_v--; }
+    while (depth_x > depth_v) { f(c); c = parent[c]; depth_x--; }
+    while (a != c && a >= 0 && c >= 0) { f(a); f(c); a = parent[a]; c = parent[c]; }
+    if (a < 0 || c < 0) return;                             // different trees of a forest: cannot happen (the search stops at the root)
+    f(a);                                                   // the common ancestor
+    if (parent[a] >= 0) f(parent[a]);                       // x may be a path node itself: its parent is rewired
+}
+
+__global__ void opt_lock_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes || o.target[v] < 0) return;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(o.gain[v]) << 32) | v;
+    opt_walk_path(b, o.parent, (int)v, o.target[v], [&](int x) { atomicMax(o.lock + x, key); });
+    atomicMax(o.lock + sibling_of(b, o.parent, (int)v), key);
+}
+
+// a move that still owns every node of its path wins; the others are dropped for this pass.  (A kernel of its own: the walk
+// reads parent pointers, which the apply kernel rewrites.)
+__global__ void opt_check_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes || o.target[v] < 0) return;
+    const unsigned long long key = ((unsigned long long)__float_as_uint(o.gain[v]) << 32) | v;
+    bool mine = true;
+    opt_walk_path(b, o.parent, (int)v, o.target[v], [&](int y) { if (o.lock[y] != key) mine = false; });
+    if (o.lock[sibling_of(b, o.parent, (int)v)] != key) mine = false;
+    if (!mine) o.target[v] = -1;
+}
+
+// winners own disjoint sets of nodes, so they rewire concurrently
+__global__ void opt_apply_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o, uint32_t* __restrict__ n_applied) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes || o.target[v] < 0) return;
+    const int x = o.target[v];
+    const int s = sibling_of(b, o.parent, (int)v);
+    const int p = o.parent[v], g = o.parent[p];
+    // cut: s takes p's place under g
+    if (node_left(b.lo[g]) == p) b.lo[g].w = __int_as_float(s); else b.hi[g].w = __int_as_float(s);
+    o.parent[s] = g;
+    // paste: p becomes the parent of (x, v) where x was (x's parent read AFTER the cut: it may be g)
+    const int q = o.parent[x];
+    if (node_left(b.lo[q]) == x) b.lo[q].w = __int_as_float(p); else b.hi[q].w = __int_as_float(p);
+    o.parent[p] = q;
+    b.lo[p].w = __int_as_float(x); b.hi[p].w = __int_as_float((int)v);
+    o.parent[x] = p;
+    atomicAdd(n_applied, 1u);
+}
+
+// boxes and primitive counts bottom-up: the second thread to reach a node computes it (the first leaves)
+__global__ void opt_refit_kernel(Bvh2 b, uint32_t n_leaves, const int* __restrict__ parent, uint32_t* __restrict__ arrived) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_leaves) return;
+    int x = parent[i];
+    while (x >= 0) {
+        __threadfence();
+        if (atomicAdd(arrived + x, 1u) == 0u) return;
+        const int l = node_left(b.lo[x]), r = node_right(b.hi[x]);
+        const volatile float4* vlo = b.lo; const volatile float4* vhi = b.hi;
+        const float lx0 = vlo[l].x, ly0 = vlo[l].y, lz0 = vlo[l].z, lx1 = vhi[l].x, ly1 = vhi[l].y, lz1 = vhi[l].z;
+        const float rx0 = vlo[r].x, ry0 = vlo[r].y, rz0 = vlo[r].z, rx1 = vhi[r].x, ry1 = vhi[r].y, rz1 = vhi[r].z;
+        b.lo[x] = make_float4(fminf(lx0, rx0), fminf(ly0, ry0), fminf(lz0, rz0), __int_as_float(l));
+        b.hi[x] = make_float4(fmaxf(lx1, rx1), fmaxf(ly1, ry1), fmaxf(lz1, rz1), __int_as_float(r));
+        b.count[x] = ((volatile uint32_t*)b.count)[l] + ((volatile uint32_t*)b.count)[r];
+        x = parent[x];
+    }
+}
+
+__global__ void opt_cost_kernel(Bvh2 b, uint32_t first_inner, uint32_t n_nodes, double* __restrict__ cost) {
+    const uint32_t i = first_inner + blockIdx.x * blockDim.x + threadIdx.x;
+    float a = i < n_nodes ? half_area(b.lo[i], b.hi[i]) : 0.f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if ((threadIdx.x & 31) == 0 && a != 0.f) atomicAdd(cost, (double)a);
+}
+
 // ---- 4. collapse to 8-wide ------------------------------------------------------------------------------------------
 struct Kids { int id[8]; int n; };
 
@@ -469,7 +642,7 @@ double now_ms() { return std::chrono::duration<double, std::milli>(std::chrono::
 
 // one PLOC run over `n` boxes already on the device; leaves are nodes [0, n), inner nodes follow.  With `prim_seg`
 // clusters only merge inside their segment and the run ends with one root per segment, in segment order.
-struct PlocOut { Bvh2 b; int* roots; uint32_t n_roots; uint32_t iters; void* d_tmp; size_t tmp_bytes; };
+struct PlocOut { Bvh2 b; int* roots; uint32_t n_roots; uint32_t iters; void* d_tmp; size_t tmp_bytes; uint32_t n_nodes; };
 
 int ploc_run(Scratch& sc, const float4* plo, const float4* phi, uint32_t n, const uint32_t* prim_seg, int r, cudaStream_t st,
              PlocOut* out, char* err, size_t errlen) {
@@ -532,6 +705,45 @@ int ploc_run(Scratch& sc, const float4* plo, const float4* phi, uint32_t n, cons
         int* t = cl_in; cl_in = cl_out; cl_out = t;
     }
     out->b = b; out->roots = cl_in; out->n_roots = m; out->iters = iters; out->d_tmp = d_tmp; out->tmp_bytes = tmp_bytes;
+    out->n_nodes = next_node;
+    return 0;
+}
+
+// reinsertion passes over the BVH2 of a PLOC run (3b above); `stats` (optional) receives the SAH cost before / after and the moves
+struct OptStats { double cost_before, cost_after; uint32_t moves, passes; };
+int optimize_run(Scratch& sc, const PlocOut& pl, uint32_t n_leaves, uint32_t passes, uint32_t max_visits, cudaStream_t st, OptStats* stats,
+                 char* err, size_t errlen) {
+    const uint32_t nn = pl.n_nodes;
+    if (stats) memset(stats, 0, sizeof *stats);
+    if (passes == 0 || nn <= n_leaves + 2) return 0;
+    OptArrays o; o.visits = nullptr;
+    uint32_t* arrived; uint32_t* d_count; double* d_cost;
+    BCU(sc.alloc(&o.parent, (size_t)nn * 4)); BCU(sc.alloc(&o.gain, (size_t)nn * 4)); BCU(sc.alloc(&o.target, (size_t)nn * 4));
+    BCU(sc.alloc(&o.lock, (size_t)nn * 8)); BCU(sc.alloc(&arrived, (size_t)nn * 4));
+    BCU(sc.alloc(&d_count, 4)); BCU(sc.alloc(&d_cost, 16));
+    BCU(cudaMemsetAsync(o.parent, 0xff, (size_t)nn * 4, st));
+    opt_parent_kernel<<<blocks(nn - n_leaves), TPB, 0, st>>>(pl.b, n_leaves, nn, o.parent);
+    BCU(cudaMemsetAsync(d_cost, 0, 16, st));
+    BCU(cudaMemsetAsync(d_count, 0, 4, st));
+    opt_cost_kernel<<<blocks(nn - n_leaves), TPB, 0, st>>>(pl.b, n_leaves, nn, d_cost);
+    for (uint32_t pass = 0; pass < passes; pass++) {
+        opt_find_kernel<<<(nn + 127) / 128, 128, 0, st>>>(pl.b, nn, o, max_visits);
+        BCU(cudaMemsetAsync(o.lock, 0, (size_t)nn * 8, st));
+        opt_lock_kernel<<<blocks(nn), TPB, 0, st>>>(pl.b, nn, o);
+        opt_check_kernel<<<blocks(nn), TPB, 0, st>>>(pl.b, nn, o);
+        opt_apply_kernel<<<blocks(nn), TPB, 0, st>>>(pl.b, nn, o, d_count);
+        BCU(cudaMemsetAsync(arrived, 0, (size_t)nn * 4, st));
+        opt_refit_kernel<<<blocks(n_leaves), TPB, 0, st>>>(pl.b, n_leaves, o.parent, arrived);
+    }
+    opt_cost_kernel<<<blocks(nn - n_leaves), TPB, 0, st>>>(pl.b, n_leaves, nn, d_cost + 1);
+    BCU(cudaGetLastError());
+    if (stats) {
+        double c[2]; uint32_t moves;
+        BCU(cudaMemcpyAsync(c, d_cost, 16, cudaMemcpyDeviceToHost, st));
+        BCU(cudaMemcpyAsync(&moves, d_count, 4, cudaMemcpyDeviceToHost, st));
+        BCU(cudaStreamSynchronize(st));
+        stats->cost_before = c[0]; stats->cost_after = c[1]; stats->moves = moves; stats->passes = passes;
+    }
     return 0;
 }
 
@@ -628,7 +840,7 @@ int build_tlas(const float* tris9_host, uint64_t n_tris, const uint64_t* object_
     const int r = (int)(radius < 1 ? 1 : (radius > 64 ? 64 : radius));
     const double t_begin = now_ms();
     Scratch sc;
-    sc.reserve((size_t)n * 288 + (size_t)(tlas ? n_objects : 0) * 16 + (64u << 20));      // every array of the run (~270 B per triangle) + slack
+    sc.reserve((size_t)n * 344 + (size_t)(tlas ? n_objects : 0) * 16 + (64u << 20));      // every array of the run (~320 B per triangle) + slack
     float* d_tris9; float4 *plo, *phi; uint32_t* prim_seg = nullptr; uint64_t* d_off = nullptr;
     BCU(sc.alloc(&d_tris9, (size_t)n * 36));
     BCU(sc.alloc(&plo, (size_t)n * 16)); BCU(sc.alloc(&phi, (size_t)n * 16));
@@ -645,7 +857,18 @@ int build_tlas(const float* tris9_host, uint64_t n_tris, const uint64_t* object_
     int rc = ploc_run(sc, plo, phi, n, prim_seg, r, st, &pl, err, errlen);
     if (rc) return rc;
     if (tlas && pl.n_roots != n_objects) { snprintf(err, errlen, "PLOC left %u roots for %u objects", pl.n_roots, n_objects); return -3; }
+    BCU(cudaStreamSynchronize(st));
     const double t_ploc = now_ms();
+    // reinsertion passes (obvhs: `reinsertion_batch_ratio`, reference src/main.rs:563-587); TRAY_CUDA_BUILD_REINSERT=0 turns them off
+    const char* re_env = getenv("TRAY_CUDA_BUILD_REINSERT");
+    const char* rv_env = getenv("TRAY_CUDA_BUILD_REINSERT_VISITS");
+    const uint32_t re_passes = re_env && *re_env ? (uint32_t)atoi(re_env) : 2u;
+    const uint32_t re_visits = rv_env && *rv_env ? (uint32_t)atoi(rv_env) : 192u;
+    OptStats os;
+    rc = optimize_run(sc, pl, n, re_passes, re_visits, st, &os, err, errlen);
+    if (rc) return rc;
+    BCU(cudaStreamSynchronize(st));
+    const double t_opt = now_ms();
 
     // node count of a BLAS is bounded by its triangle count (>= 1 node); the TLAS by the object count
     const uint64_t blas_cap = (uint64_t)n + (tlas ? n_objects : 1), tlas_cap = tlas ? (uint64_t)n_objects + 1 : 0;
@@ -664,13 +887,15 @@ int build_tlas(const float* tris9_host, uint64_t n_tris, const uint64_t* object_
     if (tlas) {
         // TLAS: the same pipeline over the BLAS boxes; its "triangles" are instance slots
         Scratch sc2;
-        sc2.reserve((size_t)n_objects * 288 + (16u << 20));
+        sc2.reserve((size_t)n_objects * 344 + (16u << 20));
         float4 *tlo, *thi; uint32_t* tl_prim;
         if (sc2.alloc(&tlo, (size_t)n_objects * 16) != cudaSuccess || sc2.alloc(&thi, (size_t)n_objects * 16) != cudaSuccess ||
             sc2.alloc(&tl_prim, (size_t)n_objects * 4) != cudaSuccess) { snprintf(err, errlen, "out of device memory"); cudaGetLastError(); return bail(-2); }
         blas_boxes_kernel<<<blocks(n_objects), TPB, 0, st>>>(pl.roots, n_objects, pl.b, tlo, thi);
         PlocOut tp;
         rc = ploc_run(sc2, tlo, thi, n_objects, nullptr, r, st, &tp, err, errlen);
+        if (rc) return bail(rc);
+        rc = optimize_run(sc2, tp, n_objects, re_passes, re_visits, st, nullptr, err, errlen);
         if (rc) return bail(rc);
         CollapseOut tc;
         tlas_start = co.n_nodes;
@@ -686,7 +911,9 @@ int build_tlas(const float* tris9_host, uint64_t n_tris, const uint64_t* object_
     out->force_exact = force_exact;
     out->stats.n_tris = n; out->stats.n_nodes = n_nodes; out->stats.ploc_iterations = pl.iters + tl_iters; out->stats.levels = co.levels + tl_levels;
     out->stats.ms_upload = (float)(t_upload - t_begin); out->stats.ms_sort = 0.f;
-    out->stats.ms_ploc = (float)(t_ploc - t_upload); out->stats.ms_collapse = (float)(t_end - t_ploc); out->stats.ms_total = (float)(t_end - t_begin);
+    out->stats.ms_ploc = (float)(t_ploc - t_upload); out->stats.ms_collapse = (float)(t_end - t_opt); out->stats.ms_total = (float)(t_end - t_begin);
+    out->stats.ms_reinsert = (float)(t_opt - t_ploc); out->stats.reinsert_passes = os.passes; out->stats.reinsert_moves = os.moves;
+    out->stats.sah_before = (float)os.cost_before; out->stats.sah_after = (float)os.cost_after;
     return 0;
 }
 

@@ -50,7 +50,9 @@ class Counters(C.Structure):
 
 class BuildStats(C.Structure):
     _fields_ = [("n_tris", C.c_uint64), ("n_nodes", C.c_uint64), ("ploc_iterations", C.c_uint32), ("levels", C.c_uint32),
-                ("ms_upload", C.c_float), ("ms_sort", C.c_float), ("ms_ploc", C.c_float), ("ms_collapse", C.c_float), ("ms_total", C.c_float)]
+                ("ms_upload", C.c_float), ("ms_sort", C.c_float), ("ms_ploc", C.c_float), ("ms_collapse", C.c_float), ("ms_total", C.c_float),
+                ("ms_reinsert", C.c_float), ("reinsert_passes", C.c_uint32), ("reinsert_moves", C.c_uint32),
+                ("sah_before", C.c_float), ("sah_after", C.c_float)]
 
     def as_dict(self):
         return {n: getattr(self, n) for n, _ in self._fields_}
