@@ -200,7 +200,7 @@ typedef struct tray_build_stats {
     uint32_t ploc_iterations, levels;
     float    ms_upload, ms_sort, ms_ploc, ms_collapse, ms_total;   /* host wall clock around synchronised phases */
     /* reinsertion passes between PLOC and the collapse (obvhs: reinsertion_batch_ratio, src/main.rs:563-587; environment
-     * TRAY_CUDA_BUILD_REINSERT = number of passes, default 2, 0 = off): time, subtrees moved, SAH cost (sum of the inner nodes'
+     * TRAY_CUDA_BUILD_REINSERT = number of passes, default 4, 0 = off): time, subtrees moved, SAH cost (sum of the inner nodes'
      * half areas) of the BVH2 before and after */
     float    ms_reinsert;
     uint32_t reinsert_passes, reinsert_moves;

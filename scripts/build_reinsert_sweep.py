@@ -23,9 +23,13 @@ for scene in scenes:
     sc.close()
     print(f"{scene} host binned-SAH BVH: {p.n_nodes} nodes, primary {min(a for a, _ in k):.3f} ms bounce {min(b for _, b in k):.3f} ms, "
           f"nodes/ray {cp['nodes'] / cp['rays']:.2f} {cb['nodes'] / max(1, cb['rays']):.2f}", flush=True)
-    for passes, visits in ((0, 192), (1, 192), (2, 64), (2, 192), (2, 512), (4, 192), (8, 192)):
+    configs = ((0, 192, 1), (1, 192, 1), (1, 192, 3), (2, 192, 3), (2, 192, 6), (3, 192, 4), (4, 192, 3), (4, 64, 3), (8, 192, 3))
+    if os.environ.get("SWEEP_SHORT"):
+        configs = ((0, 192, 1), (4, 192, 3))
+    for passes, visits, rounds in configs:
         os.environ["TRAY_CUDA_BUILD_REINSERT"] = str(passes)
         os.environ["TRAY_CUDA_BUILD_REINSERT_VISITS"] = str(visits)
+        os.environ["TRAY_CUDA_BUILD_REINSERT_ROUNDS"] = str(rounds)
         cuda.TrayCudaScene.build(tris).close()
         best = None
         for _ in range(3):
@@ -39,6 +43,6 @@ for scene in scenes:
         g.render(view, w, h, 0, cuda.RENDER_BOUNCE | cuda.RENDER_COUNTERS)
         cp, cb = g.counters()
         g.close()
-        print(f"{scene} device PLOC + {passes} reinsertion pass(es) x {visits} visits: {best['n_nodes']} nodes, build {best['ms_total']:.1f} ms (reinsert {best['ms_reinsert']:.1f}), "
+        print(f"{scene} device PLOC + {passes} reinsertion pass(es) x {visits} visits x {rounds} rounds: {best['n_nodes']} nodes, build {best['ms_total']:.1f} ms (reinsert {best['ms_reinsert']:.1f}), "
               f"moves {best['reinsert_moves']}, SAH {best['sah_before']:.4g} -> {best['sah_after']:.4g}, primary {min(a for a, _ in k):.3f} ms bounce {min(b for _, b in k):.3f} ms, "
               f"nodes/ray {cp['nodes'] / cp['rays']:.2f} {cb['nodes'] / max(1, cb['rays']):.2f}", flush=True)

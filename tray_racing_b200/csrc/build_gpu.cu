@@ -284,11 +284,12 @@ __global__ void __launch_bounds__(PLOC_TAIL) ploc_tail_kernel(int* __restrict__ 
 //   find   every node v looks for the position x that lowers the tree's SAH cost (sum of inner-node areas) most if the subtree of
 //          v is cut out and re-inserted as the sibling of x: it climbs from its parent to the root and searches the subtree on the
 //          other side of every ancestor with branch and bound (the induced growth of the boxes on the way down is the bound)
-//   lock   the moves are ordered by (gain, node): each claims every node on the path v .. common ancestor .. x with atomicMax
-//   apply  a move that still owns its whole path rewires six pointers; disjoint paths cannot interfere (nor form a cycle)
+//   lock   the moves are ordered by (gain, node): each claims the six nodes it rewires with atomicMax; a move that still owns all
+//          six wins, unless its target sits inside the subtree a higher-ranked winner moves (that could close a cycle)
+//   apply  the winners rewire their pointers concurrently
 //   refit  boxes and primitive counts bottom-up
 // All of it is deterministic (the lock key is a total order), so replicas built on different GPUs still agree byte for byte.
-struct OptArrays { int* parent; float* gain; int* target; unsigned long long* lock; uint32_t* visits; };
+struct OptArrays { int* parent; float* gain; int* target; unsigned long long* lock; uint32_t* visits; uint8_t* win; };
 
 __global__ void opt_parent_kernel(Bvh2 b, uint32_t first_inner, uint32_t n_nodes, int* __restrict__ parent) {
     const uint32_t i = first_inner + blockIdx.x * blockDim.x + threadIdx.x;
@@ -366,47 +367,64 @@ __global__ void __launch_bounds__(128) opt_find_kernel(Bvh2 b, uint32_t n_nodes,
     if (best_x >= 0 && best > aL * 1e-6f) { o.gain[v] = best; o.target[v] = best_x; }
 }
 
-// every node on the path v -> common ancestor -> x (both ends and the parents that get rewired included)
+// The six nodes a move rewires: v (parent), its parent p (children, parent), its sibling s (parent), its grandparent g (child), the
+// target x (parent) and x's parent q (child).  Moves are ordered by key = (gain, v): each claims its six nodes with atomicMax, and
+// a move that still owns all six after everybody has claimed is a winner of the pass.
 template <typename F>
-__device__ void opt_walk_path(const Bvh2& b, const int* parent, int v, int x, F f) {
-    // depth is not stored: climb both sides alternately until they meet, marking as we go would need memory; instead climb
-    // v's side to the root collecting nothing, which is O(depth) twice — paths are short (tens of nodes)
-    int depth_v = 0, depth_x = 0;
-    for (int a = v; a >= 0 && depth_v < (1 << 20); a = parent[a]) depth_v++;
-    for (int a = x; a >= 0 && depth_x < (1 << 20); a = parent[a]) depth_x++;
-    int a = v, c = x;
-    while (depth_v > depth_x) { f(a); a = parent[a]; depth_v--; }
-    while (depth_x > depth_v) { f(c); c = parent[c]; depth_x--; }
-    while (a != c && a >= 0 && c >= 0) { f(a); f(c); a = parent[a]; c = parent[c]; }
-    if (a < 0 || c < 0) return;                             // different trees of a forest: cannot happen (the search stops at the root)
-    f(a);                                                   // the common ancestor
-    if (parent[a] >= 0) f(parent[a]);                       // x may be a path node itself: its parent is rewired
+__device__ __forceinline__ void opt_six(const Bvh2& b, const int* parent, int v, int x, F f) {
+    const int p = parent[v];
+    f(v); f(p); f(sibling_of(b, parent, v)); f(parent[p]); f(x);
+    if (parent[x] >= 0) f(parent[x]);
+}
+__device__ __forceinline__ unsigned long long opt_key(const OptArrays& o, uint32_t v) {
+    return ((unsigned long long)__float_as_uint(o.gain[v]) << 32) | v;
 }
 
-__global__ void opt_lock_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o) {
+// `dirty` marks the nodes earlier rounds of this pass have rewired: a move found before those rounds is still a valid move as
+// long as none of its six nodes is dirty and its target has not ended up inside the subtree it moves (re-checked by a walk up).
+__global__ void opt_lock_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o, const uint8_t* __restrict__ dirty, int round) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes || o.target[v] < 0) return;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(o.gain[v]) << 32) | v;
-    opt_walk_path(b, o.parent, (int)v, o.target[v], [&](int x) { atomicMax(o.lock + x, key); });
-    atomicMax(o.lock + sibling_of(b, o.parent, (int)v), key);
+    if (round > 0) {
+        bool stale = false;
+        opt_six(b, o.parent, (int)v, o.target[v], [&](int y) { if (dirty[y]) stale = true; });
+        int guard = 0;
+        for (int a = o.target[v]; a >= 0 && guard < (1 << 20) && !stale; a = o.parent[a], guard++) if ((uint32_t)a == v) stale = true;
+        if (stale || o.parent[o.parent[v]] < 0) { o.target[v] = -1; return; }
+    }
+    const unsigned long long key = opt_key(o, v);
+    opt_six(b, o.parent, (int)v, o.target[v], [&](int y) { atomicMax(o.lock + y, key); });
 }
 
-// a move that still owns every node of its path wins; the others are dropped for this pass.  (A kernel of its own: the walk
-// reads parent pointers, which the apply kernel rewrites.)
 __global__ void opt_check_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_nodes || o.target[v] < 0) return;
-    const unsigned long long key = ((unsigned long long)__float_as_uint(o.gain[v]) << 32) | v;
+    const unsigned long long key = opt_key(o, v);
     bool mine = true;
-    opt_walk_path(b, o.parent, (int)v, o.target[v], [&](int y) { if (o.lock[y] != key) mine = false; });
-    if (o.lock[sibling_of(b, o.parent, (int)v)] != key) mine = false;
-    if (!mine) o.target[v] = -1;
+    opt_six(b, o.parent, (int)v, o.target[v], [&](int y) { if (o.lock[y] != key) mine = false; });
+    o.win[v] = mine ? 1 : 0;
+}
+
+// Disjoint pointer sets are not enough: if A's target lies inside the subtree B moves and B's target inside the subtree A moves,
+// applying both ties the two subtrees into a cycle.  A winner whose target has a HIGHER-keyed winner's moving node among its
+// ancestors steps back for this pass; around any would-be cycle at least one edge points to a higher key, so no cycle survives.
+__global__ void opt_cycle_kernel(uint32_t n_nodes, OptArrays o, uint8_t* __restrict__ drop) {
+    const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n_nodes) return;
+    drop[v] = 0;
+    if (o.target[v] < 0 || !o.win[v]) return;
+    const unsigned long long key = opt_key(o, v);
+    int guard = 0;
+    for (int a = o.target[v]; a >= 0 && guard < (1 << 20); a = o.parent[a], guard++)
+        if ((uint32_t)a != v && o.target[a] >= 0 && o.win[a] && opt_key(o, (uint32_t)a) > key) { drop[v] = 1; return; }
 }
 
 // winners own disjoint sets of nodes, so they rewire concurrently
-__global__ void opt_apply_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o, uint32_t* __restrict__ n_applied) {
+__global__ void opt_apply_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o, const uint8_t* __restrict__ drop, uint8_t* __restrict__ dirty,
+                                 uint32_t* __restrict__ n_applied) {
     const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_nodes || o.target[v] < 0) return;
+    if (v >= n_nodes || o.target[v] < 0 || !o.win[v] || drop[v]) return;
+    opt_six(b, o.parent, (int)v, o.target[v], [&](int y) { dirty[y] = 1; });
     const int x = o.target[v];
     const int s = sibling_of(b, o.parent, (int)v);
     const int p = o.parent[v], g = o.parent[p];
@@ -419,6 +437,7 @@ __global__ void opt_apply_kernel(Bvh2 b, uint32_t n_nodes, OptArrays o, uint32_t
     o.parent[p] = q;
     b.lo[p].w = __int_as_float(x); b.hi[p].w = __int_as_float((int)v);
     o.parent[x] = p;
+    o.target[v] = -1;                                       // done for this pass
     atomicAdd(n_applied, 1u);
 }
 
@@ -717,10 +736,12 @@ int optimize_run(Scratch& sc, const PlocOut& pl, uint32_t n_leaves, uint32_t pas
     if (stats) memset(stats, 0, sizeof *stats);
     if (passes == 0 || nn <= n_leaves + 2) return 0;
     OptArrays o; o.visits = nullptr;
-    uint32_t* arrived; uint32_t* d_count; double* d_cost;
+    uint32_t* arrived; uint32_t* d_count; double* d_cost; uint8_t* drop; uint8_t* dirty;
+    const char* rr_env = getenv("TRAY_CUDA_BUILD_REINSERT_ROUNDS");
+    const uint32_t rounds = rr_env && *rr_env ? (uint32_t)atoi(rr_env) : 3u;
     BCU(sc.alloc(&o.parent, (size_t)nn * 4)); BCU(sc.alloc(&o.gain, (size_t)nn * 4)); BCU(sc.alloc(&o.target, (size_t)nn * 4));
     BCU(sc.alloc(&o.lock, (size_t)nn * 8)); BCU(sc.alloc(&arrived, (size_t)nn * 4));
-    BCU(sc.alloc(&d_count, 4)); BCU(sc.alloc(&d_cost, 16));
+    BCU(sc.alloc(&d_count, 4)); BCU(sc.alloc(&d_cost, 16)); BCU(sc.alloc(&drop, (size_t)nn)); BCU(sc.alloc(&dirty, (size_t)nn)); BCU(sc.alloc(&o.win, (size_t)nn));
     BCU(cudaMemsetAsync(o.parent, 0xff, (size_t)nn * 4, st));
     opt_parent_kernel<<<blocks(nn - n_leaves), TPB, 0, st>>>(pl.b, n_leaves, nn, o.parent);
     BCU(cudaMemsetAsync(d_cost, 0, 16, st));
@@ -728,10 +749,14 @@ int optimize_run(Scratch& sc, const PlocOut& pl, uint32_t n_leaves, uint32_t pas
     opt_cost_kernel<<<blocks(nn - n_leaves), TPB, 0, st>>>(pl.b, n_leaves, nn, d_cost);
     for (uint32_t pass = 0; pass < passes; pass++) {
         opt_find_kernel<<<(nn + 127) / 128, 128, 0, st>>>(pl.b, nn, o, max_visits);
-        BCU(cudaMemsetAsync(o.lock, 0, (size_t)nn * 8, st));
-        opt_lock_kernel<<<blocks(nn), TPB, 0, st>>>(pl.b, nn, o);
-        opt_check_kernel<<<blocks(nn), TPB, 0, st>>>(pl.b, nn, o);
-        opt_apply_kernel<<<blocks(nn), TPB, 0, st>>>(pl.b, nn, o, d_count);
+        BCU(cudaMemsetAsync(dirty, 0, (size_t)nn, st));
+        for (uint32_t round = 0; round < rounds; round++) {     // several claim / apply rounds over the moves one search found
+            BCU(cudaMemsetAsync(o.lock, 0, (size_t)nn * 8, st));
+            opt_lock_kernel<<<blocks(nn), TPB, 0, st>>>(pl.b, nn, o, dirty, (int)round);
+            opt_check_kernel<<<blocks(nn), TPB, 0, st>>>(pl.b, nn, o);
+            opt_cycle_kernel<<<blocks(nn), TPB, 0, st>>>(nn, o, drop);
+            opt_apply_kernel<<<blocks(nn), TPB, 0, st>>>(pl.b, nn, o, drop, dirty, d_count);
+        }
         BCU(cudaMemsetAsync(arrived, 0, (size_t)nn * 4, st));
         opt_refit_kernel<<<blocks(n_leaves), TPB, 0, st>>>(pl.b, n_leaves, o.parent, arrived);
     }
@@ -862,7 +887,7 @@ int build_tlas(const float* tris9_host, uint64_t n_tris, const uint64_t* object_
     // reinsertion passes (obvhs: `reinsertion_batch_ratio`, reference src/main.rs:563-587); TRAY_CUDA_BUILD_REINSERT=0 turns them off
     const char* re_env = getenv("TRAY_CUDA_BUILD_REINSERT");
     const char* rv_env = getenv("TRAY_CUDA_BUILD_REINSERT_VISITS");
-    const uint32_t re_passes = re_env && *re_env ? (uint32_t)atoi(re_env) : 2u;
+    const uint32_t re_passes = re_env && *re_env ? (uint32_t)atoi(re_env) : 4u;
     const uint32_t re_visits = rv_env && *rv_env ? (uint32_t)atoi(rv_env) : 192u;
     OptStats os;
     rc = optimize_run(sc, pl, n, re_passes, re_visits, st, &os, err, errlen);
