@@ -398,20 +398,21 @@ def max_over_ranks(torch, dist, world, x):
 _keep_alive = []
 
 
-def strong_scaling_record(torch, dist, cuda, host, rank, world, local_rank, stream, steps):
-    """BASELINE.json configs[3] inside every --gpus N line: the San-Miguel-sized scene at a FIXED 3840x2160 frame, tiles dealt
-    over the N ranks (strong scaling).  speedup_vs_n1 = this run's own one-GPU time (rank 0 renders the whole frame alone, the
-    other ranks idle) / the N-GPU time — same box, same build, same protocol.  The BVH is built on each rank's GPU from the
-    triangle soup (tray_cuda_scene_build: deterministic, so the replicas agree)."""
+def strong_scaling_record(torch, dist, cuda, host, rank, world, local_rank, stream, steps, which="c4"):
+    """BASELINE.json configs[3] (c4) inside every --gpus N line — and configs[4] (c5, `--tlas`) at N = 8: the scene at a FIXED
+    3840x2160 frame, tiles dealt over the N ranks (strong scaling).  speedup_vs_n1 = this run's own one-GPU time (rank 0 renders
+    the whole frame alone, the other ranks idle) / the N-GPU time — same box, same build, same protocol.  The BVH is built on each
+    rank's GPU from the triangle soup (tray_cuda_scene_build[_tlas]: deterministic, so the replicas agree)."""
     global WL
     saved = WL
-    WL = WORKLOADS["c4"]
+    WL = WORKLOADS[which]
     try:
         w, h = WL["w"], WL["h"]
         mesh = host.Mesh.generate(WL["scene"], WL["seed"], 1.0)
-        scene = cuda.TrayCudaScene.build(mesh.tris(), tri_stride=TRI_STRIDE, device=local_rank)
+        scene = cuda.TrayCudaScene.build(mesh.tris(), tri_stride=TRI_STRIDE, device=local_rank,
+                                         object_offsets=mesh.object_offsets() if WL["tlas"] else None)
         scene.set_stream(stream.cuda_stream)
-        view = host.view_from_camera(mesh.camera, w, h, 0)
+        view = host.view_from_camera(mesh.camera, w, h, scene.info()["tlas_start"] if WL["tlas"] else 0)
         flags = cuda.RENDER_BOUNCE | cuda.RENDER_RGBA
         scene.render(view, w, h, 0, flags | cuda.RENDER_COUNTERS, rank, world)
         cp, cb = scene.counters()
@@ -453,7 +454,7 @@ def strong_scaling_record(torch, dist, cuda, host, rank, world, local_rank, stre
                 out["one_frame_at_a_time"] = rec
         out["unit"] = UNIT
         out["note"] = ("ms_per_step = CUDA-event time of the steps / steps, max over ranks, exchange included (kernels store pixels into "
-                       "rank 0's frame over NVLink, completion flags); no L2 flush (working set 300 MB > 126 MB L2)")
+                       "rank 0's frame over NVLink, completion flags); no L2 flush (working set 0.3 / 1.1 GB > 126 MB L2)")
         rig.close()
         torch.cuda.synchronize()
         _keep_alive.append(scene)        # closed by the caller after the process group is gone
@@ -595,14 +596,14 @@ def run_ours(args):
     # ---- end to end through the public API with HOST buffers ----
     # Every step: tray_cuda_render on every rank (view + frame parameters go in by value, 160 B per rank), the exchange step,
     # and the readback of that frame's RGBA8 into pinned host memory on rank 0 through a small ring of buffers: the D2H of frame k
-    # overlaps the kernels of the next frames; frame k is in host memory before frame k + RING is issued (RING = 2 at N = 1, 3
-    # above), the last frames are waited for inside the timed region.  N = 1: tray_cuda_frame_readback_begin / _wait.  N > 1
+    # overlaps the kernels of the next frames; frame k is in host memory before frame k + 3 is issued, the last frames are
+    # waited for inside the timed region.  N = 1: tray_cuda_frame_readback_begin / _wait.  N > 1
     # (peer exchange): rank 0 snapshots the complete frame out of its target on the frame's own stream, behind the flag waits that
     # complete it, hands the target back (consumed flags) and copies the snapshot to the host on a copy stream.
     rig.configure(overlap, in_flight)
     e2e_steps = max(3, min(steps, 50))
     owner = rank == 0
-    RING = 2 if world == 1 else 3                    # host / staging buffers: frame i is in host memory before frame i + RING is issued
+    RING = 3                                         # host / staging buffers: frame i is in host memory before frame i + RING is issued
     host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True) for _ in range(RING)] if owner else None
     stage = [torch.empty(h * w, dtype=torch.int32, device="cuda") for _ in range(RING)] if (owner and world > 1) else None
     copy_stream = torch.cuda.Stream() if (owner and world > 1) else None
@@ -627,8 +628,8 @@ def run_ours(args):
         if world == 1:
             scene.render(view, w, h, 0, rig.flags, 0, 1, timed=False)
             scene.readback_begin(host_frames[b].numpy(), b)       # untile on the frame's stream, D2H on the copy stream
-            if i > 0:
-                scene.readback_wait(b ^ 1)
+            if i > 1:
+                scene.readback_wait((i - 2) % RING)               # frame i - 2 is in host memory before frame i + 1 is issued
             return
         if owner and copy_ev[b] is not None:
             copy_ev[b].synchronize()                    # frame i - RING has landed: host buffer b and staging b are free again
@@ -637,14 +638,17 @@ def run_ours(args):
 
     def e2e_drain():
         if world == 1:
-            scene.readback_wait(0); scene.readback_wait(1)
+            for b in range(RING):
+                scene.readback_wait(b)
         elif owner:
             for e in copy_ev:
                 if e is not None:
                     e.synchronize()
 
     rig.k = 0
-    e2e_step(0); e2e_step(1); e2e_drain()             # untimed: staging allocated, copy paths warm
+    for i in range(RING):
+        e2e_step(i)                                   # untimed: every staging buffer allocated, copy paths warm
+    e2e_drain()
     rig.sync_all()
     rig.k = 0
     t0 = time.perf_counter()
@@ -669,9 +673,11 @@ def run_ours(args):
     e2e_sync_val = rays_all * e2e_steps / max_over_ranks(torch, dist, world, time.perf_counter() - t0) / 1e6
 
     # ---- strong scaling on BASELINE.json configs[3] (every N), outside every timed region above ----
-    strong = None
+    strong = strong_c5 = None
     if args.workload == "c3" and os.environ.get("TRAY_BENCH_STRONG", "1") != "0":
         strong = strong_scaling_record(torch, dist, cuda, host, rank, world, local_rank, stream, max(10, min(steps, 40)))
+        if world == 8 or os.environ.get("TRAY_BENCH_STRONG_C5") == "1":
+            strong_c5 = strong_scaling_record(torch, dist, cuda, host, rank, world, local_rank, stream, max(10, min(steps, 30)), which="c5")
 
     # ---- beside the headline (N = 1 only, outside every timed region above): the rows SURVEY.md §8 marks "next" ----
     extras = None
@@ -788,6 +794,8 @@ def run_ours(args):
         }
         if strong is not None:
             line["strong"] = strong
+        if strong_c5 is not None:
+            line["strong_c5"] = strong_c5
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
         if extras:

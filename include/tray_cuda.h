@@ -289,11 +289,13 @@ int tray_cuda_frame_download(tray_scene* scene, tray_hit* primary, tray_hit* bou
                              tray_ray* bounce_rays, uint8_t* rgba);
 
 /* Asynchronous readback of the last frame's RGBA8 (row-major, width*height*4 bytes) into HOST memory — pinned memory
- * if the copy is to overlap anything.  `begin` enqueues the untile on the scene stream and the copy on the scene's own
- * copy stream and returns; the next tray_cuda_render overlaps the copy.  Two staging buffers (slot 0 / 1): alternate
- * them, and `wait` for a slot before reading its host frame (begin on a slot still in flight waits for it first).
+ * if the copy is to overlap anything.  `begin` enqueues the untile on the frame's stream and the copy on the scene's own
+ * copy stream and returns; the next tray_cuda_render overlaps the copy.  TRAY_READBACK_SLOTS staging buffers (slot 0 .. 3): cycle
+ * through two or three of them, and `wait` for a slot before reading its host frame (begin on a slot still in flight waits for
+ * it first).
  * After a frame rendered into a frame target (tray_cuda_scene_set_frame_target) the WHOLE target is read back — every
  * shard's pixels: call it on the device that owns the frame, stream-ordered after the barrier that completes the frame. */
+#define TRAY_READBACK_SLOTS 4
 int tray_cuda_frame_readback_begin(tray_scene* scene, uint8_t* rgba_host, uint32_t slot);
 int tray_cuda_frame_readback_wait(tray_scene* scene, uint32_t slot);
 

@@ -1,7 +1,7 @@
-"""GPU tests at BASELINE.json's full sizes.  The oracle still finishes in seconds at 1080p on the 2.88 M-triangle
-scene, so C3 is compared in full; the 5 M / 19 M-triangle scenes are checked on a bounded ray sample plus
-size-independent properties (flat == TLAS closest hit, re-intersection of the reported primitive, shard
-reassembly, run-to-run determinism)."""
+"""GPU tests at BASELINE.json's full sizes.  The oracle finishes a whole frame in seconds on the box's host cores, so all five
+configs are compared pixel for pixel (C1, C2, C3 at 1920x1080; C4 and C5 `--tlas` at 3840x2160), on both frame paths, counters
+included; the 5 M / 19 M-triangle scenes additionally through size-independent properties (flat == TLAS closest hit,
+re-intersection of the reported primitive, shard reassembly, run-to-run determinism)."""
 import numpy as np
 import pytest
 
@@ -59,6 +59,13 @@ def test_c4_sanmiguel_full_4k_frame_against_oracle():
     """All 8.3 M primary rays and their bounce rays of the 5.08 M-triangle scene at 3840x2160 — not a sample."""
     ref = full_frame_against_oracle("sanmiguel", 4, 3840, 2160, n_tris=5075977)
     assert ref["primary_totals"]["rays"] == 3840 * 2160
+
+
+def test_c5_caldera_tlas_full_4k_frame_against_oracle():
+    """BASELINE configs[4]: 19.26 M triangles in ~4096 BLAS under a TLAS, every pixel of the 3840x2160 frame, primary + bounce,
+    both frame paths, instance / node / triangle counters included."""
+    ref = full_frame_against_oracle("caldera", 5, 3840, 2160, n_tris=19261109, tlas=True)
+    assert ref["primary_totals"]["insts"] > 3840 * 2160
 
 
 @pytest.mark.parametrize("name,seed,w,h", [("sanmiguel", 4, 3840, 2160), ("caldera", 5, 3840, 2160)])

@@ -106,11 +106,11 @@ struct tray_scene {
     void* d_untiled = nullptr; uint64_t untiled_cap = 0;
     // asynchronous RGBA readback: double-buffered row-major staging, copies on their own stream
     cudaStream_t copy_stream = nullptr;
-    uchar4* d_stage[2] = { nullptr, nullptr }; uint64_t stage_cap[2] = { 0, 0 }; bool stage_busy[2] = { false, false };
-    cudaEvent_t ev_untiled[2] = { nullptr, nullptr }, ev_copied[2] = { nullptr, nullptr };
+    uchar4* d_stage[TRAY_READBACK_SLOTS] = {}; uint64_t stage_cap[TRAY_READBACK_SLOTS] = {}; bool stage_busy[TRAY_READBACK_SLOTS] = {};
+    cudaEvent_t ev_untiled[TRAY_READBACK_SLOTS] = {}, ev_copied[TRAY_READBACK_SLOTS] = {};
     cudaEvent_t ev_after = nullptr;          // tray_cuda_scene_after
     uint32_t bounce_sort = 1;                // raygen_bounce_kernel: 0 append in pixel order, 1 group by direction octant, 2 octant x major axis
-    uint32_t* h_flag = nullptr;              // pinned, 2 words: the device error flag as it was when staging slot i was filled
+    uint32_t* h_flag = nullptr;              // pinned, one word per staging slot: the device error flag as it was when staging slot i was filled
     uchar4* frame_target = nullptr;          // borrowed: row-major RGBA8 frame (this or a peer device), see tray_cuda_scene_set_frame_target
     tray_counters cnt_primary{}, cnt_bounce{};
 };
@@ -364,7 +364,7 @@ void tray_cuda_scene_destroy(tray_scene* s) {
         if (f.own_stream) cudaStreamDestroy(f.own_stream);
     }
     for (auto& e : s->ev) if (e) cudaEventDestroy(e);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < TRAY_READBACK_SLOTS; i++) {
         if (s->stage_busy[i]) cudaEventSynchronize(s->ev_copied[i]);
         cudaFree(s->d_stage[i]);
         if (s->ev_untiled[i]) cudaEventDestroy(s->ev_untiled[i]);
@@ -426,9 +426,9 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         CU(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&s->ev_after, cudaEventDisableTiming));
         s->bounce_sort = (uint32_t)env_int("TRAY_CUDA_BOUNCE_SORT", 1);
-        CU(cudaMallocHost(&s->h_flag, 2 * sizeof(uint32_t)));
-        s->h_flag[0] = s->h_flag[1] = 0u;
-        for (int i = 0; i < 2; i++) {
+        CU(cudaMallocHost(&s->h_flag, TRAY_READBACK_SLOTS * sizeof(uint32_t)));
+        for (int i = 0; i < TRAY_READBACK_SLOTS; i++) {
+            s->h_flag[i] = 0u;
             CU(cudaEventCreateWithFlags(&s->ev_untiled[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
         }
@@ -1078,7 +1078,7 @@ int tray_cuda_frame_download(tray_scene* s, tray_hit* primary, tray_hit* bounce,
 }
 
 int tray_cuda_frame_readback_begin(tray_scene* s, uint8_t* rgba, uint32_t slot) {
-    if (!s || !rgba || slot > 1) return fail(TRAY_ERR_ARG, "bad argument");
+    if (!s || !rgba || slot >= TRAY_READBACK_SLOTS) return fail(TRAY_ERR_ARG, "bad argument");
     const FrameSlot& f = s->slot[s->cur];
     cudaStream_t st = slot_stream(s, s->cur);
     if (f.fw == 0 || (!f.f_has_rgba && !f.f_target)) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA");
@@ -1116,7 +1116,7 @@ int tray_cuda_frame_readback_begin(tray_scene* s, uint8_t* rgba, uint32_t slot) 
 }
 
 int tray_cuda_frame_readback_wait(tray_scene* s, uint32_t slot) {
-    if (!s || slot > 1) return fail(TRAY_ERR_ARG, "bad argument");
+    if (!s || slot >= TRAY_READBACK_SLOTS) return fail(TRAY_ERR_ARG, "bad argument");
     if (!s->stage_busy[slot]) return TRAY_OK;
     CU(cudaSetDevice(s->device));
     CU(cudaEventSynchronize(s->ev_copied[slot]));
@@ -1405,7 +1405,7 @@ int tray_cuda_group_render_timed(tray_group* g, const tray_view* view, uint32_t 
 }
 
 int tray_cuda_group_readback_begin(tray_group* g, uint8_t* rgba_host, uint32_t slot) {
-    if (!g || slot > 1) return fail(TRAY_ERR_ARG, "bad argument");
+    if (!g || slot >= TRAY_READBACK_SLOTS) return fail(TRAY_ERR_ARG, "bad argument");
     tray_scene* s0 = g->scenes[0];
     int rc = tray_cuda_frame_readback_begin(s0, rgba_host, slot);       // snapshots the frame target on devices[0], D2H on the copy stream
     if (rc) return rc;
