@@ -343,6 +343,17 @@ int tray_cuda_ipc_close(int device, void* d_ptr);
 int tray_cuda_frame_signal(tray_scene* scene, void* d_flag, uint32_t value);
 int tray_cuda_frame_wait_flag(tray_scene* scene, const void* d_flag, uint32_t value, int before_next_frame);
 
+/* The exchange as ONE DMA copy per shard instead of a store per pixel.  Pixels stored straight into a peer frame leave the SM as
+ * scattered 4-byte NVLink writes (measured: +13 % frame time on a 1/8 shard of a 4K frame, 8 GPUs); the alternative keeps the
+ * compact buffer local and moves it with the copy engine:
+ *   every rank, after tray_cuda_render (no frame target):  tray_cuda_frame_push(scene, staging_on_rank0 + shard * items * 4)
+ *                                                           (+ tray_cuda_frame_signal)      — no SM slot needed
+ *   rank 0, once the flags of all shards are in:            tray_cuda_untile_shards(scene, staging, w, h, shards, frame)
+ * `staging` holds the shards back to back, tray_cuda_shard_items(w, h, 0, shards) uchar4 entries each.  Both run on the stream of
+ * the last rendered frame. */
+int tray_cuda_frame_push(tray_scene* scene, void* d_dst);
+int tray_cuda_untile_shards(tray_scene* scene, const void* d_staging, uint32_t width, uint32_t height, uint32_t shards, void* d_frame);
+
 /* RGBA8 of every later tray_cuda_render goes to `d_frame` (row-major, width*height*4 bytes, on this or a peer
  * device) instead of the scene's compact buffer; NULL restores the compact buffer.  The pointer is borrowed.        */
 int tray_cuda_scene_set_frame_target(tray_scene* scene, void* d_frame);
@@ -356,13 +367,15 @@ int tray_cuda_scene_set_frame_target(tray_scene* scene, void* d_frame);
  * wait, rt_gpu_software.rs:333-335; under --benchmark it waits for each frame's timestamps, :337-338 — which is what
  * tray_cuda_start does).  Per frame nothing changes — same launches, same results.  "The last frame" of the
  * download / readback / device_ptrs calls is the frame of the latest tray_cuda_render.  A caller that orders its own work
- * (a collective, a timing event) against the frames uses the two calls below.  n = 1 (default) restores one frame at a time. */
+ * (a collective, a timing event) against the frames uses the calls below.  n = 1 (default) restores one frame at a time; n = 3
+ * (TRAY_MAX_FRAMES_IN_FLIGHT) keeps one more frame queued, which pays on short frames (a 1/8 shard of a 4K frame). */
+#define TRAY_MAX_FRAMES_IN_FLIGHT 3
 int tray_cuda_scene_set_frames_in_flight(tray_scene* scene, uint32_t n);
 /* `stream` (NULL = the scene stream) waits for every frame enqueued so far, whichever slot it runs in. */
 int tray_cuda_scene_fence(tray_scene* scene, void* stream);
 /* Frames enqueued from now on start after the work already enqueued on `stream`. */
 int tray_cuda_scene_after(tray_scene* scene, void* stream);
-/* The cudaStream_t (as void*) frames of slot `which` (0 / 1) run on, or — which = -1 — the stream of the last rendered frame:
+/* The cudaStream_t (as void*) frames of slot `which` (0 .. 2) run on, or — which = -1 — the stream of the last rendered frame:
  * work enqueued on it right after tray_cuda_render (a collective that completes the frame, a copy) is ordered behind that
  * frame and ahead of the next frame of the same slot, without holding back the frame in the other slot. */
 int tray_cuda_scene_frame_stream(tray_scene* scene, int which, void** stream);

@@ -51,7 +51,7 @@ def main():
     print(f"{tag} {a.scene} {w}x{h}/{S}: primary {kp:.3f} ms ({cp['rays'] / kp / 1e3:.0f} Mrays/s) bounce {kb:.3f} ms ({cb['rays'] / max(kb, 1e-9) / 1e3:.0f} Mrays/s) "
           f"sum {kp + kb:.3f} nodes/ray {cp['nodes'] / cp['rays']:.2f} {cb['nodes'] / max(1, cb['rays']):.2f} crc={crc:08x}", flush=True)
     for ov in (0, 1):
-        for nf in (1, 2):
+        for nf in (1, 2, 3):
             sc.set_frames_in_flight(nf)
             fl = base | (cuda.RENDER_OVERLAP if ov else 0)
             best = None

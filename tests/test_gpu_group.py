@@ -46,8 +46,9 @@ def test_hits_to_geometry_matches_cwbvh_tlas_scene_semantics(cornell):
         sc.close()
 
 
+@pytest.mark.parametrize("n_in_flight", [2, 3])
 @pytest.mark.parametrize("overlap", [False, True])
-def test_two_frames_in_flight_are_the_same_frames(cornell, overlap):
+def test_two_frames_in_flight_are_the_same_frames(cornell, overlap, n_in_flight):
     """tray_cuda_scene_set_frames_in_flight(2): consecutive frames alternate between two buffer sets / streams.  Every frame is
     bit-identical to the one-at-a-time frame; frame_count (--animate) changes the bounce rays, so a mix-up of slots would show."""
     p = host.PackedScene(cornell)
@@ -58,7 +59,7 @@ def test_two_frames_in_flight_are_the_same_frames(cornell, overlap):
     sc = cuda.TrayCudaScene.from_packed(p)
     fl = FLAGS | (cuda.RENDER_OVERLAP if overlap else 0)
     try:
-        sc.set_frames_in_flight(2)
+        sc.set_frames_in_flight(n_in_flight)
         for fc in range(4):                                              # download right after each render: "the last frame"
             sc.render(view, w, h, fc, fl, timed=False)
             out = sc.download(primary=True, bounce=True)
@@ -119,7 +120,7 @@ def _devices():
     return list(range(min(cuda.device_count(), 8)))
 
 
-@pytest.mark.parametrize("in_flight", [1, 2])
+@pytest.mark.parametrize("in_flight", [1, 2, 3])
 def test_group_frame_equals_single_gpu_frame(in_flight):
     """One process, all the box's GPUs: tiles dealt round-robin, pixels stored into ONE frame on devices[0] over peer access,
     completion by events.  The frame equals the single-scene frame byte for byte; per-device shards hold the oracle's hits."""
@@ -217,3 +218,29 @@ def test_completion_flags_are_stream_memory_operations(cornell):
     finally:
         sc.close()
         cuda.frame_free(flag)
+
+
+@pytest.mark.parametrize("w,h,shards", [(640, 368, 3), (101, 37, 2), (1920, 1080, 8)])
+def test_push_and_untile_shards_assemble_the_frame(cornell, w, h, shards):
+    """tray_cuda_frame_push + tray_cuda_untile_shards: every shard's compact RGBA moved by one DMA copy into a staging array, then
+    one launch writes the row-major frame — the same bytes as the single-shard frame (ragged sizes included)."""
+    import torch
+    p = host.PackedScene(cornell)
+    view = host.view_from_camera(cornell.camera, w, h)
+    sc = cuda.TrayCudaScene.from_packed(p)
+    items = cuda.local_items(w, h, 0, shards)
+    assert items == cuda.lib().tray_cuda_shard_items(w, h, 0, shards)
+    staging = cuda.frame_alloc(shards * items * 4 + w * h * 4)
+    try:
+        sc.render(view, w, h, 3, FLAGS)
+        want = sc.download(rgba=True)["rgba"].copy()
+        for s in range(shards):
+            sc.render(view, w, h, 3, FLAGS, shard=s, shards=shards, timed=False)
+            sc.push(staging + s * items * 4)
+        sc.untile_shards(staging, w, h, shards, staging + shards * items * 4)
+        sc.sync()
+        got = torch.as_tensor(cuda.DeviceArray(staging + shards * items * 4, (h, w, 4), "|u1", sc), device="cuda").cpu().numpy()
+        assert (got == want).all()
+    finally:
+        sc.close()
+        cuda.frame_free(staging)

@@ -112,6 +112,9 @@ extern "C" {
     pub fn tray_cuda_scene_set_frames_in_flight(scene: *mut TrayScene, n: u32) -> c_int;
     pub fn tray_cuda_scene_fence(scene: *mut TrayScene, stream: *mut c_void) -> c_int;
     pub fn tray_cuda_scene_after(scene: *mut TrayScene, stream: *mut c_void) -> c_int;
+    pub fn tray_cuda_frame_push(scene: *mut TrayScene, d_dst: *mut c_void) -> c_int;
+    pub fn tray_cuda_untile_shards(scene: *mut TrayScene, d_staging: *const c_void, width: u32, height: u32, shards: u32,
+        d_frame: *mut c_void) -> c_int;
     pub fn tray_cuda_frame_signal(scene: *mut TrayScene, d_flag: *mut c_void, value: u32) -> c_int;
     pub fn tray_cuda_frame_wait_flag(scene: *mut TrayScene, d_flag: *const c_void, value: u32, before_next_frame: c_int) -> c_int;
     pub fn tray_cuda_scene_frame_stream(scene: *mut TrayScene, which: c_int, stream: *mut *mut c_void) -> c_int;

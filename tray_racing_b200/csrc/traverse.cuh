@@ -967,4 +967,17 @@ __global__ void untile_kernel(const __grid_constant__ FrameParams F, const T* __
     if (item_to_pixel(F, j, px, py)) dst[(size_t)py * F.width + px] = src[j];
 }
 
+// all shards' compact RGBA (shard s at src + s * items_per_shard) -> row-major frame: one thread per PIXEL, so the frame is written
+// in full 128-byte rows (the inverse of item_to_pixel)
+__global__ void untile_shards_kernel(const uchar4* __restrict__ src, uint32_t width, uint32_t height, uint32_t tiles_x, uint32_t shards,
+                                     uint64_t items_per_shard, uchar4* __restrict__ dst) {
+    const uint32_t px = blockIdx.x * blockDim.x + threadIdx.x, py = blockIdx.y;
+    if (px >= width || py >= height) return;
+    const uint32_t k = (py >> 3) * tiles_x + (px >> 5);
+    const uint32_t shard = k % shards, local_tile = k / shards;
+    const uint32_t lx = px & 31u, ly = py & 7u;
+    const uint32_t j = local_tile * 256u + (((ly >> 2) * 4u + (lx >> 3)) << 5) + ((ly & 3u) << 3) + (lx & 7u);
+    dst[(size_t)py * width + px] = src[(size_t)shard * items_per_shard + j];
+}
+
 }  // namespace tray

@@ -101,7 +101,7 @@ struct tray_scene {
     cudaStream_t s_in = nullptr, s_out = nullptr; bool pipeline_ready = false;
     cudaEvent_t e_in[2] = { nullptr, nullptr }, e_k[2] = { nullptr, nullptr }, e_out[2] = { nullptr, nullptr };
     // frame state: one FrameSlot per frame in flight (tray_cuda_scene_set_frames_in_flight); `cur` = the slot of the last frame
-    FrameSlot slot[2];
+    FrameSlot slot[TRAY_MAX_FRAMES_IN_FLIGHT];
     int n_slots = 1, cur = 0;
     void* d_untiled = nullptr; uint64_t untiled_cap = 0;
     // asynchronous RGBA readback: double-buffered row-major staging, copies on their own stream
@@ -265,7 +265,11 @@ int launch(tray_scene* s, TraceParams& P, cudaStream_t st, unsigned long long* c
     return TRAY_OK;
 }
 
-cudaStream_t slot_stream(const tray_scene* s, int k) { return k == 0 ? s->stream : s->slot[1].own_stream; }
+cudaStream_t slot_stream(const tray_scene* s, int k) { return k == 0 ? s->stream : s->slot[k].own_stream; }
+int sync_slot_streams(const tray_scene* s) {          // the scene's own frame streams (slot 0 runs on tray_scene::stream)
+    for (int k = 1; k < TRAY_MAX_FRAMES_IN_FLIGHT; k++) CU(cudaStreamSynchronize(s->slot[k].own_stream));
+    return TRAY_OK;
+}
 
 void frame_params(FrameParams& F, const tray_view* view, uint32_t w, uint32_t h, uint32_t frame_count, uint32_t shard, uint32_t shards) {
     memset(&F, 0, sizeof F);
@@ -447,9 +451,9 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         CU(cudaMalloc(&s->d_cursor, 16 * sizeof(unsigned long long)));
         CU(cudaMalloc(&s->d_overflow, 4));
         CU(cudaMemsetAsync(s->d_cursor, 0, 16 * sizeof(unsigned long long), s->stream));
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < TRAY_MAX_FRAMES_IN_FLIGHT; k++) {
             FrameSlot& f = s->slot[k];
-            if (k == 1) CU(cudaStreamCreateWithFlags(&f.own_stream, cudaStreamNonBlocking));
+            if (k >= 1) CU(cudaStreamCreateWithFlags(&f.own_stream, cudaStreamNonBlocking));
             CU(cudaMalloc(&f.d_cursor, 16 * sizeof(unsigned long long)));
             CU(cudaMalloc(&f.d_units, sizeof(uint32_t)));
             CU(cudaMemsetAsync(f.d_cursor, 0, 16 * sizeof(unsigned long long), s->stream));
@@ -585,7 +589,7 @@ int tray_cuda_scene_set_stream(tray_scene* s, void* stream) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
     CU(cudaSetDevice(s->device));
     CU(cudaStreamSynchronize(s->stream));
-    CU(cudaStreamSynchronize(s->slot[1].own_stream));
+    { const int rc_ = sync_slot_streams(s); if (rc_) return rc_; }
     s->stream = stream ? (cudaStream_t)stream : s->own_stream;
     return TRAY_OK;
 }
@@ -599,6 +603,27 @@ int tray_cuda_untile_rgba(tray_scene* s, const void* d_compact, uint32_t w, uint
     if (F.n_items == 0) return TRAY_OK;
     // on the stream of the last rendered frame (its compact buffer is the usual source); with one frame in flight: the scene stream
     tray::untile_kernel<uchar4><<<(F.n_items + 255) / 256, 256, 0, slot_stream(s, s->cur)>>>(F, (const uchar4*)d_compact, (uchar4*)d_frame);
+    CU(cudaGetLastError());
+    return TRAY_OK;
+}
+
+int tray_cuda_frame_push(tray_scene* s, void* d_dst) {
+    if (!s || !d_dst) return fail(TRAY_ERR_ARG, "NULL argument");
+    const FrameSlot& f = s->slot[s->cur];
+    if (f.fw == 0 || !f.f_has_rgba) return fail(TRAY_ERR_ARG, "last frame was rendered without TRAY_RENDER_RGBA (or into a frame target)");
+    CU(cudaSetDevice(s->device));
+    if (f.f_items) CU(cudaMemcpyAsync(d_dst, f.d_rgba, (size_t)f.f_items * sizeof(uchar4), cudaMemcpyDeviceToDevice, slot_stream(s, s->cur)));
+    return TRAY_OK;
+}
+
+int tray_cuda_untile_shards(tray_scene* s, const void* d_staging, uint32_t w, uint32_t h, uint32_t shards, void* d_frame) {
+    if (!s || !d_staging || !d_frame) return fail(TRAY_ERR_ARG, "NULL argument");
+    if (shards == 0) shards = 1;
+    if (w == 0 || h == 0) return fail(TRAY_ERR_ARG, "bad frame size");
+    CU(cudaSetDevice(s->device));
+    const dim3 grid((w + 255) / 256, h);
+    tray::untile_shards_kernel<<<grid, 256, 0, slot_stream(s, s->cur)>>>((const uchar4*)d_staging, w, h, (w + 31) / 32, shards,
+                                                                        local_items(w, h, 0, shards), (uchar4*)d_frame);
     CU(cudaGetLastError());
     return TRAY_OK;
 }
@@ -655,7 +680,7 @@ int tray_cuda_scene_set_frame_target(tray_scene* s, void* d_frame) {
 int tray_cuda_sync(tray_scene* s) {
     if (!s) return fail(TRAY_ERR_ARG, "NULL scene");
     CU(cudaSetDevice(s->device));
-    CU(cudaStreamSynchronize(s->slot[1].own_stream));
+    { const int rc_ = sync_slot_streams(s); if (rc_) return rc_; }
     CU(cudaStreamSynchronize(s->stream));
     return check_overflow(s);
 }
@@ -812,9 +837,9 @@ uint64_t tray_cuda_shard_items(uint32_t w, uint32_t h, uint32_t shard, uint32_t 
 }
 
 int tray_cuda_scene_set_frames_in_flight(tray_scene* s, uint32_t n) {
-    if (!s || n < 1 || n > 2) return fail(TRAY_ERR_ARG, "frames in flight must be 1 or 2");
+    if (!s || n < 1 || n > TRAY_MAX_FRAMES_IN_FLIGHT) return fail(TRAY_ERR_ARG, "frames in flight must be 1 .. %d", TRAY_MAX_FRAMES_IN_FLIGHT);
     CU(cudaSetDevice(s->device));
-    CU(cudaStreamSynchronize(s->slot[1].own_stream));
+    { const int rc_ = sync_slot_streams(s); if (rc_) return rc_; }
     CU(cudaStreamSynchronize(s->stream));
     if ((int)n != s->n_slots) { s->n_slots = (int)n; s->cur = 0; }
     return TRAY_OK;
@@ -834,7 +859,7 @@ int tray_cuda_scene_fence(tray_scene* s, void* stream) {
 }
 
 int tray_cuda_scene_frame_stream(tray_scene* s, int which, void** stream) {
-    if (!s || !stream || which < -1 || which > 1) return fail(TRAY_ERR_ARG, "bad argument");
+    if (!s || !stream || which < -1 || which >= TRAY_MAX_FRAMES_IN_FLIGHT) return fail(TRAY_ERR_ARG, "bad argument");
     *stream = (void*)slot_stream(s, which < 0 ? s->cur : which);
     return TRAY_OK;
 }
@@ -882,7 +907,7 @@ int tray_cuda_scene_after(tray_scene* s, void* stream) {
     if (!s || !stream) return fail(TRAY_ERR_ARG, "NULL argument");
     CU(cudaSetDevice(s->device));
     CU(cudaEventRecord(s->ev_after, (cudaStream_t)stream));
-    for (int k = 0; k < 2; k++)
+    for (int k = 0; k < TRAY_MAX_FRAMES_IN_FLIGHT; k++)
         if (slot_stream(s, k) != (cudaStream_t)stream) CU(cudaStreamWaitEvent(slot_stream(s, k), s->ev_after, 0));
     return TRAY_OK;
 }
@@ -1256,11 +1281,11 @@ int tray_cuda_hits_to_geometry(tray_scene* s, const tray_hit* hits, uint64_t n, 
 struct tray_group {
     std::vector<tray_scene*> scenes;
     std::vector<int> devices;
-    uchar4* target[2] = { nullptr, nullptr };          // row-major frames on devices[0], one per frame in flight
+    uchar4* target[TRAY_MAX_FRAMES_IN_FLIGHT] = {};    // row-major frames on devices[0], one per frame in flight
     uint64_t target_bytes = 0;
     int in_flight = 1, cur = 0;
-    cudaEvent_t ev_snap[2] = { nullptr, nullptr };     // devices[0]: the frame in target[i] has been copied out (readback)
-    bool snap_pending[2] = { false, false };
+    cudaEvent_t ev_snap[TRAY_MAX_FRAMES_IN_FLIGHT] = {};   // devices[0]: the frame in target[i] has been copied out (readback)
+    bool snap_pending[TRAY_MAX_FRAMES_IN_FLIGHT] = {};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      // devices[0]: frame timing
 };
 
@@ -1271,7 +1296,7 @@ int group_ensure_target(tray_group* g, uint32_t w, uint32_t h) {
     CU(cudaSetDevice(g->devices[0]));
     for (auto* sc : g->scenes) { int rc = tray_cuda_sync(sc); if (rc) return rc; }
     CU(cudaSetDevice(g->devices[0]));
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < TRAY_MAX_FRAMES_IN_FLIGHT; i++) {
         cudaFree(g->target[i]); g->target[i] = nullptr;
         CU(cudaMalloc(&g->target[i], bytes));
         CU(cudaMemset(g->target[i], 0, bytes));
@@ -1288,7 +1313,7 @@ void tray_cuda_group_destroy(tray_group* g) {
     for (auto* sc : g->scenes) tray_cuda_scene_destroy(sc);
     if (!g->devices.empty()) {
         cudaSetDevice(g->devices[0]);
-        for (int i = 0; i < 2; i++) { cudaFree(g->target[i]); if (g->ev_snap[i]) cudaEventDestroy(g->ev_snap[i]); }
+        for (int i = 0; i < TRAY_MAX_FRAMES_IN_FLIGHT; i++) { cudaFree(g->target[i]); if (g->ev_snap[i]) cudaEventDestroy(g->ev_snap[i]); }
         if (g->ev_t0) cudaEventDestroy(g->ev_t0);
         if (g->ev_t1) cudaEventDestroy(g->ev_t1);
     }
@@ -1328,7 +1353,7 @@ int tray_cuda_group_create(const void* nodes, uint64_t n_nodes, const void* tris
             }
         }
         CU(cudaSetDevice(g->devices[0]));
-        for (int i = 0; i < 2; i++) CU(cudaEventCreateWithFlags(&g->ev_snap[i], cudaEventDisableTiming));
+        for (int i = 0; i < TRAY_MAX_FRAMES_IN_FLIGHT; i++) CU(cudaEventCreateWithFlags(&g->ev_snap[i], cudaEventDisableTiming));
         CU(cudaEventCreate(&g->ev_t0)); CU(cudaEventCreate(&g->ev_t1));
         return TRAY_OK;
     };
@@ -1347,7 +1372,7 @@ int tray_cuda_group_scene(tray_group* g, int i, tray_scene** out) {
 }
 
 int tray_cuda_group_set_frames_in_flight(tray_group* g, uint32_t n) {
-    if (!g || n < 1 || n > 2) return fail(TRAY_ERR_ARG, "frames in flight must be 1 or 2");
+    if (!g || n < 1 || n > TRAY_MAX_FRAMES_IN_FLIGHT) return fail(TRAY_ERR_ARG, "frames in flight must be 1 .. %d", TRAY_MAX_FRAMES_IN_FLIGHT);
     for (auto* sc : g->scenes) { int rc = tray_cuda_scene_set_frames_in_flight(sc, n); if (rc) return rc; }
     g->in_flight = (int)n; g->cur = 0;
     return TRAY_OK;
@@ -1358,7 +1383,7 @@ int tray_cuda_group_render(tray_group* g, const tray_view* view, uint32_t w, uin
     int rc = group_ensure_target(g, w, h);
     if (rc) return rc;
     const int n = (int)g->scenes.size();
-    g->cur = g->in_flight > 1 ? (g->cur + 1) % 2 : 0;
+    g->cur = g->in_flight > 1 ? (g->cur + 1) % g->in_flight : 0;
     uchar4* const target = g->target[g->cur];
     for (int i = 0; i < n; i++) {
         tray_scene* sc = g->scenes[i];

@@ -27,7 +27,7 @@ EXPORTS = (
     "tray_cuda_scene_build", "tray_cuda_scene_download", "tray_cuda_frame_readback_begin", "tray_cuda_frame_readback_wait",
     "tray_cuda_scene_build_tlas", "tray_cuda_scene_download_instances",
     "tray_cuda_scene_set_variant", "tray_cuda_shard_items", "tray_cuda_scene_set_frames_in_flight", "tray_cuda_scene_fence",
-    "tray_cuda_scene_after", "tray_cuda_scene_frame_stream", "tray_cuda_frame_signal", "tray_cuda_frame_wait_flag", "tray_cuda_scene_set_geometry_offsets", "tray_cuda_hits_to_geometry",
+    "tray_cuda_scene_after", "tray_cuda_scene_frame_stream", "tray_cuda_frame_signal", "tray_cuda_frame_wait_flag", "tray_cuda_frame_push", "tray_cuda_untile_shards", "tray_cuda_scene_set_geometry_offsets", "tray_cuda_hits_to_geometry",
     "tray_cuda_group_create", "tray_cuda_group_destroy", "tray_cuda_group_size", "tray_cuda_group_scene",
     "tray_cuda_group_set_frames_in_flight", "tray_cuda_group_render", "tray_cuda_group_render_timed",
     "tray_cuda_group_readback_begin", "tray_cuda_group_readback_wait", "tray_cuda_group_frame_ptr", "tray_cuda_group_sync",
@@ -161,6 +161,10 @@ def lib() -> C.CDLL:
         L.tray_cuda_scene_fence.argtypes = [vp, vp]
         L.tray_cuda_scene_after.restype = i32
         L.tray_cuda_scene_after.argtypes = [vp, vp]
+        L.tray_cuda_frame_push.restype = i32
+        L.tray_cuda_frame_push.argtypes = [vp, vp]
+        L.tray_cuda_untile_shards.restype = i32
+        L.tray_cuda_untile_shards.argtypes = [vp, vp, u32, u32, u32, vp]
         L.tray_cuda_frame_signal.restype = i32
         L.tray_cuda_frame_signal.argtypes = [vp, vp, u32]
         L.tray_cuda_frame_wait_flag.restype = i32
@@ -362,6 +366,14 @@ class TrayCudaScene:
     def after(self, cuda_stream: int):
         """Frames enqueued from now on start after the work already enqueued on `cuda_stream`."""
         _check(lib().tray_cuda_scene_after(self._h, cuda_stream))
+
+    def push(self, d_dst: int):
+        """One DMA copy of the last frame's compact RGBA shard to `d_dst` (this or a peer device) on the frame's stream."""
+        _check(lib().tray_cuda_frame_push(self._h, C.c_void_p(d_dst)))
+
+    def untile_shards(self, d_staging: int, width: int, height: int, shards: int, d_frame: int):
+        """All shards' compact RGBA (back to back in `d_staging`) -> the row-major frame, one launch on the frame's stream."""
+        _check(lib().tray_cuda_untile_shards(self._h, C.c_void_p(d_staging), width, height, shards, C.c_void_p(d_frame)))
 
     def signal(self, d_flag: int, value: int):
         """Behind the last frame: write `value` to the 32-bit flag at device address `d_flag` (possibly peer memory) — no kernel."""
