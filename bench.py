@@ -895,7 +895,7 @@ def run_single_process(args):
     g = cuda.TrayCudaGroup.from_packed(packed, devices=list(range(n)))
     steps, warmup = args.steps, max(args.warmup, 3)
     res = {}
-    for nf in (1, 2):
+    for nf in (1, 2, 3):
         g.set_frames_in_flight(nf)
         for _ in range(warmup):
             g.render(view, w, h, 0, flags)
@@ -907,7 +907,7 @@ def run_single_process(args):
         g.sync()
         ms = (time.perf_counter() - t0) * 1e3 / steps
         res[nf] = {"ms_per_step": ms, "value": rays / ms / 1e3, "frame_equals_single_gpu_frame": same}
-    nf = 2 if res[2]["ms_per_step"] < res[1]["ms_per_step"] else 1
+    nf = min(res, key=lambda q: res[q]["ms_per_step"])
     g.set_frames_in_flight(nf)
     per_frame_ms = [g.render(view, w, h, 0, flags, timed=True) for _ in range(12)][2:]
     host_frames = [torch.empty((h, w, 4), dtype=torch.uint8, pin_memory=True).numpy() for _ in range(2)]
@@ -932,7 +932,9 @@ def run_single_process(args):
             "dtype": "f32", "data": "synthetic", "impl_note": "--single-process: one process, tray_cuda_group_* (C ABI), no torchrun / NCCL",
             "config": {"workload": workload_name(w, h, n), "n_tris": packed.n_tris, "n_nodes": packed.n_nodes, "frames_in_flight": nf,
                        "frame_path": "two launches per frame", "parallelism": f"one process, {n} device(s), tiles dealt round-robin, BVH replicated",
-                       "exchange": "kernels store pixels into devices[0]'s frame over peer access; completion by events",
+                       "exchange": ("one peer DMA copy of every device's compact shard into devices[0]'s staging + one untile launch there"
+                                    if os.environ.get("TRAY_CUDA_GROUP_EXCHANGE", "1") != "0" else
+                                    "kernels store pixels into devices[0]'s frame over peer access") + "; completion by events",
                        "timing": "host clock around the asynchronous frames, tray_cuda_group_sync on both sides (CUDA events do not span devices); "
                                  "per_frame_ms_cuda_events = tray_cuda_group_render_timed, one frame at a time"},
             "by_frames_in_flight": res, "per_frame_ms_cuda_events": {"min": min(per_frame_ms), "mean": sum(per_frame_ms) / len(per_frame_ms)},

@@ -425,10 +425,11 @@ int tray_cuda_hits_to_geometry(tray_scene* scene, const tray_hit* hits, uint64_t
 /* ---- one process, several GPUs --------------------------------------------------------------------------------------------
  * The slot `start(..) -> f32` is one call from one host thread (rt_gpu_software.rs:24-32).  A tray_group keeps that shape on
  * a box with several GPUs: the BVH is replicated on `devices[0..n)` (NULL = devices 0..n-1), the frame's 32x8 tiles are dealt
- * round-robin to the devices, and every device's traversal kernels store their finished pixels straight into ONE row-major
- * RGBA8 frame on devices[0] through peer access (cudaDeviceEnablePeerAccess — no IPC handles, no NCCL, no second process).
+ * round-robin to the devices, and every device's pixels reach ONE row-major RGBA8 frame on devices[0] through peer access
+ * (cudaDeviceEnablePeerAccess — no IPC handles, no NCCL, no second process): by one DMA copy of the device's compact shard plus
+ * one untile launch on devices[0], or stored pixel by pixel from the traversal kernels (tray_cuda_group_set_exchange).
  * Frame completion is a set of events: devices[0]'s stream waits for the event each other device records behind its last
- * launch.  Results are bit-identical to the single-GPU frame (tests/test_gpu_group.py).
+ * launch / copy.  Results are bit-identical to the single-GPU frame (tests/test_gpu_group.py).
  *   tray_cuda_group_render          enqueue one frame on every device (shard i of n on devices[i]); asynchronous
  *   tray_cuda_group_render_timed    same, synchronous: *ms_frame = CUDA-event time on devices[0] from before the first launch
  *                                   (no device starts earlier) to the frame being complete
@@ -443,6 +444,11 @@ void tray_cuda_group_destroy(tray_group* group);
 int  tray_cuda_group_size(const tray_group* group);
 int  tray_cuda_group_scene(tray_group* group, int i, tray_scene** out_scene);
 int  tray_cuda_group_set_frames_in_flight(tray_group* group, uint32_t n);
+/* How the shards reach devices[0]'s frame: push != 0 (default) — every device keeps its compact shard and moves it with ONE peer DMA
+ * copy (cudaMemcpyPeerAsync) into a staging array on devices[0], which untiles all shards in one launch; push == 0 — the traversal
+ * kernels store finished pixels straight into the frame over peer access (scattered 4-byte NVLink writes: cheaper on sparse
+ * frames, 13 % dearer on a fully covered 4K frame over 8 GPUs).  Same bytes either way. */
+int  tray_cuda_group_set_exchange(tray_group* group, int push);
 int  tray_cuda_group_render(tray_group* group, const tray_view* view, uint32_t width, uint32_t height,
                             uint32_t frame_count, uint32_t flags);
 int  tray_cuda_group_render_timed(tray_group* group, const tray_view* view, uint32_t width, uint32_t height,

@@ -120,8 +120,9 @@ def _devices():
     return list(range(min(cuda.device_count(), 8)))
 
 
+@pytest.mark.parametrize("push", [True, False])
 @pytest.mark.parametrize("in_flight", [1, 2, 3])
-def test_group_frame_equals_single_gpu_frame(in_flight):
+def test_group_frame_equals_single_gpu_frame(in_flight, push):
     """One process, all the box's GPUs: tiles dealt round-robin, pixels stored into ONE frame on devices[0] over peer access,
     completion by events.  The frame equals the single-scene frame byte for byte; per-device shards hold the oracle's hits."""
     m = host.Mesh.generate("kitchen", 1, 1.0)
@@ -140,6 +141,7 @@ def test_group_frame_equals_single_gpu_frame(in_flight):
     g = cuda.TrayCudaGroup.from_packed(p, devices=devs)
     try:
         g.set_frames_in_flight(in_flight)
+        g.set_exchange(push)            # DMA push of the compact shards + untile on devices[0], or pixel stores into the frame
         for rep in range(3):
             g.render(view, w, h, 0, FLAGS)
             assert (g.frame() == want0).all(), rep

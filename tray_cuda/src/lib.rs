@@ -128,6 +128,7 @@ extern "C" {
     pub fn tray_cuda_group_size(group: *const TrayGroup) -> c_int;
     pub fn tray_cuda_group_scene(group: *mut TrayGroup, i: c_int, out_scene: *mut *mut TrayScene) -> c_int;
     pub fn tray_cuda_group_set_frames_in_flight(group: *mut TrayGroup, n: u32) -> c_int;
+    pub fn tray_cuda_group_set_exchange(group: *mut TrayGroup, push: c_int) -> c_int;
     pub fn tray_cuda_group_render(group: *mut TrayGroup, view: *const TrayView, width: u32, height: u32, frame_count: u32,
         flags: u32) -> c_int;
     pub fn tray_cuda_group_render_timed(group: *mut TrayGroup, view: *const TrayView, width: u32, height: u32, frame_count: u32,

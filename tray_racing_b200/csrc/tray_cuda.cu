@@ -1287,6 +1287,13 @@ struct tray_group {
     cudaEvent_t ev_snap[TRAY_MAX_FRAMES_IN_FLIGHT] = {};   // devices[0]: the frame in target[i] has been copied out (readback)
     bool snap_pending[TRAY_MAX_FRAMES_IN_FLIGHT] = {};
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr;      // devices[0]: frame timing
+    // exchange 1 ("push", default): every device keeps its compact shard and moves it with one peer DMA copy into staging[] on
+    // devices[0], which untiles all shards in one launch; exchange 0: the kernels store pixels straight into the frame
+    int exchange = 1;
+    uchar4* staging[TRAY_MAX_FRAMES_IN_FLIGHT] = {};
+    uint64_t staging_bytes = 0;
+    cudaEvent_t ev_staged[TRAY_MAX_FRAMES_IN_FLIGHT] = {};  // devices[0]: staging[i] has been untiled (it may be overwritten)
+    bool staged_pending[TRAY_MAX_FRAMES_IN_FLIGHT] = {};
 };
 
 namespace {
@@ -1304,6 +1311,19 @@ int group_ensure_target(tray_group* g, uint32_t w, uint32_t h) {
     g->target_bytes = bytes;
     return TRAY_OK;
 }
+int group_ensure_staging(tray_group* g, uint32_t w, uint32_t h) {
+    const uint64_t bytes = (uint64_t)g->scenes.size() * local_items(w, h, 0, (uint32_t)g->scenes.size()) * 4;
+    if (bytes <= g->staging_bytes) return TRAY_OK;
+    for (auto* sc : g->scenes) { int rc = tray_cuda_sync(sc); if (rc) return rc; }
+    CU(cudaSetDevice(g->devices[0]));
+    for (int i = 0; i < TRAY_MAX_FRAMES_IN_FLIGHT; i++) {
+        cudaFree(g->staging[i]); g->staging[i] = nullptr;
+        CU(cudaMalloc(&g->staging[i], bytes));
+        g->staged_pending[i] = false;
+    }
+    g->staging_bytes = bytes;
+    return TRAY_OK;
+}
 }  // namespace
 
 extern "C" {
@@ -1313,7 +1333,11 @@ void tray_cuda_group_destroy(tray_group* g) {
     for (auto* sc : g->scenes) tray_cuda_scene_destroy(sc);
     if (!g->devices.empty()) {
         cudaSetDevice(g->devices[0]);
-        for (int i = 0; i < TRAY_MAX_FRAMES_IN_FLIGHT; i++) { cudaFree(g->target[i]); if (g->ev_snap[i]) cudaEventDestroy(g->ev_snap[i]); }
+        for (int i = 0; i < TRAY_MAX_FRAMES_IN_FLIGHT; i++) {
+            cudaFree(g->target[i]); cudaFree(g->staging[i]);
+            if (g->ev_snap[i]) cudaEventDestroy(g->ev_snap[i]);
+            if (g->ev_staged[i]) cudaEventDestroy(g->ev_staged[i]);
+        }
         if (g->ev_t0) cudaEventDestroy(g->ev_t0);
         if (g->ev_t1) cudaEventDestroy(g->ev_t1);
     }
@@ -1353,7 +1377,11 @@ int tray_cuda_group_create(const void* nodes, uint64_t n_nodes, const void* tris
             }
         }
         CU(cudaSetDevice(g->devices[0]));
-        for (int i = 0; i < TRAY_MAX_FRAMES_IN_FLIGHT; i++) CU(cudaEventCreateWithFlags(&g->ev_snap[i], cudaEventDisableTiming));
+        for (int i = 0; i < TRAY_MAX_FRAMES_IN_FLIGHT; i++) {
+            CU(cudaEventCreateWithFlags(&g->ev_snap[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&g->ev_staged[i], cudaEventDisableTiming));
+        }
+        g->exchange = env_int("TRAY_CUDA_GROUP_EXCHANGE", 1) ? 1 : 0;
         CU(cudaEventCreate(&g->ev_t0)); CU(cudaEventCreate(&g->ev_t1));
         return TRAY_OK;
     };
@@ -1378,30 +1406,59 @@ int tray_cuda_group_set_frames_in_flight(tray_group* g, uint32_t n) {
     return TRAY_OK;
 }
 
+int tray_cuda_group_set_exchange(tray_group* g, int push) {
+    if (!g) return fail(TRAY_ERR_ARG, "NULL group");
+    int rc = tray_cuda_group_sync(g); if (rc) return rc;
+    g->exchange = push ? 1 : 0;
+    return TRAY_OK;
+}
+
 int tray_cuda_group_render(tray_group* g, const tray_view* view, uint32_t w, uint32_t h, uint32_t frame_count, uint32_t flags) {
     if (!g || !view) return fail(TRAY_ERR_ARG, "NULL argument");
     int rc = group_ensure_target(g, w, h);
     if (rc) return rc;
     const int n = (int)g->scenes.size();
+    const bool push = g->exchange == 1 && n > 1;
+    if (push) { rc = group_ensure_staging(g, w, h); if (rc) return rc; }
     g->cur = g->in_flight > 1 ? (g->cur + 1) % g->in_flight : 0;
     uchar4* const target = g->target[g->cur];
+    const uint64_t items = local_items(w, h, 0, (uint32_t)n);
+    const bool snap = g->snap_pending[g->cur];             // the frame this target held last is still being copied out
     for (int i = 0; i < n; i++) {
         tray_scene* sc = g->scenes[i];
         const int k = sc->n_slots > 1 ? (sc->cur + 1) % sc->n_slots : 0;          // the slot this frame will take on device i
-        if (i > 0 && g->snap_pending[g->cur]) {         // the previous frame in this target must have been copied out first
+        if (!push && i > 0 && snap) {                      // the previous frame in this target must have been copied out first
             CU(cudaSetDevice(sc->device));
             CU(cudaStreamWaitEvent(slot_stream(sc, k), g->ev_snap[g->cur], 0));
         }
-        sc->frame_target = target;
+        sc->frame_target = push ? nullptr : target;
         rc = tray_cuda_render(sc, view, w, h, frame_count, flags | TRAY_RENDER_RGBA, (uint32_t)i, (uint32_t)n, nullptr, nullptr);
         if (rc) return rc;
-        if (i > 0) CU(cudaEventRecord(sc->slot[sc->cur].done, slot_stream(sc, sc->cur)));
+        cudaStream_t st = slot_stream(sc, sc->cur);
+        if (push) {
+            // one DMA copy of the compact shard into devices[0]'s staging (behind the untile of the frame that used it last)
+            if (g->staged_pending[g->cur]) CU(cudaStreamWaitEvent(st, g->ev_staged[g->cur], 0));
+            const FrameSlot& f = sc->slot[sc->cur];
+            if (f.f_items)
+                CU(cudaMemcpyPeerAsync(g->staging[g->cur] + (uint64_t)i * items, g->devices[0], f.d_rgba, sc->device, (size_t)f.f_items * sizeof(uchar4), st));
+        }
+        if (i > 0) CU(cudaEventRecord(sc->slot[sc->cur].done, st));
     }
     g->snap_pending[g->cur] = false;
-    // frame complete on devices[0]: its stream waits for every other device's last launch
+    // frame complete on devices[0]: its stream waits for every other device's last launch / copy
     tray_scene* s0 = g->scenes[0];
+    cudaStream_t st0 = slot_stream(s0, s0->cur);
     CU(cudaSetDevice(s0->device));
-    for (int i = 1; i < n; i++) CU(cudaStreamWaitEvent(slot_stream(s0, s0->cur), g->scenes[i]->slot[g->scenes[i]->cur].done, 0));
+    for (int i = 1; i < n; i++) CU(cudaStreamWaitEvent(st0, g->scenes[i]->slot[g->scenes[i]->cur].done, 0));
+    if (push) {
+        if (snap) CU(cudaStreamWaitEvent(st0, g->ev_snap[g->cur], 0));
+        tray::untile_shards_kernel<<<dim3((w + 255) / 256, h), 256, 0, st0>>>(g->staging[g->cur], w, h, (w + 31) / 32, (uint32_t)n, items, target);
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(g->ev_staged[g->cur], st0));
+        g->staged_pending[g->cur] = true;
+        FrameSlot& f0 = s0->slot[s0->cur];               // the readback of devices[0]'s scene reads the assembled frame
+        f0.f_target = target; f0.f_has_rgba = false;
+    }
     return TRAY_OK;
 }
 

@@ -29,7 +29,7 @@ EXPORTS = (
     "tray_cuda_scene_set_variant", "tray_cuda_shard_items", "tray_cuda_scene_set_frames_in_flight", "tray_cuda_scene_fence",
     "tray_cuda_scene_after", "tray_cuda_scene_frame_stream", "tray_cuda_frame_signal", "tray_cuda_frame_wait_flag", "tray_cuda_frame_push", "tray_cuda_untile_shards", "tray_cuda_scene_set_geometry_offsets", "tray_cuda_hits_to_geometry",
     "tray_cuda_group_create", "tray_cuda_group_destroy", "tray_cuda_group_size", "tray_cuda_group_scene",
-    "tray_cuda_group_set_frames_in_flight", "tray_cuda_group_render", "tray_cuda_group_render_timed",
+    "tray_cuda_group_set_frames_in_flight", "tray_cuda_group_set_exchange", "tray_cuda_group_render", "tray_cuda_group_render_timed",
     "tray_cuda_group_readback_begin", "tray_cuda_group_readback_wait", "tray_cuda_group_frame_ptr", "tray_cuda_group_sync",
     "tray_cuda_start_multi",
 )
@@ -185,6 +185,8 @@ def lib() -> C.CDLL:
         L.tray_cuda_group_scene.argtypes = [vp, i32, C.POINTER(vp)]
         L.tray_cuda_group_set_frames_in_flight.restype = i32
         L.tray_cuda_group_set_frames_in_flight.argtypes = [vp, u32]
+        L.tray_cuda_group_set_exchange.restype = i32
+        L.tray_cuda_group_set_exchange.argtypes = [vp, i32]
         L.tray_cuda_group_render.restype = i32
         L.tray_cuda_group_render.argtypes = [vp, C.POINTER(TrayView), u32, u32, u32, u32]
         L.tray_cuda_group_render_timed.restype = i32
@@ -524,6 +526,10 @@ class TrayCudaGroup:
 
     def set_frames_in_flight(self, n: int):
         _check(lib().tray_cuda_group_set_frames_in_flight(self._h, int(n)))
+
+    def set_exchange(self, push: bool):
+        """push (default): one peer DMA copy per shard + one untile launch on devices[0]; else the kernels store pixels into the frame."""
+        _check(lib().tray_cuda_group_set_exchange(self._h, int(push)))
 
     def render(self, view: TrayView, width: int, height: int, frame_count: int = 0, flags: int = RENDER_BOUNCE | RENDER_RGBA, timed: bool = False):
         self.frame_size = (width, height)
