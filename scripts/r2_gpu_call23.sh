@@ -1,0 +1,11 @@
+set -x
+cd "$GRAFT_REPO_ROOT"
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -6 > gpurun_out/r2_t23_pytest.log; cat gpurun_out/r2_t23_pytest.log
+for scene in hairball kitchen; do
+  for lib in libtray_cuda_r2base.so libtray_cuda.so libtray_cuda_t7.so libtray_cuda_r2base.so libtray_cuda.so; do
+    TRAY_CUDA_LIB=$PWD/tray_racing_b200/$lib timeout 300 python scripts/r2_perf.py $scene --frames 40 2>&1 | grep -v "^+" | grep -E "primary|x2 in flight"
+  done
+done 2>&1 | tee gpurun_out/r2_tnode_ab.log
+for lib in libtray_cuda_r2base.so libtray_cuda.so; do
+  TRAY_CUDA_LIB=$PWD/tray_racing_b200/$lib timeout 300 python scripts/r2_perf.py sanmiguel --w 3840 --h 2160 --frames 20 2>&1 | grep -v "^+" | grep -E "primary|x2 in flight"
+done 2>&1 | tee -a gpurun_out/r2_tnode_ab.log

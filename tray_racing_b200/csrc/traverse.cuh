@@ -45,6 +45,10 @@ constexpr int STACK_SMEM = TRAY_STACK_SMEM;      // entries per thread in shared
 constexpr int STACK_SPILL = 48 - STACK_SMEM;     // further entries per thread in local memory (total 48 > obvhs' 32, cwbvh.rs:88)
 constexpr unsigned FULL = 0xffffffffu;
 constexpr uint32_t INVALID = 0xffffffffu;
+// rows are LUT_ROW = 260 bytes apart: the same hit byte under different octants then falls into different banks (lanes of an
+// incoherent warp mostly hold one-bit hit bytes; at a 256-byte pitch they would all collide in banks 0, 1, 2, 4, ...)
+constexpr uint32_t LUT_ROW = 260u, LUT_BYTES = 8u * LUT_ROW;
+constexpr uint32_t WIDE_BIT = 0x40000000u;       // trace_kernel: bit 30 of a lane's ray index = RayConst::wide
 constexpr float F32_MAX_ = 3.402823466e+38f;
 constexpr float F32_EPS_ = 1.1920929e-7f;     // sampling.hlsl:3
 constexpr float BOX_EPS_ = 0.0001f;           // query.hlsl:274
@@ -152,6 +156,7 @@ __device__ __forceinline__ long long clk_after(uint32_t dep) { long long c; asm 
 struct RayConst {
     float ox, oy, oz, dx, dy, dz, ix, iy, iz, tmin;
     uint32_t oct_inv4;
+    uint32_t lut_off;   // shared-memory address of this ray's row of the child-order table: s_lut + (oct_inv & 7) * LUT_ROW
     bool wide;      // |1/d| >= 2^64 on some axis: 2^23 * adj_inv could overflow, use the unfused node test
     // MODE 1 (semantic variants, tray_cuda_scene_set_variant) only — dead registers in every other kernel:
     float tdx, tdy, tdz;    // the direction the TRIANGLE test sees (the caller's, when the zero patch feeds the box test only)
@@ -159,7 +164,7 @@ struct RayConst {
 };
 
 __device__ __forceinline__ void prepare_ray(RayConst& r, float ox, float oy, float oz, float dx, float dy, float dz, float tmin,
-                                            uint32_t variant = 0u) {
+                                            uint32_t variant = 0u, uint32_t lut_base = 0u) {
     r.ox = ox; r.oy = oy; r.oz = oz; r.tmin = tmin;
     r.dx = dx == 0.0f ? F32_EPS_ : dx;           // query.hlsl:334
     r.dy = dy == 0.0f ? F32_EPS_ : dy;
@@ -170,6 +175,7 @@ __device__ __forceinline__ void prepare_ray(RayConst& r, float ox, float oy, flo
     r.ix = __fdiv_rn(1.0f, r.dx); r.iy = __fdiv_rn(1.0f, r.dy); r.iz = __fdiv_rn(1.0f, r.dz);   // Ray::inv_direction
     r.oct_inv4 = (r.dx < 0.0f ? 0u : 0x04040404u) | (r.dy < 0.0f ? 0u : 0x02020202u) |
                  (r.dz < 0.0f ? 0u : 0x01010101u);                                              // query.hlsl:314-326
+    r.lut_off = lut_base + (r.oct_inv4 & 7u) * LUT_ROW;
     r.wide = !(fmaxf(fmaxf(fabsf(r.ix), fabsf(r.iy)), fabsf(r.iz)) < 1.8446744e19f);
 }
 
@@ -317,6 +323,122 @@ __device__ __forceinline__ uint32_t node_test_fast(const RayConst& r, float tmax
     uint32_t mask = 0;
     node_half_fast<0>(mask, r, tmax, c, n1.z, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, k4b);
     node_half_fast<1>(mask, r, tmax, c, n1.w, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, k4b);
+    return mask;
+}
+
+// ---- node test in slot space ------------------------------------------------------------------------
+// The lane kernel keeps the top byte of the hit mask / node group word in SLOT space: an inner child (bit_index = 24 + slot,
+// query.hlsl:251-262) sets bit 24 + slot, WITHOUT the octant XOR.  That XOR exists so that firstbithigh (query.hlsl:358) finds
+// the hit child nearest along the ray, and `slot = bit ^ oct_inv` (:370) undoes it; here the pair becomes ONE lookup when the
+// next child is chosen: child_order[oct_inv][hit byte] = the hit slot whose (slot ^ oct_inv) is largest (2 KB table in shared
+// memory, built at kernel start).  Same child, same order, same `rel` (query.hlsl:371 counts imask bits below `slot`: slot space
+// already).  The node test drops is_inner4 / inner_mask4 / the XOR (query.hlsl:251-257): child_bits << bit_index is the whole
+// contribution of a hit child (:291-298), for leaves (bit_index = triangle offset) and inner children alike.
+// (A fully pre-decoded 128-byte node, one 32-bit word per child, was built and measured — profiles/experiments/r2_tnode_*: node
+// test 215 -> 172 instructions, but 60 % more L1 traffic; the L1 serves scattered 16-byte accesses at ~32 B/clk/SM, it went from
+// 42 % to 75 % busy and the incoherent bounce rays of C3 got 5 % slower.  The node stays the caller's 80 bytes.)
+
+// child_order[oi][t]: of the slots set in the hit byte t, the one whose (slot ^ oi) is largest (t = 0: unused)
+__device__ __forceinline__ void child_order_fill(uint8_t* lut, unsigned tid, unsigned n_threads) {
+    for (unsigned k = tid; k < 2048u; k += n_threads) {
+        const unsigned oi = k >> 8, t = k & 255u;
+        unsigned best = 0, best_key = 0;
+        for (unsigned j = 0; j < 8u; j++)
+            if (((t >> j) & 1u) && ((j ^ oi) >= best_key)) { best_key = j ^ oi; best = j; }
+        lut[oi * LUT_ROW + t] = (uint8_t)best;
+    }
+}
+
+// exact (unfused) form: CwBvhNode::intersect_ray, twin query.hlsl:213-303 (wide rays, huge node scales, MODE 1)
+template <int J>
+__device__ __forceinline__ uint32_t child_test_s(uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz,
+                                                 float ax, float ay, float az, float bx, float by, float bz, float tmax,
+                                                 uint32_t child_bits4, uint32_t meta4, uint32_t k4b, float box_tmin) {
+    const float tnx = add(mul(byte_f32<J>(nx, k4b), ax), bx), tfx = add(mul(byte_f32<J>(fx, k4b), ax), bx);
+    const float tny = add(mul(byte_f32<J>(ny, k4b), ay), by), tfy = add(mul(byte_f32<J>(fy, k4b), ay), by);
+    const float tnz = add(mul(byte_f32<J>(nz, k4b), az), bz), tfz = add(mul(byte_f32<J>(fz, k4b), az), bz);
+    const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), box_tmin);      // query.hlsl:288
+    const float tfar = fminf(fminf(fminf(tfx, tfy), tfz), tmax);          // query.hlsl:289
+    const uint32_t contrib = byte_u32<J>(child_bits4) << ((meta4 >> (8 * J)) & 31u);       // query.hlsl:291-298, slot space
+    return tmin <= tfar ? contrib : 0u;
+}
+__device__ __forceinline__ uint32_t node_test_s(const RayConst& r, float tmax, const uint4& n0, const uint4& n1, const uint4& n2,
+                                                const uint4& n3, const uint4& n4, uint32_t k4b, float box_tmin = BOX_EPS_, bool divide = false) {
+    const uint32_t e = n0.w;
+    const float sx_ = __uint_as_float((e & 0xffu) << 23), sy_ = __uint_as_float(((e >> 8) & 0xffu) << 23), sz_ = __uint_as_float(((e >> 16) & 0xffu) << 23);
+    const float px_ = sub(__uint_as_float(n0.x), r.ox), py_ = sub(__uint_as_float(n0.y), r.oy), pz_ = sub(__uint_as_float(n0.z), r.oz);
+    const float ax = divide ? __fdiv_rn(sx_, r.dx) : mul(sx_, r.ix);
+    const float ay = divide ? __fdiv_rn(sy_, r.dy) : mul(sy_, r.iy);
+    const float az = divide ? __fdiv_rn(sz_, r.dz) : mul(sz_, r.iz);
+    const float bx = divide ? __fdiv_rn(px_, r.dx) : mul(px_, r.ix);
+    const float by = divide ? __fdiv_rn(py_, r.dy) : mul(py_, r.iy);
+    const float bz = divide ? __fdiv_rn(pz_, r.dz) : mul(pz_, r.iz);
+    const bool sx = r.dx < 0.0f, sy = r.dy < 0.0f, sz = r.dz < 0.0f;
+    uint32_t mask = 0;
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const uint32_t meta4 = i == 0 ? n1.z : n1.w;
+        const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+        const uint32_t lox = i == 0 ? n2.x : n2.y, hix = i == 0 ? n2.z : n2.w;
+        const uint32_t loy = i == 0 ? n3.x : n3.y, hiy = i == 0 ? n3.z : n3.w;
+        const uint32_t loz = i == 0 ? n4.x : n4.y, hiz = i == 0 ? n4.z : n4.w;
+        const uint32_t nx = sx ? hix : lox, fx = sx ? lox : hix;                   // query.hlsl:266-273
+        const uint32_t ny = sy ? hiy : loy, fy = sy ? loy : hiy;
+        const uint32_t nz = sz ? hiz : loz, fz = sz ? loz : hiz;
+        mask |= child_test_s<0>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, meta4, k4b, box_tmin);
+        mask |= child_test_s<1>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, meta4, k4b, box_tmin);
+        mask |= child_test_s<2>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, meta4, k4b, box_tmin);
+        mask |= child_test_s<3>(nx, fx, ny, fy, nz, fz, ax, ay, az, bx, by, bz, tmax, child_bits4, meta4, k4b, box_tmin);
+    }
+    return mask;
+}
+
+// fused form (the arithmetic of child_test_fast, bit-identical to node_test_s)
+template <int J, bool YI2F>
+__device__ __forceinline__ void child_test_fast_s(uint32_t& mask, uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz,
+                                                  const NodeConsts& c, float tmax, uint32_t child_bits4, uint32_t meta4, uint32_t k4b) {
+    float tnx, tfx, tny, tfy, tnz, tfz;
+    unpack2f(fadd2(ffma2(pack2(byte_biased<J>(nx, k4b), byte_biased<J>(fx, k4b)), c.AX, c.CX), c.BX), tnx, tfx);
+    if (YI2F) unpack2f(fadd2(ffma2(pack2f(byte_i2f<J>(ny), byte_i2f<J>(fy)), c.AY, c.Z0), c.BY), tny, tfy);
+    else unpack2f(fadd2(ffma2(pack2(byte_biased<J>(ny, k4b), byte_biased<J>(fy, k4b)), c.AY, c.CY), c.BY), tny, tfy);
+    if (I2F_Z) unpack2f(fadd2(ffma2(pack2f(byte_i2f<J>(nz), byte_i2f<J>(fz)), c.AZ, c.Z0), c.BZ), tnz, tfz);
+    else unpack2f(fadd2(ffma2(pack2(byte_biased<J>(nz, k4b), byte_biased<J>(fz, k4b)), c.AZ, c.CZ), c.BZ), tnz, tfz);
+    const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), BOX_EPS_);
+    const float tfar = fminf(fminf(fminf(tfx, tfy), tfz), tmax);
+    const uint32_t contrib = byte_u32<J>(child_bits4) << ((meta4 >> (8 * J)) & 31u);
+    asm("{.reg .pred p; setp.le.f32 p, %1, %2; @p or.b32 %0, %0, %3;}" : "+r"(mask) : "f"(tmin), "f"(tfar), "r"(contrib));
+}
+template <int I>
+__device__ __forceinline__ void node_half_fast_s(uint32_t& mask, const RayConst& r, float tmax, const NodeConsts& c, uint32_t meta4,
+                                                 uint32_t lox, uint32_t hix, uint32_t loy, uint32_t hiy, uint32_t loz, uint32_t hiz, uint32_t k4b) {
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const bool sx = r.dx < 0.0f, sy = r.dy < 0.0f, sz = r.dz < 0.0f;
+    const uint32_t nx = sx ? hix : lox, fx = sx ? lox : hix;                          // query.hlsl:266-273
+    const uint32_t ny = sy ? hiy : loy, fy = sy ? loy : hiy;
+    const uint32_t nz = sz ? hiz : loz, fz = sz ? loz : hiz;
+    constexpr bool YI = I2F_Y == 2 || (I2F_Y == 1 && I == 0);
+    child_test_fast_s<0, YI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b);
+    child_test_fast_s<1, YI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b);
+    child_test_fast_s<2, YI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b);
+    child_test_fast_s<3, YI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b);
+}
+__device__ __forceinline__ uint32_t node_test_fast_s(const RayConst& r, float tmax, const uint4& n0, const uint4& n1, const uint4& n2,
+                                                     const uint4& n3, const uint4& n4, uint32_t k4b, float zero) {
+    const uint32_t e = n0.w;
+    const float ax = mul(__uint_as_float((e & 0xffu) << 23), r.ix);
+    const float ay = mul(__uint_as_float(((e >> 8) & 0xffu) << 23), r.iy);
+    const float az = mul(__uint_as_float(((e >> 16) & 0xffu) << 23), r.iz);
+    const float bx = mul(sub(__uint_as_float(n0.x), r.ox), r.ix);
+    const float by = mul(sub(__uint_as_float(n0.y), r.oy), r.iy);
+    const float bz = mul(sub(__uint_as_float(n0.z), r.oz), r.iz);
+    const float cx = mul(ax, -8388608.0f), cy = mul(ay, -8388608.0f), cz = mul(az, -8388608.0f);   // -2^23 * A, exact
+    NodeConsts c;
+    c.AX = pack2f(ax, ax); c.AY = pack2f(ay, ay); c.AZ = pack2f(az, az);
+    c.CX = pack2f(cx, cx); c.CY = pack2f(cy, cy); c.CZ = pack2f(cz, cz);
+    c.BX = pack2f(bx, bx); c.BY = pack2f(by, by); c.BZ = pack2f(bz, bz); c.Z0 = pack2f(zero, zero);
+    uint32_t mask = 0;
+    node_half_fast_s<0>(mask, r, tmax, c, n1.z, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, k4b);
+    node_half_fast_s<1>(mask, r, tmax, c, n1.w, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, k4b);
     return mask;
 }
 
@@ -622,9 +744,11 @@ __device__ __forceinline__ bool poll_hit(const tray_hit* src, float2& ph) {     
 template <bool TLAS, bool COUNT, int TRI_STRIDE, bool ANYHIT = false, bool FRAME = false, int MODE = 0>
 __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams P) {
     __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
+    __shared__ uint8_t s_lut[LUT_BYTES];          // child_order[oct_inv][hit byte] (see node_test_s)
     uint2 spill[STACK_SPILL];
+    child_order_fill(s_lut, threadIdx.x, BLOCK_THREADS);
+    __syncthreads();
     const unsigned lane = threadIdx.x & 31u;
-    uint2* const my_stack = s_stack + threadIdx.x;
     const uint32_t k4b = P.k4b;
     const uint32_t n_work = P.n_work_dev ? *P.n_work_dev : P.n_work;
 
@@ -632,32 +756,37 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
     float best_t = 0.f;
     uint32_t best_prim = INVALID;
     uint32_t cur_x = 0, cur_y = 0, tri_x = 0, tri_y = 0;
-    int sp = 0;
+    // the stack pointer IS the byte offset of the lane's next free entry in s_stack ([entry][thread]): depth * SP_STEP + thread * 8
+    // (one register instead of a depth and a per-thread base address)
+    constexpr uint32_t SP_STEP = BLOCK_THREADS * 8u, SP_SMEM_END = STACK_SMEM * SP_STEP, SP_END = (STACK_SMEM + STACK_SPILL) * SP_STEP;
+    uint32_t sp = threadIdx.x * 8u;
+#define TRAY_STK(off) (*reinterpret_cast<uint2*>(reinterpret_cast<char*>(s_stack) + (off)))
     uint32_t tlas_sp = INVALID, bvh_off = 0;
     uint32_t ray_idx = 0;
     bool exhausted = false;                      // warp-uniform
     unsigned long long c_rays = 0, c_nodes = 0, c_tris = 0, c_insts = 0, c_hits = 0;
     unsigned long long b_rays = 0, b_nodes = 0, b_tris = 0, b_insts = 0, b_hits = 0;    // FRAME && COUNT: the bounce rays' share
-    // FRAME: bit 31 of ray_idx marks a bounce ray (items are < 2^31, checked by the host)
+    // FRAME: bit 31 of ray_idx marks a bounce ray; bit 30 (WIDE_BIT) a ray that must take the unfused node test (RayConst::wide) —
+    // the host keeps batches and frames below 2^30 rays per launch, so the index itself fits in 30 bits
 #define TRAY_CNT(name) do { if (COUNT) { if (FRAME && (ray_idx >> 31)) b_##name++; else c_##name++; } } while (0)
     uint32_t cur_unit = INVALID, cand_unit = INVALID, H = 0, sleeps = 0;   // FRAME, warp-uniform: 32-pixel group being fed from, claimed group, its pixels still to shoot
     bool units_done = false;
 
     auto push = [&](uint32_t x, uint32_t y) {
-        if (sp < STACK_SMEM) my_stack[sp * BLOCK_THREADS] = make_uint2(x, y);
-        else if (sp < STACK_SMEM + STACK_SPILL) spill[sp - STACK_SMEM] = make_uint2(x, y);
+        if (sp < SP_SMEM_END) TRAY_STK(sp) = make_uint2(x, y);
+        else if (sp < SP_END) spill[sp / SP_STEP - STACK_SMEM] = make_uint2(x, y);
         else { atomicOr(P.overflow, 1u); return; }
-        sp++;
+        sp += SP_STEP;
     };
     // called when the lane has neither triangles nor nodes left in hand: pop the stack, or retire the ray
     // (query.hlsl:417-427; tlas:480-486; the popped-triangle-group case is query.hlsl:389-393)
     auto pop_or_retire = [&]() {
-        if (sp == 0) {
+        if (sp < SP_STEP) {
             tray_hit h;
             h.t = best_prim != INVALID ? best_t : __int_as_float(0x7f800000);   // RayHit::none()
             h.prim = best_prim;
             if (FRAME) {
-                const uint32_t it = ray_idx & 0x7fffffffu;
+                const uint32_t it = ray_idx & 0x3fffffffu;
                 if (COUNT && best_prim != INVALID) TRAY_CNT(hits);
                 if (!(ray_idx >> 31))      // ONE 64-bit scalar store (single-copy atomic, unlike a .v2 pair): the record itself tells a reader that it is there
                     publish_hit(P.hits_out + it, h);
@@ -672,7 +801,8 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                 cur_x = 0; cur_y = 0;
                 return;
             }
-            const uint32_t item = P.ray_item ? __ldg(P.ray_item + ray_idx) : ray_idx;
+            const uint32_t ri = ray_idx & 0x3fffffffu;
+            const uint32_t item = P.ray_item ? __ldg(P.ray_item + ri) : ri;
             P.hits_out[item] = h;
             if (P.rgba_out) {
                 float col;
@@ -685,9 +815,9 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
             if (COUNT && best_prim != INVALID) c_hits++;
             cur_x = 0; cur_y = 0;                                                                    // IDLE
         } else {
-            if (TLAS && (uint32_t)sp == tlas_sp) { tlas_sp = INVALID; bvh_off = P.tlas_start; }
-            sp--;
-            const uint2 e = sp < STACK_SMEM ? my_stack[sp * BLOCK_THREADS] : spill[sp - STACK_SMEM];
+            if (TLAS && sp == tlas_sp) { tlas_sp = INVALID; bvh_off = P.tlas_start; }
+            sp -= SP_STEP;
+            const uint2 e = sp < SP_SMEM_END ? TRAY_STK(sp) : spill[sp / SP_STEP - STACK_SMEM];
             if (e.y & 0xff000000u) { cur_x = e.x; cur_y = e.y; }
             else { tri_x = e.x; tri_y = e.y; cur_x = 0; cur_y = 0; }
         }
@@ -722,9 +852,10 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                     if (base < n_work && ray_idx < n_work) {
                         const float4* rp = reinterpret_cast<const float4*>(P.rays + ray_idx);
                         const float4 a = __ldg(rp), b = __ldg(rp + 1);
-                        prepare_ray(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w, MODE == 1 ? P.variant : 0u);
+                        prepare_ray(r, a.x, a.y, a.z, b.x, b.y, b.z, a.w, MODE == 1 ? P.variant : 0u, (uint32_t)__cvta_generic_to_shared(s_lut));
+                        if (r.wide) ray_idx |= WIDE_BIT;
                         best_t = b.w; best_prim = INVALID;
-                        cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp = 0;   // root group, query.hlsl:343
+                        cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp &= SP_STEP - 1u;   // root group, query.hlsl:343
                         tlas_sp = INVALID; bvh_off = TLAS ? P.tlas_start : 0u;
                         if (COUNT) c_rays++;
                     }
@@ -747,11 +878,11 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                             const float4* gp = reinterpret_cast<const float4*>(P.gen_rays + item);     // written by this warp at the claim
                             const float4 ga = __ldcg(gp), gb = __ldcg(gp + 1);
                             const float ox = ga.x, oy = ga.y, oz = ga.z, dx = gb.x, dy = gb.y, dz = gb.z;
-                            prepare_ray(r, ox, oy, oz, dx, dy, dz, 0.0f);                       // Ray::new(o, dir, 0.0, f32::MAX)
+                            prepare_ray(r, ox, oy, oz, dx, dy, dz, 0.0f, 0u, (uint32_t)__cvta_generic_to_shared(s_lut));   // Ray::new(o, dir, 0.0, f32::MAX)
                             best_t = F32_MAX_; best_prim = INVALID;
-                            cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp = 0;
+                            cur_x = 0; cur_y = 0x80000000u; tri_x = 0; tri_y = 0; sp &= SP_STEP - 1u;
                             tlas_sp = INVALID; bvh_off = TLAS ? P.tlas_start : 0u;
-                            ray_idx = item | 0x80000000u;
+                            ray_idx = item | 0x80000000u | (r.wide ? WIDE_BIT : 0u);
                             if (COUNT) b_rays++;
                         }
                         int n_take = min(__popc(idle), __popc(H));
@@ -837,36 +968,25 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
         if (!tri_phase) {
             if (want_node) {
                 const uint32_t hits_imask = cur_y;
-                const uint32_t off = 31u - (uint32_t)__clz((int)hits_imask);                 // query.hlsl:358
-                cur_y &= ~(1u << off);                                                         // :362
+                uint32_t slot;                                                                 // query.hlsl:358 + :370 in one lookup (see node_test_s)
+                asm("ld.shared.u8 %0, [%1];" : "=r"(slot) : "r"(r.lut_off + (hits_imask >> 24)));
+                cur_y = hits_imask ^ (0x01000000u << slot);                                    // :362
                 if (cur_y & 0xff000000u) push(cur_x, cur_y);                                   // :365-368
-                const uint32_t slot = (off - 24u) ^ (r.oct_inv4 & 0xffu);                      // :370
-                const uint32_t rel = (uint32_t)__popc(hits_imask & ~(0xffffffffu << slot));    // :371
+                const uint32_t rel = (uint32_t)__popc(hits_imask & ((1u << slot) - 1u));       // :371 (slot < 8: imask bits only)
                 const uint4* np = P.nodes + (size_t)(bvh_off + cur_x + rel) * 5u;              // :373, tlas:383
                 SC(const long long sc_a = clk_after(rel); sc_acc[1] += sc_a - sc_voted;)
                 const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
                 SC(const long long sc_b = clk_after(n0.x ^ n1.x ^ n2.x ^ n3.x ^ n4.x); sc_acc[2] += sc_b - sc_a;)
                 TRAY_CNT(nodes);
-                uint32_t hitmask;
-                if (MODE == 1) hitmask = node_test(r, best_t, n0, n1, n2, n3, n4, k4b, r.box_tmin, (P.variant & TRAY_VARIANT_BOX_DIVIDE) != 0u);
-                else hitmask = (r.wide || P.force_exact) ? node_test(r, best_t, n0, n1, n2, n3, n4, k4b)
-                                                : node_test_fast(r, best_t, n0, n1, n2, n3, n4, k4b, P.zero);   // :380
+                uint32_t hitmask;                                                              // slot space (see node_test_s)
+                if (MODE == 1) hitmask = node_test_s(r, best_t, n0, n1, n2, n3, n4, k4b, r.box_tmin, (P.variant & TRAY_VARIANT_BOX_DIVIDE) != 0u);
+                else hitmask = ((ray_idx & WIDE_BIT) || P.force_exact) ? node_test_s(r, best_t, n0, n1, n2, n3, n4, k4b)
+                                                : node_test_fast_s(r, best_t, n0, n1, n2, n3, n4, k4b, P.zero);   // :380
                 SC(const long long sc_c = clk_after(hitmask); sc_acc[3] += sc_c - sc_b; sc_n[0]++;)
                 cur_x = n1.x; tri_x = n1.y;                                                    // :383-384
-                cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386
+                cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386 (top byte: hit inner children, slot space)
                 tri_y = hitmask & 0x00ffffffu;                                                 // :387
                 if (tri_y == 0u && cur_y < 0x01000000u) pop_or_retire();
-                if (TRAY_PREFETCH) {
-                    if (tri_y != 0u) {
-                        if (!TLAS || tlas_sp != INVALID)
-                            prefetch_l1(P.tris + (size_t)(tri_x + 31u - (uint32_t)__clz((int)tri_y)) * (TRI_STRIDE / 16));
-                    } else if (cur_y >= 0x01000000u) {
-                        const uint32_t o2 = 31u - (uint32_t)__clz((int)cur_y);
-                        const uint32_t s2 = (o2 - 24u) ^ (r.oct_inv4 & 0xffu);
-                        const uint4* q = P.nodes + (size_t)(bvh_off + cur_x + (uint32_t)__popc(cur_y & ~(0xffffffffu << s2))) * 5u;
-                        prefetch_l1(q); prefetch_l1(q + 4);
-                    }
-                }
                 SC(sc_acc[4] += clk_after(cur_y ^ tri_y) - sc_c;)
             }
         } else {
@@ -878,7 +998,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                     // TLAS leaf: g is an instance slot (query_tlas.hlsl:410-446)
                     if (tri_y != 0u) push(tri_x, tri_y);
                     if (cur_y & 0xff000000u) push(cur_x, cur_y);
-                    tlas_sp = (uint32_t)sp;
+                    tlas_sp = sp;
                     bvh_off = __ldg(P.blas_offsets + g);
                     TRAY_CNT(insts);
                     cur_x = 0; cur_y = 0x80000000u; tri_y = 0;
@@ -910,7 +1030,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                         if (t2 < best_t) { best_t = t2; best_prim = g2; }
                     }
 #endif
-                    if (ANYHIT && best_prim != INVALID) { sp = 0; tri_y = 0u; cur_y = 0u; }   // drop the rest of the traversal
+                    if (ANYHIT && best_prim != INVALID) { sp &= SP_STEP - 1u; tri_y = 0u; cur_y = 0u; }   // drop the rest of the traversal
                     if (tri_y == 0u && cur_y < 0x01000000u) pop_or_retire();
                     SC(sc_acc[7] += clk_after(cur_y ^ tri_y ^ __float_as_uint(best_t)) - sc_b; sc_n[1]++;)
                 }
@@ -956,6 +1076,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
         }
     }
 #undef TRAY_CNT
+#undef TRAY_STK
 }
 
 // compact local order -> row-major frame (one thread per local work item)

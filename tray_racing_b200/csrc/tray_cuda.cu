@@ -917,7 +917,7 @@ int tray_cuda_render(tray_scene* s, const tray_view* view, uint32_t w, uint32_t 
     if (!s || !view) return fail(TRAY_ERR_ARG, "NULL argument");
     if (shards == 0) shards = 1;
     if (w == 0 || h == 0 || shard >= shards) return fail(TRAY_ERR_ARG, "bad frame size / shard (%ux%u, %u of %u)", w, h, shard, shards);
-    if ((uint64_t)((w + 31) / 32) * ((h + 7) / 8) * 256ull >= 0x80000000ull) return fail(TRAY_ERR_ARG, "frame too large");
+    if ((uint64_t)((w + 31) / 32) * ((h + 7) / 8) * 256ull >= 0x40000000ull) return fail(TRAY_ERR_ARG, "frame too large");
     CU(cudaSetDevice(s->device));
     const bool want_count = (flags & TRAY_RENDER_COUNTERS) != 0;
     if (want_count != s->counting) tray_cuda_set_counting(s, want_count);
