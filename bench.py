@@ -649,6 +649,7 @@ def run_ours(args):
     hbm_peak, hbm_src = measured_peaks()
     l2_peak = cuda.bandwidth_probe(48 << 20, 50, local_rank)          # streaming read of an L2-resident 48 MiB buffer
     hbm_read = cuda.bandwidth_probe(2048 << 20, 8, local_rank)        # same kernel, buffer >> L2
+    l1_gather = cuda.l1_gather_probe(32 << 10, 200, local_rank)       # every lane its own 16-byte record of an L1-resident table
 
     # ---- end to end through the public API with HOST buffers ----
     # Every step: tray_cuda_render on every rank (view + frame parameters go in by value, 160 B per rank), the exchange step,
@@ -798,13 +799,19 @@ def run_ours(args):
             "traffic": ncu_figure("primary_kernel_dram_bytes_per_launch") if args.workload == "c3" else None,
             "algorithmic_bytes_per_launch": bytes_p, "bytes_per_ray": bytes_p / max(1, cp["rays"]), "ms_per_launch": kp_ms,
             "nodes_per_ray": cp["nodes"] / max(1, cp["rays"]), "tris_per_ray": cp["tris"] / max(1, cp["rays"]),
-            "what_binds": "SM issue slots, not a memory pipe: DRAM moves ~4 % of the algorithmic bytes, L2 runs at ~12 % of its throughput (ncu, profiles/)",
+            "what_binds": "SM issue slots (ALU pipe) first, the L1's gather rate second; not DRAM (~4 % of the algorithmic bytes) and not L2 (~12 % of its throughput; ncu, profiles/)",
             "issue": {"peak_warp_inst_per_s": issue_peak, "sm_mhz": clk_hz,
                       "warp_inst_per_launch": winst_p, "thread_inst_per_launch": tinst_p,
                       "warp_inst_per_ray": (winst_p / cp["rays"]) if winst_p else None,
                       "lanes_per_inst": (tinst_p / winst_p) if (winst_p and tinst_p) else None,
                       "frac_of_issue_peak": (winst_p / (kp_ms * 1e-3) / issue_peak) if winst_p else None,
                       "note": "instruction counts per launch from the committed ncu capture of this kernel (profiles/roofline_traffic.json), duration live"},
+            "l1_gather": {"peak": l1_gather, "achieved": bytes_p / kp_ms / 1e6, "frac": bytes_p / kp_ms / 1e6 / l1_gather, "unit": "GB/s",
+                          "bytes_per_clk_per_sm": l1_gather * 1e9 / (sm_count * clk_hz * 1e6),
+                          "peak_source": "measured in this run (tray_cuda_l1_gather_probe): every lane of every warp reads its own 16-byte record "
+                                         "from a different 128-byte line of an L1-resident 32 KiB table — how a traversal warp reads nodes and triangles",
+                          "note": "the memory pipe this kernel loads most: every node visit is 5 and every triangle test 3 such accesses per lane "
+                                  "(ncu l1tex__throughput 42 % on this launch; 75 % with 128-byte nodes, profiles/experiments/r2_tnode_*)"},
             "hbm": {"peak": hbm_peak, "peak_source": hbm_src, "frac": bytes_p / kp_ms / 1e6 / hbm_peak,
                     "hbm_read_gbs_measured_here": hbm_read, "note": "side figure: the kernel is not HBM-bound (see traffic)"},
             "bounce_kernel": {"achieved": bytes_b / kb_ms / 1e6 if cb["rays"] else None, "frac": (bytes_b / kb_ms / 1e6 / l2_peak) if cb["rays"] else None,

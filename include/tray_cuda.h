@@ -474,6 +474,12 @@ int tray_cuda_start_multi(const int* devices, int n_devices,
  * node array lives under), one much larger than L2 measures HBM read bandwidth.                   */
 int tray_cuda_bandwidth_probe(int device, uint64_t bytes, int iters, float* out_gbs);
 
+/* The third denominator: what the L1 delivers to a GATHER — every lane of a warp reading its own 16-byte record from a
+ * different 128-byte line of an L1-resident table of `bytes` (<= 64 KiB), which is how a traversal warp reads nodes and
+ * triangles.  Grid and block shape of the traversal kernels; `iters` rounds of 8 independent loads per lane.  Reported as
+ * GB/s over the whole chip (divide by SMs x clock for bytes per clock per SM).                                          */
+int tray_cuda_l1_gather_probe(int device, uint32_t bytes, int iters, float* out_gbs);
+
 const char* tray_cuda_last_error(void);
 
 #ifdef __cplusplus

@@ -256,6 +256,7 @@ static inline int closer(float t, float tmax) {
 /* ---- CwBvh::ray_traverse / ray_traverse_tlas_blas; twins query.hlsl:328-438, query_tlas.hlsl:333-500 */
 /* `any_hit`: stop at the first accepted triangle (the "faster anyhit query" rt_cpu.rs:78-79 asks for; the reference's
  * own intersects_bl_bvh, query.hlsl:440-445, runs the full closest-hit loop).  Same order of tests up to that point. */
+static int g_oplog_detail = 0;   /* step log flavour (orc_trace_oplog_detail): 'T'/'U' first / later triangle of a group, lower case = the test moved tmax */
 static int trace_one_ex(const orc_scene* s, const orc_ray* ray, orc_hit* out, orc_count* cnt, uint8_t* oplog, int any_hit) {
     uint32_t n_ops = 0;   /* optional step log: 'N' node fetch+test, 'T' triangle test, 'I' instance entry */
     prep_ray r; prepare_ray(ray, &r);
@@ -299,6 +300,7 @@ static int trace_one_ex(const orc_scene* s, const orc_ray* ray, orc_hit* out, or
             cur_x = 0; cur_y = 0;
         }
 
+        int first_of_group = 1;
         while (tri_y != 0) {                                               /* :396 */
             uint32_t local = firstbithigh(tri_y);                          /* :398 */
             tri_y &= ~(1u << local);                                       /* :401 */
@@ -321,8 +323,12 @@ static int trace_one_ex(const orc_scene* s, const orc_ray* ray, orc_hit* out, or
                 break;
             }
             n_tris++;                                                      /* PROFILE_RT tri_hit_count, :407-409 */
-            if (oplog) oplog[n_ops++] = 'T';
             float t = tri_intersect(s->tris + (uint64_t)global * s->tri_stride, s->tri_stride, &r, best_t);
+            if (oplog) {
+                uint8_t c = 'T';
+                if (g_oplog_detail) { c = first_of_group ? 'T' : 'U'; if (closer(t, best_t)) c |= 0x20; }
+                oplog[n_ops++] = c; first_of_group = 0;
+            }
             if (closer(t, best_t)) { best_t = t; best_prim = global; }     /* :410-413 with the CPU tie rule */
             if (any_hit && best_prim != ORC_INVALID_PRIM) break;
         }
@@ -397,6 +403,16 @@ int orc_trace_oplog(const orc_scene* s, const orc_ray* rays, uint64_t n, const o
         if (e < rc) rc = e;
         if (c.nodes + c.tris + c.insts != counts[i].nodes + counts[i].tris + counts[i].insts) rc = -5;
     }
+    return rc;
+}
+
+/* The same log with triangle groups and tmax updates marked: 'T' / 'U' = first / later triangle of a group, lower case =
+ * the test moved the ray's tmax (tests/tools/sched_sim.c, policy 4). */
+int orc_trace_oplog_detail(const orc_scene* s, const orc_ray* rays, uint64_t n, const orc_count* counts,
+                           uint8_t* ops, const uint64_t* offsets, int nthreads) {
+    g_oplog_detail = 1;
+    const int rc = orc_trace_oplog(s, rays, n, counts, ops, offsets, nthreads);
+    g_oplog_detail = 0;
     return rc;
 }
 

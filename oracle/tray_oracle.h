@@ -76,6 +76,9 @@ int orc_trace_any(const orc_scene* s, const orc_ray* rays, uint64_t n, orc_hit* 
 /* per-ray step log ('N' node, 'T' triangle, 'I' instance entry) for warp-scheduling studies in tests/tools */
 int orc_trace_oplog(const orc_scene* s, const orc_ray* rays, uint64_t n, const orc_count* counts,
                     uint8_t* ops, const uint64_t* offsets, int nthreads);
+/* same, with triangle groups ('T' first / 'U' later triangle) and tmax updates (lower case) marked */
+int orc_trace_oplog_detail(const orc_scene* s, const orc_ray* rays, uint64_t n, const orc_count* counts,
+                           uint8_t* ops, const uint64_t* offsets, int nthreads);
 
 /* O(rays x tris) reference: same triangle test, same first-wins rule in ascending index order;
  * also reports how many triangles tie with the winning t (for the tie census). */

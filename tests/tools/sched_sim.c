@@ -121,3 +121,81 @@ int sched_sim(const uint8_t* ops, const uint64_t* offsets, uint64_t n_rays, cons
     free(w); free(heap);
     return 0;
 }
+
+/* ---- policy 4 (round 2): one ray per lane, two triangles of a group per triangle step (tri2), and optionally a SPECULATIVE
+ * node step: a lane that waits with a triangle group whose successor is a node step joins the warp's node phase early, testing
+ * that node against its current tmax; when its triangle group ends without having moved tmax the result stands (the node step
+ * is skipped), otherwise it is thrown away and the step is replayed.  Input: the detailed log (orc_trace_oplog_detail).
+ * cfg.K: bit 0 = tri2, bit 1 = speculate; csel = extra slots of a node step that carries speculative lanes. */
+static int is_later(uint8_t c) { return c == 'U' || c == 'u'; }
+int sched_sim4(const uint8_t* ops, const uint64_t* offsets, uint64_t n_rays, const sim_cfg* c, sim_out* o, double* extra) {
+    const int tri2 = c->K & 1, spec_on = (c->K >> 1) & 1;
+    warp* w = (warp*)calloc((size_t)c->n_warps, sizeof(warp));
+    int* heap = (int*)malloc(sizeof(int) * (size_t)c->n_warps);
+    uint8_t* spec = (uint8_t*)calloc((size_t)c->n_warps * 32, 1);     /* 0 none, 1 speculated, 2 speculated and dirty */
+    for (int i = 0; i < c->n_warps; i++) { w[i].pos = (uint64_t*)calloc(32, 8); w[i].end = (uint64_t*)calloc(32, 8); heap[i] = i; }
+    memset(o, 0, sizeof *o);
+    double n_spec = 0, n_commit = 0, n_replay = 0;
+    uint64_t cursor = 0;
+    int live = c->n_warps;
+    while (live > 0) {
+        const int wi = heap[0];
+        warp* W = &w[wi];
+        uint8_t* sp = spec + (size_t)wi * 32;
+        int idle = 0, n_tri = 0, n_node = 0;
+        for (int l = 0; l < 32; l++) {
+            if (W->pos[l] == W->end[l]) { idle++; continue; }
+            if (ops[W->pos[l]] == 'N') n_node++; else n_tri++;
+        }
+        const int busy = 32 - idle;
+        if (idle > 0 && !W->exhausted && (idle >= c->refill_min || busy == 0)) {
+            for (int l = 0; l < 32; l++)
+                if (W->pos[l] == W->end[l] && cursor < n_rays) { W->pos[l] = offsets[cursor]; W->end[l] = offsets[cursor + 1]; cursor++; sp[l] = 0; }
+            if (cursor >= n_rays) W->exhausted = 1;
+            W->t += c->cr; o->slots += c->cr; o->refills += 1;
+        } else if (busy == 0) {
+            if (W->t > o->makespan) o->makespan = W->t;
+            heap[0] = heap[--live];
+            if (live > 0) heap_sift(heap, live, 0, w);
+            continue;
+        } else {
+            const int tri_phase = n_node == 0 || n_tri * c->tri_weight >= n_node;
+            if (!tri_phase) {
+                int done = 0, specs = 0;
+                for (int l = 0; l < 32; l++) {
+                    if (W->pos[l] == W->end[l]) continue;
+                    const uint8_t op = ops[W->pos[l]];
+                    if (op == 'N') { W->pos[l]++; done++; }
+                    else if (spec_on && sp[l] == 0 && op != 'I') {
+                        uint64_t e = W->pos[l] + 1;
+                        while (e < W->end[l] && is_later(ops[e])) e++;
+                        if (e < W->end[l] && ops[e] == 'N') { sp[l] = 1; specs++; }
+                    }
+                }
+                const int cost = c->cn + (specs ? c->csel : 0);
+                W->t += cost; o->slots += cost; o->node_steps += 1; o->node_lanes += done + specs; n_spec += specs;
+            } else {
+                int done = 0;
+                for (int l = 0; l < 32; l++) {
+                    if (W->pos[l] == W->end[l] || ops[W->pos[l]] == 'N') continue;
+                    done++;
+                    int n = 1;
+                    if (tri2 && ops[W->pos[l]] != 'I' && W->pos[l] + 1 < W->end[l] && is_later(ops[W->pos[l] + 1])) n = 2;
+                    for (int k = 0; k < n; k++) { if ((ops[W->pos[l]] & 0x20) && sp[l] == 1) sp[l] = 2; W->pos[l]++; }
+                    const int group_over = W->pos[l] == W->end[l] || !is_later(ops[W->pos[l]]);
+                    if (group_over && sp[l]) {
+                        if (sp[l] == 1 && W->pos[l] < W->end[l] && ops[W->pos[l]] == 'N') { W->pos[l]++; n_commit += 1; }
+                        else n_replay += 1;
+                        sp[l] = 0;
+                    }
+                }
+                W->t += c->ct; o->slots += c->ct; o->tri_steps += 1; o->tri_lanes += done;
+            }
+        }
+        heap_sift(heap, live, 0, w);
+    }
+    if (extra) { extra[0] = n_spec; extra[1] = n_commit; extra[2] = n_replay; }
+    for (int i = 0; i < c->n_warps; i++) { free(w[i].pos); free(w[i].end); }
+    free(w); free(heap); free(spec);
+    return 0;
+}

@@ -36,6 +36,7 @@ def sim_lib():
         subprocess.check_call(["gcc", "-O2", "-fPIC", "-shared", "-o", so, src])
     L = C.CDLL(so)
     L.sched_sim.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Cfg), C.POINTER(Out)]
+    L.sched_sim4.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(Cfg), C.POINTER(Out), C.POINTER(C.c_double)]
     return L
 
 
@@ -51,16 +52,17 @@ def tile_order(w, h):
     return (py * w + px)[ok]
 
 
-def oplog(orc, rays):
+def oplog(orc, rays, detail=False):
     hits, cnt, tot = orc.trace(rays, counts=True)
     n_ops = cnt["nodes"].astype(np.uint64) + cnt["tris"] + cnt["insts"]
     offsets = np.zeros(rays.shape[0] + 1, dtype=np.uint64)
     np.cumsum(n_ops, out=offsets[1:])
     ops = np.zeros(int(offsets[-1]) + 1, dtype=np.uint8)
     L = ob.lib()
-    L.orc_trace_oplog.restype = C.c_int
-    L.orc_trace_oplog.argtypes = [C.POINTER(ob.OrcScene), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
-    rc = L.orc_trace_oplog(C.byref(orc.scene), rays.ctypes.data, rays.shape[0], cnt.ctypes.data, ops.ctypes.data, offsets.ctypes.data, 0)
+    fn = L.orc_trace_oplog_detail if detail else L.orc_trace_oplog
+    fn.restype = C.c_int
+    fn.argtypes = [C.POINTER(ob.OrcScene), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    rc = fn(C.byref(orc.scene), rays.ctypes.data, rays.shape[0], cnt.ctypes.data, ops.ctypes.data, offsets.ctypes.data, 0)
     assert rc == 0, rc
     return ops, offsets, tot
 
@@ -76,6 +78,7 @@ def main():
     ap.add_argument("--ct", type=int, default=165)
     ap.add_argument("--cr", type=int, default=80)
     ap.add_argument("--csel", type=int, default=25)
+    ap.add_argument("--spec", action="store_true", help="round 2: only the tri2 / speculative-node-step study (policy 4, detailed log)")
     a = ap.parse_args()
     mesh = host.Mesh.generate(a.scene, a.seed, 1.0)
     packed = host.PackedScene(mesh, use_tlas=False, tri_stride=48)
@@ -95,6 +98,20 @@ def main():
         print(f"== {name}: {n} rays, nodes/ray {tot['nodes'] / n:.2f}, tris/ray {tot['tris'] / n:.2f}, warps {n_warps}")
         ideal = (tot["nodes"] * a.cn + tot["tris"] * a.ct) / 32.0 / n
         print(f"   ideal (32/32 lanes, no overhead): {ideal:.1f} warp-slots/ray")
+        if a.spec:
+            ops, offsets, tot = oplog(orc, rays, detail=True)
+            base = None
+            for label, K, tw, cn, ct, csel in (("one triangle per step (r1)", 0, 4, 300, 130, 0), ("tri2 (the r2 kernel)", 1, 4, 290, 170, 0), ("tri2 tw=3", 1, 3, 290, 170, 0),
+                                               ("tri2 + speculative node step (+20)", 3, 4, 290, 175, 20), ("  .. tw=3", 3, 3, 290, 175, 20), ("  .. tw=2", 3, 2, 290, 175, 20), ("  .. tw=6", 3, 6, 290, 175, 20),
+                                               ("  .. free (+0)", 3, 4, 290, 170, 0)):
+                cfg = Cfg(4, K, n_warps, 4, tw, cn, ct, a.cr, csel)
+                out = Out(); extra = (C.c_double * 3)()
+                L.sched_sim4(ops.ctypes.data, offsets.ctypes.data, n, C.byref(cfg), C.byref(out), extra)
+                spr = out.slots / n
+                base = base or spr
+                print(f"   {label:36s} slots/ray {spr:7.1f}  x{base / spr:4.2f}  node steps/ray {out.node_steps * 32 / n:6.2f} lanes {out.node_lanes / max(1, out.node_steps):5.2f}  "
+                      f"tri steps/ray {out.tri_steps * 32 / n:5.2f} lanes {out.tri_lanes / max(1, out.tri_steps):5.2f}  spec/ray {extra[0] / n:4.2f} committed {extra[1] / max(1, extra[0]):4.2f}")
+            continue
         base = None
         for label, policy, K, rmin, tw in (("K=1 (round-1 kernel)", 0, 1, 4, 4), ("K=1 tw=2", 0, 1, 4, 2), ("K=1 tw=8", 0, 1, 4, 8),
                                            ("drain tw=4 (cn 300, loop 45 + 110/round)", 2, 1, 4, 4), ("drain tw=2", 2, 1, 4, 2), ("drain tw=1", 2, 1, 4, 1), ("drain tw=8", 2, 1, 4, 8), ("K=2 per lane", 0, 2, 8, 4), ("K=2 per lane tw=2", 0, 2, 8, 2), ("K=3 per lane", 0, 3, 8, 4),

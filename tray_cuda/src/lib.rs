@@ -87,6 +87,7 @@ extern "C" {
     pub fn tray_cuda_counters(scene: *mut TrayScene, primary: *mut TrayCounters, bounce: *mut TrayCounters) -> c_int;
     pub fn tray_cuda_set_counting(scene: *mut TrayScene, enabled: c_int) -> c_int;
     pub fn tray_cuda_bandwidth_probe(device: c_int, bytes: u64, iters: c_int, out_gbs: *mut f32) -> c_int;
+    pub fn tray_cuda_l1_gather_probe(device: c_int, bytes: u32, iters: c_int, out_gbs: *mut f32) -> c_int;
     pub fn tray_cuda_device_count() -> c_int;
     pub fn tray_cuda_last_error() -> *const c_char;
     pub fn tray_cuda_scene_create(nodes: *const c_void, n_nodes: u64, tris: *const c_void, n_tris: u64, tri_stride: u32,

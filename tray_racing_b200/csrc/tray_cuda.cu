@@ -316,9 +316,46 @@ __global__ void __launch_bounds__(512) bandwidth_kernel(const uint4* __restrict_
         }
     if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) out[0] = acc.x;   // never true in practice; keeps the loads alive
 }
+// every lane gathers 16-byte records from its own pseudo-random line of a small (L1-resident) table
+__global__ void __launch_bounds__(128, 8) l1_gather_kernel(const uint4* __restrict__ buf, uint32_t n_lines, int iters, uint32_t* out) {
+    uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    uint4 acc = make_uint4(0, 0, 0, 0);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            x = x * 1664525u + 1013904223u;
+            const uint32_t line = __umulhi(x, n_lines), quad = (x >> 3) & 7u;      // 128-byte line, 16-byte record inside it
+            const uint4 v = __ldg(buf + (size_t)line * 8u + quad);
+            acc.x ^= v.x; acc.y ^= v.y; acc.z ^= v.z; acc.w ^= v.w;
+        }
+    }
+    if ((acc.x ^ acc.y ^ acc.z ^ acc.w) == 0x12345678u) out[0] = acc.x;
+}
 }  // namespace
 
 extern "C" {
+
+int tray_cuda_l1_gather_probe(int device, uint32_t bytes, int iters, float* out_gbs) {
+    if (!out_gbs || bytes < 1024 || bytes > (64u << 10) || iters < 1) return fail(TRAY_ERR_ARG, "bad argument");
+    if (tray_cuda_device_count() == 0) return fail(TRAY_ERR_NO_DEVICE, "no CUDA device");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop; CU(cudaGetDeviceProperties(&prop, device));
+    uint4* buf = nullptr; uint32_t* out = nullptr;
+    const uint32_t n_lines = bytes / 128;
+    CU(cudaMalloc(&buf, (size_t)n_lines * 128)); CU(cudaMalloc(&out, 4));
+    CU(cudaMemset(buf, 0x5a, (size_t)n_lines * 128));
+    cudaEvent_t e0, e1; CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int grid = prop.multiProcessorCount * 8;
+    l1_gather_kernel<<<grid, 128>>>(buf, n_lines, 2, out);
+    CU(cudaEventRecord(e0));
+    l1_gather_kernel<<<grid, 128>>>(buf, n_lines, iters, out);
+    CU(cudaEventRecord(e1));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0.f; CU(cudaEventElapsedTime(&ms, e0, e1));
+    *out_gbs = (float)((double)grid * 128.0 * 8.0 * iters * 16.0 / (ms * 1e-3) / 1e9);
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf); cudaFree(out);
+    return TRAY_OK;
+}
 
 int tray_cuda_bandwidth_probe(int device, uint64_t bytes, int iters, float* out_gbs) {
     if (!out_gbs || bytes < 4096 || iters < 1) return fail(TRAY_ERR_ARG, "bad argument");

@@ -21,7 +21,7 @@ EXPORTS = (
     "tray_cuda_scene_info", "tray_cuda_trace", "tray_cuda_trace_device", "tray_cuda_render",
     "tray_cuda_shard_pixels", "tray_cuda_frame_download", "tray_cuda_frame_device_ptrs", "tray_cuda_sync",
     "tray_cuda_counters", "tray_cuda_set_counting", "tray_cuda_start", "tray_cuda_last_error",
-    "tray_cuda_untile_rgba", "tray_cuda_scene_set_stream", "tray_cuda_bandwidth_probe",
+    "tray_cuda_untile_rgba", "tray_cuda_scene_set_stream", "tray_cuda_bandwidth_probe", "tray_cuda_l1_gather_probe",
     "tray_cuda_frame_alloc", "tray_cuda_frame_free", "tray_cuda_ipc_export", "tray_cuda_ipc_open", "tray_cuda_ipc_close",
     "tray_cuda_scene_set_frame_target", "tray_cuda_render_timed", "tray_cuda_trace_any", "tray_cuda_trace_any_device",
     "tray_cuda_scene_build", "tray_cuda_scene_download", "tray_cuda_frame_readback_begin", "tray_cuda_frame_readback_wait",
@@ -132,6 +132,8 @@ def lib() -> C.CDLL:
         L.tray_cuda_scene_set_stream.argtypes = [vp, vp]
         L.tray_cuda_bandwidth_probe.restype = i32
         L.tray_cuda_bandwidth_probe.argtypes = [i32, u64, i32, f32p]
+        L.tray_cuda_l1_gather_probe.restype = i32
+        L.tray_cuda_l1_gather_probe.argtypes = [i32, u32, i32, f32p]
         L.tray_cuda_frame_alloc.restype = i32
         L.tray_cuda_frame_alloc.argtypes = [i32, u64, C.POINTER(vp)]
         L.tray_cuda_frame_free.restype = i32
@@ -213,6 +215,14 @@ def _check(rc: int):
 
 def device_count() -> int:
     return lib().tray_cuda_device_count()
+
+
+def l1_gather_probe(nbytes: int = 32 << 10, iters: int = 200, device: int = 0) -> float:
+    """GB/s (whole chip) the L1 delivers when every lane gathers its own 16-byte record from a different line of an
+    L1-resident `nbytes` table — the access pattern of a traversal warp."""
+    g = C.c_float()
+    _check(lib().tray_cuda_l1_gather_probe(device, int(nbytes), int(iters), C.byref(g)))
+    return g.value
 
 
 def bandwidth_probe(nbytes: int, iters: int = 20, device: int = 0) -> float:
