@@ -103,8 +103,13 @@ def main():
             base = None
             for label, K, tw, cn, ct, csel in (("one triangle per step (r1)", 0, 4, 300, 130, 0), ("tri2 (the r2 kernel)", 1, 4, 290, 170, 0), ("tri2 tw=3", 1, 3, 290, 170, 0),
                                                ("tri2 + speculative node step (+20)", 3, 4, 290, 175, 20), ("  .. tw=3", 3, 3, 290, 175, 20), ("  .. tw=2", 3, 2, 290, 175, 20), ("  .. tw=6", 3, 6, 290, 175, 20),
-                                               ("  .. free (+0)", 3, 4, 290, 170, 0)):
-                cfg = Cfg(4, K, n_warps, 4, tw, cn, ct, a.cr, csel)
+                                               ("  .. free (+0)", 3, 4, 290, 170, 0),
+                                               ("tri2, refill cost 140 (rm 4)", 1, 4, 290, 170, -140), ("tri2, refill 60, rm 4", 1, 4, 290, 170, -60), ("tri2, refill 60, rm 2", 1, 4, 290, 170, -60 - 2000),
+                                               ("tri2, refill 60, rm 1", 1, 4, 290, 170, -60 - 1000), ("tri2, refill 140, rm 2", 1, 4, 290, 170, -140 - 2000), ("tri2, refill 140, rm 1", 1, 4, 290, 170, -140 - 1000)):
+                rm, cr = 4, a.cr
+                if csel < 0:            # encoded refill study: -(cost) - 1000 * refill_min
+                    v = -csel; rm = v // 1000 or 4; cr = v % 1000; csel = 0
+                cfg = Cfg(4, K, n_warps, rm, tw, cn, ct, cr, csel)
                 out = Out(); extra = (C.c_double * 3)()
                 L.sched_sim4(ops.ctypes.data, offsets.ctypes.data, n, C.byref(cfg), C.byref(out), extra)
                 spr = out.slots / n
