@@ -119,6 +119,20 @@ def test_no_device_means_error_not_fallback():
         cuda.start(np.zeros(80, np.uint8), np.zeros(16, np.uint8), np.zeros(48, np.uint8), 0, v, 64, 64, 0.01)
 
 
+def test_probes_reject_bad_arguments_and_need_a_device():
+    """The roofline probes (bandwidth, L1 gather) validate their arguments before touching a device and report a missing
+    device as an error, like every compute entry point."""
+    with pytest.raises(cuda.TrayCudaError):
+        cuda.l1_gather_probe(nbytes=128 << 10)            # the table must fit the L1: <= 64 KiB
+    with pytest.raises(cuda.TrayCudaError):
+        cuda.l1_gather_probe(nbytes=32 << 10, iters=0)
+    with pytest.raises(cuda.TrayCudaError):
+        cuda.bandwidth_probe(16, 1)
+    if cuda.device_count() == 0:
+        with pytest.raises(cuda.TrayCudaError, match="no CUDA device"):
+            cuda.l1_gather_probe()
+
+
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(cuda, "_lib", None)
     monkeypatch.setattr(cuda, "LIB_PATH", str(tmp_path / "libtray_cuda.so"))

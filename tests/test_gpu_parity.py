@@ -430,3 +430,16 @@ def test_async_readback_matches_synchronous_download(cornell):
             assert np.array_equal(got[f], want[f]), f"frame {f}"
     finally:
         sc.close()
+
+
+@pytest.mark.gpu
+def test_roofline_probes_measure_something_sane():
+    """bench.py's denominators: L2-resident streaming reads run faster than HBM-sized ones, and the L1 gather probe (every lane
+    its own 16-byte record of an L1-resident table) lands between 10 and 128 bytes per clock per SM."""
+    l2 = cuda.bandwidth_probe(32 << 20, 10)
+    hbm = cuda.bandwidth_probe(1024 << 20, 2)
+    assert l2 > hbm > 500.0
+    g = cuda.l1_gather_probe(32 << 10, 50)
+    sms = 148
+    per_clk = g * 1e9 / (sms * 1.9e9)
+    assert 10.0 < per_clk < 128.0, g

@@ -88,7 +88,7 @@ struct tray_scene {
     uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
     bool counting = false;
     uint32_t variant = 0;                    // TRAY_VARIANT_* (tray_cuda_scene_set_variant): the MODE 1 kernels
-    uint32_t refill_min = 4, tri_weight = 4, gen_min = 4;
+    uint32_t refill_min = 4, tri_weight = 3, gen_min = 4;
     bool overlap_default = false;            // TRAY_CUDA_OVERLAP=1: tray_cuda_render always takes the one-launch frame kernel
     bool pool = false;                       // pooled kernel (traverse_pool.cuh) or one-ray-per-lane kernel (traverse.cuh)
     uint32_t pool_refill_min = 8, pool_tri_weight = 1;
@@ -446,7 +446,7 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
         const uint8_t* e = (const uint8_t*)nodes + i * 80 + 12;
         if (e[0] >= 167 || e[1] >= 167 || e[2] >= 167) s->force_exact = true;   // scale = 2^(e-127) >= 2^40
     }
-    s->tri_weight = (uint32_t)env_int("TRAY_CUDA_TRI_WEIGHT", 4);
+    s->tri_weight = (uint32_t)env_int("TRAY_CUDA_TRI_WEIGHT", 3);     // 3: +0.6 ... 1.2 % over 4 with two triangles per step (profiles/experiments/r2_triweight_ab.log)
     s->gen_min = (uint32_t)env_int("TRAY_CUDA_GEN_MIN", 4);
     s->overlap_default = env_int("TRAY_CUDA_OVERLAP", 0) != 0;
     s->pool = env_int("TRAY_CUDA_POOL", 0) != 0;
