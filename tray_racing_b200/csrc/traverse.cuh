@@ -38,6 +38,9 @@ constexpr int BLOCK_THREADS = TRAY_BLOCK_THREADS;
 #ifndef TRAY_STACK_SMEM
 #define TRAY_STACK_SMEM 12
 #endif
+#ifndef TRAY_MASK_IMAD
+#define TRAY_MASK_IMAD 1     // hit-mask accumulation as a predicated IMAD (FMA pipe) instead of a LOP3 (ALU pipe): +1.1 % (profiles/experiments/r2_pipe_balance_ab.log)
+#endif
 #ifndef TRAY_TRI2
 #define TRAY_TRI2 1          // two triangles of a lane's pending group per triangle step (bit-exact; -2.5 % frame time, profiles/experiments/r2_ab_*)
 #endif
@@ -56,8 +59,12 @@ constexpr float BOX_EPS_ = 0.0001f;           // query.hlsl:274
 #define TRAY_I2F_Z 1
 #endif
 #ifndef TRAY_I2F_Y
-#define TRAY_I2F_Y 0
+#define TRAY_I2F_Y 2         // r2: with the slot-space node test the ALU pipe is the node test's bottleneck again; all y-plane bytes through
+#endif                       //     I2F.U8 as well (32 conversions per node on the XU pipe) is the balance point: 24 -> +1.6 %, 32 -> +3.1 %, 40 -> -1.5 %
+#ifndef TRAY_I2F_X
+#define TRAY_I2F_X 0
 #endif
+constexpr int I2F_X = TRAY_I2F_X;             // the same for the x-plane bytes (lane kernel only): measured slower, the XU pipe saturates
 constexpr int I2F_Y = TRAY_I2F_Y;             // 0: no y-plane bytes via I2F.U8, 1: children 0-3 only, 2: all children
 constexpr bool I2F_Z = TRAY_I2F_Z != 0;       // convert the z-plane bytes on the XU pipe (I2F.U8) instead of PRMT+bias
 
@@ -90,6 +97,7 @@ struct TraceParams {
     uint32_t k4b;                             // 0x4B000000, passed at run time (see byte_f32)
     uint32_t force_exact;                     // scene has node scales >= 2^40: always take the unfused node test
     float zero;                               // 0.0f, passed at run time (see child_test_fast)
+    uint32_t one;                             // 1, passed at run time (TRAY_MASK_IMAD: keeps the mask accumulation an IMAD on the FMA pipe)
     uint32_t refill_min;                      // idle lanes needed before a partial warp refills
     uint32_t tri_weight;                      // vote: triangle phase when n_tri * tri_weight >= n_node
     uint32_t variant;                         // MODE 1 kernels only: TRAY_VARIANT_* switches (tray_cuda_scene_set_variant)
@@ -394,11 +402,12 @@ __device__ __forceinline__ uint32_t node_test_s(const RayConst& r, float tmax, c
 }
 
 // fused form (the arithmetic of child_test_fast, bit-identical to node_test_s)
-template <int J, bool YI2F>
+template <int J, bool YI2F, bool XI2F>
 __device__ __forceinline__ void child_test_fast_s(uint32_t& mask, uint32_t nx, uint32_t fx, uint32_t ny, uint32_t fy, uint32_t nz, uint32_t fz,
-                                                  const NodeConsts& c, float tmax, uint32_t child_bits4, uint32_t meta4, uint32_t k4b) {
+                                                  const NodeConsts& c, float tmax, uint32_t child_bits4, uint32_t meta4, uint32_t k4b, uint32_t one) {
     float tnx, tfx, tny, tfy, tnz, tfz;
-    unpack2f(fadd2(ffma2(pack2(byte_biased<J>(nx, k4b), byte_biased<J>(fx, k4b)), c.AX, c.CX), c.BX), tnx, tfx);
+    if (XI2F) unpack2f(fadd2(ffma2(pack2f(byte_i2f<J>(nx), byte_i2f<J>(fx)), c.AX, c.Z0), c.BX), tnx, tfx);
+    else unpack2f(fadd2(ffma2(pack2(byte_biased<J>(nx, k4b), byte_biased<J>(fx, k4b)), c.AX, c.CX), c.BX), tnx, tfx);
     if (YI2F) unpack2f(fadd2(ffma2(pack2f(byte_i2f<J>(ny), byte_i2f<J>(fy)), c.AY, c.Z0), c.BY), tny, tfy);
     else unpack2f(fadd2(ffma2(pack2(byte_biased<J>(ny, k4b), byte_biased<J>(fy, k4b)), c.AY, c.CY), c.BY), tny, tfy);
     if (I2F_Z) unpack2f(fadd2(ffma2(pack2f(byte_i2f<J>(nz), byte_i2f<J>(fz)), c.AZ, c.Z0), c.BZ), tnz, tfz);
@@ -406,24 +415,30 @@ __device__ __forceinline__ void child_test_fast_s(uint32_t& mask, uint32_t nx, u
     const float tmin = fmaxf(fmaxf(fmaxf(tnx, tny), tnz), BOX_EPS_);
     const float tfar = fminf(fminf(fminf(tfx, tfy), tfz), tmax);
     const uint32_t contrib = byte_u32<J>(child_bits4) << ((meta4 >> (8 * J)) & 31u);
+#if TRAY_MASK_IMAD
+    // the children's bits are disjoint, so OR = ADD = contrib * 1 + mask: an IMAD on the FMA pipe instead of a LOP3 on the ALU pipe
+    asm("{.reg .pred p; setp.le.f32 p, %1, %2; @p mad.lo.u32 %0, %3, %4, %0;}" : "+r"(mask) : "f"(tmin), "f"(tfar), "r"(contrib), "r"(one));
+#else
     asm("{.reg .pred p; setp.le.f32 p, %1, %2; @p or.b32 %0, %0, %3;}" : "+r"(mask) : "f"(tmin), "f"(tfar), "r"(contrib));
+#endif
 }
 template <int I>
 __device__ __forceinline__ void node_half_fast_s(uint32_t& mask, const RayConst& r, float tmax, const NodeConsts& c, uint32_t meta4,
-                                                 uint32_t lox, uint32_t hix, uint32_t loy, uint32_t hiy, uint32_t loz, uint32_t hiz, uint32_t k4b) {
+                                                 uint32_t lox, uint32_t hix, uint32_t loy, uint32_t hiy, uint32_t loz, uint32_t hiz, uint32_t k4b, uint32_t one) {
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     const bool sx = r.dx < 0.0f, sy = r.dy < 0.0f, sz = r.dz < 0.0f;
     const uint32_t nx = sx ? hix : lox, fx = sx ? lox : hix;                          // query.hlsl:266-273
     const uint32_t ny = sy ? hiy : loy, fy = sy ? loy : hiy;
     const uint32_t nz = sz ? hiz : loz, fz = sz ? loz : hiz;
     constexpr bool YI = I2F_Y == 2 || (I2F_Y == 1 && I == 0);
-    child_test_fast_s<0, YI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b);
-    child_test_fast_s<1, YI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b);
-    child_test_fast_s<2, YI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b);
-    child_test_fast_s<3, YI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b);
+    constexpr bool XI = I2F_X == 2 || (I2F_X == 1 && I == 0);
+    child_test_fast_s<0, YI, XI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b, one);
+    child_test_fast_s<1, YI, XI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b, one);
+    child_test_fast_s<2, YI, XI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b, one);
+    child_test_fast_s<3, YI, XI>(mask, nx, fx, ny, fy, nz, fz, c, tmax, child_bits4, meta4, k4b, one);
 }
 __device__ __forceinline__ uint32_t node_test_fast_s(const RayConst& r, float tmax, const uint4& n0, const uint4& n1, const uint4& n2,
-                                                     const uint4& n3, const uint4& n4, uint32_t k4b, float zero) {
+                                                     const uint4& n3, const uint4& n4, uint32_t k4b, float zero, uint32_t one) {
     const uint32_t e = n0.w;
     const float ax = mul(__uint_as_float((e & 0xffu) << 23), r.ix);
     const float ay = mul(__uint_as_float(((e >> 8) & 0xffu) << 23), r.iy);
@@ -437,8 +452,8 @@ __device__ __forceinline__ uint32_t node_test_fast_s(const RayConst& r, float tm
     c.CX = pack2f(cx, cx); c.CY = pack2f(cy, cy); c.CZ = pack2f(cz, cz);
     c.BX = pack2f(bx, bx); c.BY = pack2f(by, by); c.BZ = pack2f(bz, bz); c.Z0 = pack2f(zero, zero);
     uint32_t mask = 0;
-    node_half_fast_s<0>(mask, r, tmax, c, n1.z, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, k4b);
-    node_half_fast_s<1>(mask, r, tmax, c, n1.w, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, k4b);
+    node_half_fast_s<0>(mask, r, tmax, c, n1.z, n2.x, n2.z, n3.x, n3.z, n4.x, n4.z, k4b, one);
+    node_half_fast_s<1>(mask, r, tmax, c, n1.w, n2.y, n2.w, n3.y, n3.w, n4.y, n4.w, k4b, one);
     return mask;
 }
 
@@ -981,7 +996,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                 uint32_t hitmask;                                                              // slot space (see node_test_s)
                 if (MODE == 1) hitmask = node_test_s(r, best_t, n0, n1, n2, n3, n4, k4b, r.box_tmin, (P.variant & TRAY_VARIANT_BOX_DIVIDE) != 0u);
                 else hitmask = ((ray_idx & WIDE_BIT) || P.force_exact) ? node_test_s(r, best_t, n0, n1, n2, n3, n4, k4b)
-                                                : node_test_fast_s(r, best_t, n0, n1, n2, n3, n4, k4b, P.zero);   // :380
+                                                : node_test_fast_s(r, best_t, n0, n1, n2, n3, n4, k4b, P.zero, P.one);   // :380
                 SC(const long long sc_c = clk_after(hitmask); sc_acc[3] += sc_c - sc_b; sc_n[0]++;)
                 cur_x = n1.x; tri_x = n1.y;                                                    // :383-384
                 cur_y = (hitmask & 0xff000000u) | (n0.w >> 24);                                // :386 (top byte: hit inner children, slot space)

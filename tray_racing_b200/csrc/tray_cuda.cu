@@ -185,7 +185,7 @@ void base_params(const tray_scene* s, TraceParams& P) {
     P.nodes = s->d_nodes; P.tris = s->d_tris; P.blas_offsets = s->d_blas; P.tlas_start = s->tlas_start;
     P.cursor = (uint32_t*)s->d_cursor; P.overflow = s->d_overflow;
     P.refill_min = s->refill_min; P.tri_weight = s->tri_weight; P.k4b = 0x4B000000u; P.force_exact = s->force_exact ? 1u : 0u;
-    P.variant = s->variant;
+    P.variant = s->variant; P.one = 1u;
 }
 
 // one launch: reset the cursor, run the persistent grid (sized to the chip, or to the work if that is smaller)
