@@ -38,6 +38,12 @@ constexpr int BLOCK_THREADS = TRAY_BLOCK_THREADS;
 #ifndef TRAY_STACK_SMEM
 #define TRAY_STACK_SMEM 12
 #endif
+#ifndef TRAY_STK_PTX
+#define TRAY_STK_PTX 1       // traversal stack in a PTX-declared shared array (see trace_kernel)
+#endif
+#ifndef TRAY_PUSH_LATE
+#define TRAY_PUSH_LATE 1     // the node step pushes the remaining siblings AFTER it has issued the node fetch
+#endif
 #ifndef TRAY_MASK_IMAD
 #define TRAY_MASK_IMAD 1     // hit-mask accumulation as a predicated IMAD (FMA pipe) instead of a LOP3 (ALU pipe): +1.1 % (profiles/experiments/r2_pipe_balance_ab.log)
 #endif
@@ -758,7 +764,9 @@ __device__ __forceinline__ bool poll_hit(const tray_hit* src, float2& ph) {     
 // hand at once; nothing was postponed, nothing mismatched, and the extra vote cost 3 %.  profiles/experiments/r2_relaxed_*.)
 template <bool TLAS, bool COUNT, int TRI_STRIDE, bool ANYHIT = false, bool FRAME = false, int MODE = 0>
 __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams P) {
+#if !TRAY_STK_PTX
     __shared__ uint2 s_stack[STACK_SMEM * BLOCK_THREADS];
+#endif
     __shared__ uint8_t s_lut[LUT_BYTES];          // child_order[oct_inv][hit byte] (see node_test_s)
     uint2 spill[STACK_SPILL];
     child_order_fill(s_lut, threadIdx.x, BLOCK_THREADS);
@@ -775,7 +783,19 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
     // (one register instead of a depth and a per-thread base address)
     constexpr uint32_t SP_STEP = BLOCK_THREADS * 8u, SP_SMEM_END = STACK_SMEM * SP_STEP, SP_END = (STACK_SMEM + STACK_SPILL) * SP_STEP;
     uint32_t sp = threadIdx.x * 8u;
-#define TRAY_STK(off) (*reinterpret_cast<uint2*>(reinterpret_cast<char*>(s_stack) + (off)))
+#if TRAY_STK_PTX
+    // the stack lives in a shared-memory array declared in PTX, so that its address is a plain CTA-local offset that ptxas keeps in a
+    // uniform register (STS.64 [R + UR]) — the address of a C++ __shared__ array goes through the generic->shared conversion, which
+    // on sm_90+ reads SR_CgaCtaId and rebuilds the shared window base (S2R + MOV + LEA + IADD) at EVERY push and pop: +2.3 % on C3,
+    // +1.2 % on C1 together with the late push (profiles/experiments/r2_push_late_ab.log)
+    uint32_t stk_base;
+    asm volatile(".shared .align 16 .b8 tray_stack_mem[%1];\n\tmov.u32 %0, tray_stack_mem;" : "=r"(stk_base) : "n"(STACK_SMEM * BLOCK_THREADS * 8));
+    auto stk_store = [&](uint32_t off, uint32_t x, uint32_t y) { asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(stk_base + off), "r"(x), "r"(y) : "memory"); };
+    auto stk_load = [&](uint32_t off) { uint2 e; asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(stk_base + off) : "memory"); return e; };
+#else
+    auto stk_store = [&](uint32_t off, uint32_t x, uint32_t y) { *reinterpret_cast<uint2*>(reinterpret_cast<char*>(s_stack) + off) = make_uint2(x, y); };
+    auto stk_load = [&](uint32_t off) { return *reinterpret_cast<uint2*>(reinterpret_cast<char*>(s_stack) + off); };
+#endif
     uint32_t tlas_sp = INVALID, bvh_off = 0;
     uint32_t ray_idx = 0;
     bool exhausted = false;                      // warp-uniform
@@ -788,7 +808,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
     bool units_done = false;
 
     auto push = [&](uint32_t x, uint32_t y) {
-        if (sp < SP_SMEM_END) TRAY_STK(sp) = make_uint2(x, y);
+        if (sp < SP_SMEM_END) stk_store(sp, x, y);
         else if (sp < SP_END) spill[sp / SP_STEP - STACK_SMEM] = make_uint2(x, y);
         else { atomicOr(P.overflow, 1u); return; }
         sp += SP_STEP;
@@ -832,7 +852,7 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
         } else {
             if (TLAS && sp == tlas_sp) { tlas_sp = INVALID; bvh_off = P.tlas_start; }
             sp -= SP_STEP;
-            const uint2 e = sp < SP_SMEM_END ? TRAY_STK(sp) : spill[sp / SP_STEP - STACK_SMEM];
+            const uint2 e = sp < SP_SMEM_END ? stk_load(sp) : spill[sp / SP_STEP - STACK_SMEM];
             if (e.y & 0xff000000u) { cur_x = e.x; cur_y = e.y; }
             else { tri_x = e.x; tri_y = e.y; cur_x = 0; cur_y = 0; }
         }
@@ -986,11 +1006,12 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
                 uint32_t slot;                                                                 // query.hlsl:358 + :370 in one lookup (see node_test_s)
                 asm("ld.shared.u8 %0, [%1];" : "=r"(slot) : "r"(r.lut_off + (hits_imask >> 24)));
                 cur_y = hits_imask ^ (0x01000000u << slot);                                    // :362
-                if (cur_y & 0xff000000u) push(cur_x, cur_y);                                   // :365-368
+                if (!TRAY_PUSH_LATE && (cur_y & 0xff000000u)) push(cur_x, cur_y);              // :365-368
                 const uint32_t rel = (uint32_t)__popc(hits_imask & ((1u << slot) - 1u));       // :371 (slot < 8: imask bits only)
                 const uint4* np = P.nodes + (size_t)(bvh_off + cur_x + rel) * 5u;              // :373, tlas:383
                 SC(const long long sc_a = clk_after(rel); sc_acc[1] += sc_a - sc_voted;)
                 const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+                if (TRAY_PUSH_LATE && (cur_y & 0xff000000u)) push(cur_x, cur_y);               // :365-368, in the shadow of the node fetch
                 SC(const long long sc_b = clk_after(n0.x ^ n1.x ^ n2.x ^ n3.x ^ n4.x); sc_acc[2] += sc_b - sc_a;)
                 TRAY_CNT(nodes);
                 uint32_t hitmask;                                                              // slot space (see node_test_s)
@@ -1091,7 +1112,6 @@ __global__ void __launch_bounds__(BLOCK_THREADS, TRAY_MIN_BLOCKS) trace_kernel(c
         }
     }
 #undef TRAY_CNT
-#undef TRAY_STK
 }
 
 // compact local order -> row-major frame (one thread per local work item)

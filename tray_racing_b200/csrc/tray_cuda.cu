@@ -88,7 +88,7 @@ struct tray_scene {
     uint64_t device_bytes = 0, l2_bytes = 0, l2_persist = 0;
     bool counting = false;
     uint32_t variant = 0;                    // TRAY_VARIANT_* (tray_cuda_scene_set_variant): the MODE 1 kernels
-    uint32_t refill_min = 4, tri_weight = 3, gen_min = 4;
+    uint32_t refill_min = 6, tri_weight = 3, gen_min = 4;
     bool overlap_default = false;            // TRAY_CUDA_OVERLAP=1: tray_cuda_render always takes the one-launch frame kernel
     bool pool = false;                       // pooled kernel (traverse_pool.cuh) or one-ray-per-lane kernel (traverse.cuh)
     uint32_t pool_refill_min = 8, pool_tri_weight = 1;
@@ -440,7 +440,7 @@ int scene_create_impl(const void* nodes, uint64_t n_nodes, const void* tris, uin
     if (!s) return fail(TRAY_ERR_ARG, "out of host memory");
     s->device = device; s->n_nodes = n_nodes; s->n_tris = n_tris; s->tri_stride = tri_stride;
     s->n_instances = n_instances; s->tlas_start = tlas_start; s->tlas = n_instances > 0;
-    s->refill_min = (uint32_t)env_int("TRAY_CUDA_REFILL_MIN", 4);
+    s->refill_min = (uint32_t)env_int("TRAY_CUDA_REFILL_MIN", 6);       // 6: +0.3 % (C3) ... +2 % (C1) over 4 with the r2 kernel (profiles/experiments/r2_refill_min_ab.log)
     s->force_exact = env_int("TRAY_CUDA_FORCE_EXACT", 0) != 0 || (built && built->force_exact);
     for (uint64_t i = 0; !built && i < n_nodes && !s->force_exact; i++) {
         const uint8_t* e = (const uint8_t*)nodes + i * 80 + 12;
