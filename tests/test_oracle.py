@@ -430,3 +430,27 @@ def test_new_variant_switches_touch_only_what_they_name(cornell):
     rel = np.abs(a["t"][both] - c["t"][both]) / np.abs(a["t"][both])
     assert (rel <= 1e-4).all() and (rel <= 1e-5).mean() > 0.9
     assert (a["prim"][both] == c["prim"][both]).mean() > 0.99
+
+
+def test_child_order_table_equals_the_octant_permutation():
+    """The lane kernel keeps hit inner children in SLOT space and picks the next one through child_order[oct_inv][hit byte]
+    (traverse.cuh, node test in slot space).  The reference permutes instead: child `slot` sets bit slot ^ oct_inv, firstbithigh
+    picks the highest bit, `slot = bit ^ oct_inv` undoes it (query.hlsl:256-262, 358, 370).  For every octant and every hit
+    byte both give the same child, and the remaining set keeps giving the same order."""
+    for oi in range(8):
+        for t in range(1, 256):
+            order_ref, order_tab = [], []
+            perm = 0
+            for j in range(8):
+                if (t >> j) & 1:
+                    perm |= 1 << (j ^ oi)
+            while perm:
+                off = perm.bit_length() - 1                  # firstbithigh
+                perm &= ~(1 << off)
+                order_ref.append(off ^ oi)                   # slot_index
+            rest = t
+            while rest:
+                best = max((j for j in range(8) if (rest >> j) & 1), key=lambda j: j ^ oi)    # child_order_fill
+                rest &= ~(1 << best)
+                order_tab.append(best)
+            assert order_ref == order_tab, (oi, t)
